@@ -1,0 +1,189 @@
+"""Weight-file tooling for the `weight.ggml` layout of the reference.
+
+Layout (reference: mobilevit/convert-tf-to-ggml.py:16-33, read back by mobilevit/main.cpp:872-942)::
+
+    repeat { int32 name_len; char name[name_len]; int32 n_dims; int32 dims[n_dims];  # TF order
+             float32 data[prod(dims)] }
+
+Tensor names are the TF variable paths of `TFMobileViTModel`.  The reference script
+needs TensorFlow and a download of apple/mobilevit-small; neither exists here, so this module writes
+random-init weights of the same architecture and names (numpy only).  No compute happens here.
+"""
+from __future__ import annotations
+
+import struct
+from collections import OrderedDict
+
+import numpy as np
+
+P = "tf_mobile_vi_t_model/mobilevit"
+
+# SURVEY.md 8(d) / App. A.  `stages` = transformer layers per ViT block, MobileNet stage counts are 1 and 3.
+VARIANTS = {
+    "s": dict(hidden=(144, 192, 240), neck=(16, 32, 64, 96, 128, 160, 640), expand=4.0),
+    "xs": dict(hidden=(96, 120, 144), neck=(16, 32, 48, 64, 80, 96, 384), expand=4.0),
+    "xxs": dict(hidden=(64, 80, 96), neck=(16, 16, 24, 48, 64, 80, 320), expand=2.0),
+}
+VIT_STAGES = (2, 4, 3)
+MLP_RATIO = 2.0
+NUM_HEADS = 4
+
+
+def make_divisible(value: float, divisor: int = 8) -> int:
+    new_value = max(divisor, int(value + divisor / 2) // divisor * divisor)
+    if new_value < 0.9 * value:
+        new_value += divisor
+    return int(new_value)
+
+
+def _conv(rng, out, path, kh, kw, ic, oc, norm=True, depthwise=False):
+    # conv N(0, 2/fan_in); BN gamma U(.75,1.25), beta N(0,.1^2), mean N(0,.1^2), var U(.75,1.25)
+    fan_in = kh * kw * (1 if depthwise else ic)
+    shape = (kh, kw, 1, oc) if depthwise else (kh, kw, ic, oc)
+    out[f"{path}/convolution/kernel:0"] = rng.normal(0.0, np.sqrt(2.0 / fan_in), shape).astype(np.float32)
+    if norm:
+        out[f"{path}/normalization/gamma:0"] = rng.uniform(0.75, 1.25, (oc,)).astype(np.float32)
+        out[f"{path}/normalization/beta:0"] = rng.normal(0.0, 0.1, (oc,)).astype(np.float32)
+        out[f"{path}/normalization/moving_mean:0"] = rng.normal(0.0, 0.1, (oc,)).astype(np.float32)
+        out[f"{path}/normalization/moving_variance:0"] = rng.uniform(0.75, 1.25, (oc,)).astype(np.float32)
+
+
+def _inverted_residual(rng, out, path, cin, cout, expand):
+    e = make_divisible(int(round(cin * expand)), 8)
+    _conv(rng, out, f"{path}/expand_1x1", 1, 1, cin, e)
+    _conv(rng, out, f"{path}/conv_3x3", 3, 3, e, e, depthwise=True)
+    _conv(rng, out, f"{path}/reduce_1x1", 1, 1, e, cout)
+
+
+def _dense(rng, out, path, cin, cout):
+    out[f"{path}/kernel:0"] = rng.normal(0.0, np.sqrt(1.0 / cin), (cin, cout)).astype(np.float32)
+    out[f"{path}/bias:0"] = rng.normal(0.0, 0.02, (cout,)).astype(np.float32)
+
+
+def _ln(rng, out, path, c):
+    out[f"{path}/gamma:0"] = rng.uniform(0.75, 1.25, (c,)).astype(np.float32)
+    out[f"{path}/beta:0"] = rng.normal(0.0, 0.1, (c,)).astype(np.float32)
+
+
+def make_synthetic_weights(variant: str = "s", seed: int = 1234) -> "OrderedDict[str, np.ndarray]":
+    """Random-init MobileViT weights under the reference's tensor names (313 tensors for every variant)."""
+    cfg = VARIANTS[variant]
+    neck, hidden, expand = cfg["neck"], cfg["hidden"], cfg["expand"]
+    rng = np.random.default_rng(seed)
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    _conv(rng, out, f"{P}/conv_stem", 3, 3, 3, neck[0])
+    # layer.0: one inverted residual, stride 1; layer.1: three, first stride 2 (main.cpp:334-391)
+    _inverted_residual(rng, out, f"{P}/encoder/layer.0/layer.0", neck[0], neck[1], expand)
+    cin = neck[1]
+    for i in range(3):
+        _inverted_residual(rng, out, f"{P}/encoder/layer.1/layer.{i}", cin, neck[2], expand)
+        cin = neck[2]
+    for v in range(3):  # main.cpp:393-503
+        base = f"{P}/encoder/layer.{v + 2}"
+        cin, cout, d = neck[2 + v], neck[3 + v], hidden[v]
+        _inverted_residual(rng, out, f"{base}/downsampling_layer", cin, cout, expand)
+        _conv(rng, out, f"{base}/conv_kxk", 3, 3, cout, cout)
+        _conv(rng, out, f"{base}/conv_1x1", 1, 1, cout, d, norm=False)
+        f = int(d * MLP_RATIO)
+        for j in range(VIT_STAGES[v]):
+            tb = f"{base}/transformer/layer.{j}"
+            _dense(rng, out, f"{tb}/attention/attention/query", d, d)
+            _dense(rng, out, f"{tb}/attention/attention/key", d, d)
+            _dense(rng, out, f"{tb}/attention/attention/value", d, d)
+            _dense(rng, out, f"{tb}/attention/output/dense", d, d)
+            _dense(rng, out, f"{tb}/intermediate/dense", d, f)
+            _dense(rng, out, f"{tb}/output/dense", f, d)
+            _ln(rng, out, f"{tb}/layernorm_before", d)
+            _ln(rng, out, f"{tb}/layernorm_after", d)
+        _ln(rng, out, f"{base}/layernorm", d)
+        _conv(rng, out, f"{base}/conv_projection", 1, 1, d, cout)
+        _conv(rng, out, f"{base}/fusion", 3, 3, 2 * cout, cout)
+    _conv(rng, out, f"{P}/conv_1x1_exp", 1, 1, neck[5], neck[6])
+    return out
+
+
+def write_weight_file(path: str, tensors: "OrderedDict[str, np.ndarray]") -> int:
+    """Write tensors in the convert-tf-to-ggml.py record layout.  Returns the number of floats written."""
+    total = 0
+    with open(path, "wb") as f:
+        for name, arr in tensors.items():
+            arr = np.ascontiguousarray(arr, dtype=np.float32)
+            nb = name.encode("utf-8")
+            f.write(struct.pack("i", len(nb)))
+            f.write(nb)
+            f.write(struct.pack("i", arr.ndim))
+            for d in arr.shape:
+                f.write(struct.pack("i", int(d)))
+            f.write(arr.tobytes())
+            total += arr.size
+    return total
+
+
+def read_weight_file(path: str) -> "OrderedDict[str, np.ndarray]":
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    with open(path, "rb") as f:
+        while True:
+            head = f.read(4)
+            if len(head) < 4:
+                break
+            (n,) = struct.unpack("i", head)
+            name = f.read(n).decode("utf-8")
+            (nd,) = struct.unpack("i", f.read(4))
+            dims = struct.unpack("i" * nd, f.read(4 * nd))
+            cnt = int(np.prod(dims))
+            out[name] = np.frombuffer(f.read(4 * cnt), dtype=np.float32).reshape(dims).copy()
+    return out
+
+
+# ---- Hugging Face torch MobileViTModel <-> file names, used by the golden generator ----
+
+def hf_config_kwargs(variant: str) -> dict:
+    cfg = VARIANTS[variant]
+    return dict(hidden_sizes=list(cfg["hidden"]), neck_hidden_sizes=list(cfg["neck"]), expand_ratio=cfg["expand"],
+                num_attention_heads=NUM_HEADS, mlp_ratio=MLP_RATIO, hidden_dropout_prob=0.0,
+                attention_probs_dropout_prob=0.0, classifier_dropout_prob=0.0)
+
+
+def to_hf_state_dict(tensors: "OrderedDict[str, np.ndarray]") -> dict:
+    """Map file tensors to torch MobileViTModel state-dict entries (numpy arrays)."""
+    sd = {}
+    for name, arr in tensors.items():
+        assert name.startswith(P + "/") and name.endswith(":0")
+        parts = name[len(P) + 1:-2].split("/")
+        leaf = parts[-1]
+        if parts[-2] == "convolution":
+            key = ".".join(parts[:-2]) + ".convolution.weight"
+            sd[key] = np.ascontiguousarray(arr.transpose(3, 2, 0, 1))  # (KH,KW,IC,OC) -> (OC,IC,KH,KW)
+        elif parts[-2] == "normalization":
+            m = {"gamma": "weight", "beta": "bias", "moving_mean": "running_mean", "moving_variance": "running_var"}
+            sd[".".join(parts[:-2]) + ".normalization." + m[leaf]] = arr
+        elif leaf == "kernel":
+            sd[".".join(parts[:-1]) + ".weight"] = np.ascontiguousarray(arr.T)
+        elif leaf == "bias":
+            sd[".".join(parts[:-1]) + ".bias"] = arr
+        elif leaf == "gamma":
+            sd[".".join(parts[:-1]) + ".weight"] = arr
+        elif leaf == "beta":
+            sd[".".join(parts[:-1]) + ".bias"] = arr
+        else:
+            raise KeyError(name)
+    return sd
+
+
+def synthetic_images(n: int, h: int = 256, w: int = 256, seed: int = 7) -> np.ndarray:
+    """image 0 = the reference's own test pattern (main.cpp:680-688); the rest are
+    structured (per-channel offset + sinusoid + 0.15 U(0,1) noise, clamped to [0,1]).  Returns [n,h,w,3] f32."""
+    rng = np.random.default_rng(seed)
+    imgs = np.empty((n, h, w, 3), dtype=np.float32)
+    idx = np.arange(h * w * 3, dtype=np.int64)
+    imgs[0] = ((idx % 256) / 255.0).astype(np.float32).reshape(h, w, 3)
+    yy, xx = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    for i in range(1, n):
+        for c in range(3):
+            off = rng.uniform(0.2, 0.8)
+            fx, fy = rng.uniform(0.5, 6.0, 2) * 2 * np.pi / np.array([w, h])
+            ph = rng.uniform(0, 2 * np.pi)
+            amp = rng.uniform(0.1, 0.4)
+            img = off + amp * np.sin(fx * xx + fy * yy + ph) + 0.15 * rng.uniform(0, 1, (h, w))
+            imgs[i, :, :, c] = np.clip(img, 0.0, 1.0)
+    return imgs

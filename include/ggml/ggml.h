@@ -1,0 +1,251 @@
+/*
+ * ggml.h -- the drop-in boundary of libggml_b200.
+ *
+ * This header declares the subset of the ggml public C API that the reference programs call
+ * (/root/reference/mobilevit/main.cpp includes "ggml/ggml.h" at :1,
+ *  /root/reference/rnn_text_gen/rnn_text_generation.cpp includes <ggml.h> at :1).
+ * Upstream ggml is NOT vendored by the reference (mobilevit/README.md:10-14 tells the user to
+ * `git clone` it), so the signatures below restate upstream ggml's early-2024 public API as the two
+ * programs use it.  Every symbol cites the reference call site(s) it serves.
+ *
+ * Behind this surface there is no CPU interpreter: graph construction only records nodes;
+ * ggml_graph_compute_with_ctx() lowers the recorded graph to hand-written sm_100a CUDA kernels
+ * (see DESIGN.md).  If no CUDA device is usable the compute call aborts -- there is no CPU fallback.
+ *
+ * Plain C ABI: extern "C", pointers and sizes only.
+ */
+#ifndef GGML_B200_GGML_H
+#define GGML_B200_GGML_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGML_MAX_DIMS       4
+#define GGML_MAX_SRC        4
+#define GGML_MAX_NAME       64
+#define GGML_MAX_OP_PARAMS  64
+#define GGML_DEFAULT_GRAPH_SIZE 2048   /* upstream default; the reference graph is ~1.4k nodes */
+#define GGML_B200_STATIC_GRAPH_NODES 512 /* capacity of a by-value ggml_cgraph (rnn.cpp:149,289) */
+
+/* main.cpp:729,730,981 -- abort-on-failure convention (prints file:line, abort()). */
+#define GGML_ASSERT(x)                                                                   \
+    do {                                                                                 \
+        if (!(x)) {                                                                      \
+            fprintf(stderr, "GGML_ASSERT: %s:%d: %s\n", __FILE__, __LINE__, #x);         \
+            abort();                                                                     \
+        }                                                                                \
+    } while (0)
+
+typedef uint16_t ggml_fp16_t; /* main.cpp:929 */
+
+enum ggml_type {            /* main.cpp:612,907-916; rnn.cpp:42,284 */
+    GGML_TYPE_F32 = 0,
+    GGML_TYPE_F16 = 1,
+    GGML_TYPE_I32 = 26,     /* same numeric value as upstream */
+    GGML_TYPE_COUNT
+};
+
+enum ggml_op {
+    GGML_OP_NONE = 0,
+    GGML_OP_ADD, GGML_OP_SUB, GGML_OP_MUL, GGML_OP_DIV,
+    GGML_OP_SQRT, GGML_OP_SILU, GGML_OP_TANH,
+    GGML_OP_NORM, GGML_OP_SOFT_MAX,
+    GGML_OP_MUL_MAT,
+    GGML_OP_REPEAT, GGML_OP_CONCAT, GGML_OP_GET_ROWS,
+    GGML_OP_CONT,
+    GGML_OP_RESHAPE, GGML_OP_VIEW, GGML_OP_PERMUTE, GGML_OP_TRANSPOSE,
+    GGML_OP_CONV_2D, GGML_OP_CONV_DEPTHWISE_2D,
+    GGML_OP_POOL_MEAN_HW,   /* build addition: global average pool */
+    GGML_OP_COUNT
+};
+
+enum ggml_tensor_flag { GGML_TENSOR_FLAG_INPUT = 1, GGML_TENSOR_FLAG_OUTPUT = 2, GGML_TENSOR_FLAG_PARAM = 4 };
+
+struct ggml_context;        /* opaque arena (main.cpp:607,658) */
+
+/* Public tensor record.  The reference reads type/ne (main.cpp:724-726,780-783,977-979), writes nb
+ * (rnn.cpp:212,226), reads/writes data (main.cpp:931,934; rnn.cpp:124-147,306-307) and reads n_dims
+ * (rnn.cpp:35), so those fields keep upstream's names and meaning.  `data` is a HOST pointer: it is
+ * allocated eagerly for leaf tensors; for op results it is NULL until a compute call has produced the
+ * tensor and it was a graph output (or small enough to be mirrored, see DESIGN.md "host shadows"). */
+struct ggml_tensor {
+    enum ggml_type type;
+    int            n_dims;
+    int64_t        ne[GGML_MAX_DIMS];
+    size_t         nb[GGML_MAX_DIMS];
+    enum ggml_op   op;
+    int32_t        op_params[GGML_MAX_OP_PARAMS / sizeof(int32_t)];
+    int32_t        flags;
+    struct ggml_tensor * src[GGML_MAX_SRC];
+    struct ggml_tensor * view_src;
+    size_t         view_offs;
+    void *         data;
+    char           name[GGML_MAX_NAME];
+    void *         extra;   /* libggml_b200 private */
+    struct ggml_context * ctx; /* owning context (libggml_b200 private) */
+};
+
+/* main.cpp:608,636; rnn.cpp:149 (`ggml_cgraph gf = {}` on the stack) and :289 (returned by value):
+ * the struct must be complete and value-copyable. */
+struct ggml_cgraph {
+    int size;
+    int n_nodes;
+    int n_leafs;
+    struct ggml_tensor ** nodes;
+    struct ggml_tensor ** leafs;
+    void * plan;            /* libggml_b200 private: compiled device plan, built lazily */
+    struct ggml_tensor * static_nodes[GGML_B200_STATIC_GRAPH_NODES];
+    struct ggml_tensor * static_leafs[GGML_B200_STATIC_GRAPH_NODES];
+};
+
+struct ggml_init_params {   /* main.cpp:605,656; rnn.cpp:98-102,271-275 */
+    size_t mem_size;
+    void * mem_buffer;
+    bool   no_alloc;
+};
+
+/* ---- context (main.cpp:607,658,699) ---- */
+struct ggml_context * ggml_init(struct ggml_init_params params);
+void                  ggml_free(struct ggml_context * ctx);
+size_t                ggml_used_mem(const struct ggml_context * ctx);
+
+/* ---- timers (main.cpp:639-641,651,689-698) ---- */
+void    ggml_time_init(void);
+int64_t ggml_time_ms(void);
+int64_t ggml_time_us(void);
+
+/* ---- tensor creation (main.cpp:612,833,907-916,1076; rnn.cpp:42,108-115,244,283-284) ---- */
+struct ggml_tensor * ggml_new_tensor_1d(struct ggml_context * ctx, enum ggml_type type, int64_t ne0);
+struct ggml_tensor * ggml_new_tensor_2d(struct ggml_context * ctx, enum ggml_type type, int64_t ne0, int64_t ne1);
+struct ggml_tensor * ggml_new_tensor_3d(struct ggml_context * ctx, enum ggml_type type, int64_t ne0, int64_t ne1, int64_t ne2);
+struct ggml_tensor * ggml_new_tensor_4d(struct ggml_context * ctx, enum ggml_type type, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3);
+struct ggml_tensor * ggml_new_f32(struct ggml_context * ctx, float value);
+struct ggml_tensor * ggml_set_name(struct ggml_tensor * tensor, const char * name);   /* main.cpp:614 */
+void                 ggml_set_input(struct ggml_tensor * tensor);                    /* main.cpp:615 */
+void                 ggml_set_output(struct ggml_tensor * tensor);
+void                 ggml_set_param(struct ggml_context * ctx, struct ggml_tensor * tensor); /* rnn.cpp:150-152,286-287 */
+
+/* ---- accessors (main.cpp:627,931-934,952,1230; rnn.cpp:27,44,75,303) ---- */
+void *  ggml_get_data(const struct ggml_tensor * tensor);
+float * ggml_get_data_f32(const struct ggml_tensor * tensor);
+size_t  ggml_nbytes(const struct ggml_tensor * tensor);
+int64_t ggml_nelements(const struct ggml_tensor * tensor);
+int     ggml_n_dims(const struct ggml_tensor * tensor);
+size_t  ggml_type_size(enum ggml_type type);
+bool    ggml_is_contiguous(const struct ggml_tensor * tensor);
+void    ggml_set_i32_1d(const struct ggml_tensor * tensor, int i, int32_t value);
+int32_t ggml_get_i32_1d(const struct ggml_tensor * tensor, int i);
+void    ggml_set_f32_1d(const struct ggml_tensor * tensor, int i, float value);
+float   ggml_get_f32_1d(const struct ggml_tensor * tensor, int i);
+
+/* ---- fp16 (main.cpp:930) ---- */
+float       ggml_fp16_to_fp32(ggml_fp16_t x);
+ggml_fp16_t ggml_fp32_to_fp16(float x);
+void        ggml_fp16_to_fp32_row(const ggml_fp16_t * x, float * y, int n);
+void        ggml_fp32_to_fp16_row(const float * x, ggml_fp16_t * y, int n);
+
+/* ---- binary ops with broadcast of b (main.cpp:810,821,826,837,842,867,1002-1018,1073,1111,1165) ---- */
+struct ggml_tensor * ggml_add(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+struct ggml_tensor * ggml_sub(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+struct ggml_tensor * ggml_mul(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+struct ggml_tensor * ggml_div(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+
+/* ---- unary ops (main.cpp:824,849,1079,1148; rnn.cpp:53,236) ---- */
+struct ggml_tensor * ggml_sqrt(struct ggml_context * ctx, struct ggml_tensor * a);
+struct ggml_tensor * ggml_silu(struct ggml_context * ctx, struct ggml_tensor * a);
+struct ggml_tensor * ggml_tanh(struct ggml_context * ctx, struct ggml_tensor * a);
+struct ggml_tensor * ggml_soft_max(struct ggml_context * ctx, struct ggml_tensor * a);       /* over ne0 */
+struct ggml_tensor * ggml_norm(struct ggml_context * ctx, struct ggml_tensor * a, float eps); /* over ne0, no affine (main.cpp:1006,1118,1196) */
+
+/* ---- matmul (main.cpp:1022,1039,1056,1075,1082,1095,1134,1151; rnn.cpp:204,219,253) ----
+ * a: [K, M, b2, b3]   b: [K, N, c2, c3]   result F32 [M, N, c2, c3]; a is broadcast over dims 2,3.
+ * If a is F16, b is rounded to F16 first and products accumulate in f32 (upstream vec_dot_f16). */
+struct ggml_tensor * ggml_mul_mat(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+
+/* ---- data movement / views (main.cpp:721-768,790-805,975-986,1009-1093,1136,1152,1219; rnn.cpp:47,129-143,200-250) ---- */
+struct ggml_tensor * ggml_repeat(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+struct ggml_tensor * ggml_concat(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b); /* 2-arg form: along dim 2 */
+struct ggml_tensor * ggml_get_rows(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b);
+struct ggml_tensor * ggml_cont(struct ggml_context * ctx, struct ggml_tensor * a);
+struct ggml_tensor * ggml_cont_4d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3);
+struct ggml_tensor * ggml_reshape_2d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1);
+struct ggml_tensor * ggml_reshape_3d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1, int64_t ne2);
+struct ggml_tensor * ggml_reshape_4d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3);
+struct ggml_tensor * ggml_permute(struct ggml_context * ctx, struct ggml_tensor * a, int axis0, int axis1, int axis2, int axis3); /* result.ne[axis_i] = a.ne[i] */
+struct ggml_tensor * ggml_transpose(struct ggml_context * ctx, struct ggml_tensor * a);
+
+/* ---- convolution (main.cpp:788,798) ----
+ * kernel a: [KW, KH, IC, OC] F16 (depthwise: [KW, KH, 1, C]); input b: [W, H, C, N] F32; result F32
+ * [OW, OH, OC, N].  Numerics follow upstream im2col(F16)+mul_mat: activations are rounded to F16,
+ * products accumulate in f32. */
+struct ggml_tensor * ggml_conv_2d(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b,
+                                  int s0, int s1, int p0, int p1, int d0, int d1);
+struct ggml_tensor * ggml_conv_depthwise_2d(struct ggml_context * ctx, struct ggml_tensor * a, struct ggml_tensor * b,
+                                            int s0, int s1, int p0, int p1, int d0, int d1);
+
+/* ---- graph (main.cpp:608,636,640; rnn.cpp:149,154-158,289,311) ---- */
+struct ggml_cgraph * ggml_new_graph(struct ggml_context * ctx);
+void                 ggml_build_forward_expand(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor);
+struct ggml_cgraph   ggml_build_forward(struct ggml_tensor * tensor);    /* old by-value API, rnn.cpp:289 */
+void                 ggml_graph_compute_with_ctx(struct ggml_context * ctx, struct ggml_cgraph * cgraph, int n_threads);
+void                 ggml_graph_release_plan(struct ggml_cgraph * cgraph); /* frees the cached device plan */
+
+/* =====================================================================================================
+ * libggml_b200 extensions (not in upstream ggml).  All optional: an unmodified caller never needs them.
+ * ===================================================================================================== */
+
+/* build addition: mean over ne0 x ne1 -> [1,1,C,N] (the "pooled logits"). */
+struct ggml_tensor * ggml_b200_pool_mean_hw(struct ggml_context * ctx, struct ggml_tensor * a);
+
+/* Execution mode of ggml_graph_compute_with_ctx:
+ *   GGML_B200_MODE_FAST  (default) pattern-matched fused plan (NHWC f16 activations, tcgen05 GEMMs);
+ *                        falls back (with a one-line notice) to EXACT for graphs it cannot match.
+ *   GGML_B200_MODE_EXACT one simple f32-accurate CUDA kernel per ggml node, ggml layouts and rounding
+ *                        points -- the "TF32/f32 validation mode" of BASELINE.json's north_star.
+ * Also settable with the environment variable GGML_B200_MODE=fast|exact. */
+enum ggml_b200_mode { GGML_B200_MODE_FAST = 0, GGML_B200_MODE_EXACT = 1 };
+void ggml_b200_set_mode(enum ggml_b200_mode mode);
+int  ggml_b200_get_mode(void);
+
+/* Device selection and stream.  `stream` is a cudaStream_t passed as void* (NULL = the library's own). */
+int    ggml_b200_device_count(void);
+void   ggml_b200_set_device(int device);
+void   ggml_b200_set_stream(void * stream);
+void * ggml_b200_get_stream(void);
+void   ggml_b200_synchronize(void);
+
+/* Keep a leaf / an output on the device: bind a leaf to caller-owned device memory (skips the H2D copy
+ * in compute), or ask where a graph output lives after compute (skips nothing; the D2H copy is skipped
+ * with ggml_b200_graph_set_download(false)). */
+void   ggml_b200_tensor_set_device_data(struct ggml_tensor * leaf, void * device_ptr);
+void * ggml_b200_tensor_get_device_data(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor);
+void   ggml_b200_graph_set_transfers(struct ggml_cgraph * cgraph, bool upload_inputs, bool download_outputs);
+
+/* Introspection of the compiled plan (bench.py's gpu_launches, DESIGN.md's memory-planner numbers). */
+struct ggml_b200_plan_stats {
+    int     mode;              /* enum ggml_b200_mode actually used */
+    int     n_graph_nodes;     /* ggml nodes in the graph */
+    int     n_launches;        /* kernel launches per compute */
+    int     n_folded;          /* nodes constant-folded at plan time */
+    int64_t arena_bytes;       /* device arena after liveness planning */
+    int64_t naive_bytes;       /* sum of all intermediate tensors (what ggml's arena would need) */
+    int64_t weight_bytes;      /* device-resident constants */
+    int     used_cuda_graph;
+};
+void ggml_b200_graph_plan_stats(struct ggml_cgraph * cgraph, struct ggml_b200_plan_stats * out);
+/* Build (or fetch) the plan without running it. */
+void ggml_b200_graph_prepare(struct ggml_context * ctx, struct ggml_cgraph * cgraph);
+
+const char * ggml_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_GGML_H */
