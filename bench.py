@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: MobileViT-S images/sec at batch 256 (256x256) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variant s] [--batch 256] [--hw 256]
+
+A "step" is one forward pass of the hot path (mobilevit_model::extract_features, main.cpp:604-646, generalised to a
+batch) over one batch of synthetic images.  One process per GPU (torchrun for N>1); the batch shards as independent
+per-GPU sub-batches with no data-path collective (weak scaling: `--batch` images per GPU); torch.distributed is used
+only for the barrier and the max-over-ranks of the timings.
+
+  value         device-resident: inputs already in HBM, outputs stay in HBM; CUDA events on the launching stream
+  e2e           through the host API (write the pinned input buffer, mvit_compute, read the host outputs):
+                H2D of the step's images + forward + D2H of features and pooled logits, every step
+  roofline      dominant kernel of the step: algorithmic FLOPs (or bytes) / its CUDA-event time / measured peak
+  cpu_baseline  the CPU oracle (a port of the reference's ggml algorithm; upstream ggml itself is not available) on a
+                bounded sample of the same workload, all host cores
+
+`--impl reference` times the oracle port alone (rank 0 only), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = {"s": 4.000, "xs": 2.051, "xxs": 0.814}  # at 256x256, SURVEY.md 8(d)
+ACT_MB_PER_IMAGE = {"s": 73.1, "xs": 57.8, "xxs": 25.3}     # layer-wise f16 activation traffic, SURVEY.md 8(d)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops_burst": float(p["bf16_tflops"]),
+                "tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(weight_path: str, variant: str, hw: int, n_images: int, threads: int):
+    """images/s of the CPU oracle port on a bounded sample (test infrastructure used as the reported baseline)."""
+    from ggml_experiments_b200 import weights as W
+    from oracle import binding
+    m = binding.OracleModel(weight_path)
+    imgs = W.synthetic_images(n_images, hw, hw, seed=7)
+    _, _, secs = m.forward(imgs, 0, threads, return_time=True)
+    return n_images / secs, secs
+
+
+def run_reference(args, weight_path: str):
+    from oracle import binding
+    binding.build()
+    cores = binding.lib().mvo_max_threads()
+    sample = min(args.batch, max(8, cores))
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_oracle_rate(weight_path, args.variant, args.hw, min(sample, cores), cores)
+    times = []
+    for _ in range(args.steps):
+        rate, secs = cpu_oracle_rate(weight_path, args.variant, args.hw, sample, cores)
+        times.append(secs)
+    tot = sum(times)
+    value = sample * args.steps / tot
+    desc = f"{sample} of {args.batch} images per step, batch-1 graphs looped over {cores} host threads"
+    return {
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 conv operands / f32 accumulate, f32 dense (ggml CPU semantics)",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
+                         "note": "CPU oracle restatement of the reference's ggml algorithm; upstream ggml is not vendored"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def metric_name(args):
+    return f"MobileViT-{args.variant.upper()} images/sec at batch {args.batch}"
+
+
+def workload_config(args):
+    return {"workload": f"MobileViT-{args.variant.upper()} forward (extract_features), conv weights f16, {args.hw}x{args.hw} synthetic images, "
+                        f"random-init weights in convert-tf-to-ggml layout",
+            "variant": args.variant, "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "image": args.hw,
+            "parallelism": f"independent sub-batches x{args.gpus} (no collective)",
+            "l2": "inputs larger than L2: %.0f MB of f32 images per step per GPU" % (args.batch * args.hw * args.hw * 12 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="s", choices=["s", "xs", "xxs"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--mode", default=os.environ.get("GGML_B200_MODE", "fast"), choices=["fast", "exact"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from ggml_experiments_b200 import weights as W
+    tmpdir = tempfile.mkdtemp(prefix=f"mvit_bench_r{rank}_")
+    weight_path = os.path.join(tmpdir, "weight.ggml")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        W.write_weight_file(weight_path, W.make_synthetic_weights(args.variant, seed=1234))
+        print(json.dumps(run_reference(args, weight_path)), flush=True)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ggml_experiments_b200 as G
+    from ggml_experiments_b200 import mobilevit as MV
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = G.lib_ggml()
+    L.ggml_b200_set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    L.ggml_b200_set_stream(ctypes_void(stream.cuda_stream))
+    MV.set_mode(MV.FAST if args.mode == "fast" else MV.EXACT)
+
+    W.write_weight_file(weight_path, W.make_synthetic_weights(args.variant, seed=1234))
+    model = G.MobileViT(weight_path)
+    n, h, w = args.batch, args.hw, args.hw
+    model.prepare(n, h, w)
+    info = model.plan_info(n, h, w)
+
+    # synthetic inputs, written in place into the library's pinned input buffer (main.cpp:627-634 flow)
+    host_in = model.host_input(n, h, w)
+    base = W.synthetic_images(min(n, 16), h, w, seed=7 + rank)
+    for i in range(n):
+        host_in[i] = base[i % base.shape[0]]
+    feat, pooled = model.compute(n, h, w)  # first full pass: H2D + forward + D2H (also warms everything up)
+    pooled0 = pooled.copy()
+    assert np.isfinite(feat).all()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------------
+    for _ in range(args.warmup):
+        model.forward_device(n, h, w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        model.forward_device(n, h, w)
+    ev1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop()
+    value = args.batch * world * args.steps / (dev_ms / 1e3)
+
+    # ---- end to end through the host API ("e2e") ------------------------------------------------------------
+    for _ in range(2):
+        model.compute(n, h, w)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        f, p = model.compute(n, h, w)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = args.batch * world * args.steps / e2e_s
+    assert np.array_equal(p, pooled0), "replayed forward is not deterministic"
+    h2d = n * h * w * 3 * 4
+    d2h = int(f.nbytes + p.nbytes)
+
+    # ---- per-kernel roofline (rank 0) -----------------------------------------------------------------------
+    peaks = load_peaks()
+    roofline, kernels = None, []
+    if rank == 0:
+        prof = model.profile(n, h, w, reps=3)
+        agg = {}
+        for r in prof:
+            a = agg.setdefault(r["kernel"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["launches"] += 1
+        tot_ms = sum(a["ms"] for a in agg.values()) or 1.0
+        ridge = peaks["tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            ai = a["flops"] / a["bytes"] if a["bytes"] else 0.0
+            bound = "tensor" if ai > ridge else "hbm"
+            ach = (a["flops"] / (a["ms"] * 1e-3) / 1e12) if bound == "tensor" else (a["bytes"] / (a["ms"] * 1e-3) / 1e9)
+            peak = peaks["tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"]
+            kernels.append({"kernel": k, "launches": a["launches"], "ms_per_step": round(a["ms"], 4), "share": round(a["ms"] / tot_ms, 4),
+                            "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                            "frac": round(ach / peak, 4), "gflop": round(a["flops"] / 1e9, 3), "mbytes": round(a["bytes"] / 1e6, 2)})
+        if kernels:
+            d = kernels[0]
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as tf:
+                    traffic = json.load(tf).get(d["kernel"])
+            except Exception:
+                pass
+            roofline = {"kernel": d["kernel"], "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                        "frac": d["frac"], "traffic": traffic, "share_of_step": d["share"], "launches_per_step": d["launches"],
+                        "peak_source": peaks["source"] + (" sustained" if d["bound"] == "tensor" else " copy bandwidth")}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding
+        binding.build()
+        cores = binding.lib().mvo_max_threads()
+        per_img_s = {"s": 1.1, "xs": 0.6, "xxs": 0.3}[args.variant] * (args.hw / 256.0) ** 2
+        sample = args.cpu_sample or int(min(args.batch, max(cores, min(4 * cores, 15.0 * cores / per_img_s))))
+        rate, secs = cpu_oracle_rate(weight_path, args.variant, args.hw, sample, cores)
+        rate1, secs1 = cpu_oracle_rate(weight_path, args.variant, args.hw, 2, 1)
+        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} of {args.batch} images, batch-1 graphs looped over {cores} threads, {secs:.1f} s",
+               "single_thread_images_per_s": rate1,
+               "note": "CPU oracle restatement of the reference's ggml algorithm (upstream ggml is not vendored); the reference itself runs 1 thread (main.cpp:640)"}
+
+    if rank == 0:
+        gf = GFLOP_PER_IMAGE.get(args.variant, 0.0) * (args.hw / 256.0) ** 2
+        per_gpu = value / world
+        out = {
+            "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ggml conv rounding points), f32 residual stream",
+            "data": "synthetic", "config": dict(workload_config(args), mode=("fast" if info["mode"] == 0 else "exact")),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": info["launches"] * args.steps,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "model_roofline": {"gflop_per_image": gf, "tflops_achieved_per_gpu": per_gpu * gf / 1e3,
+                               "frac_of_tensor_peak": per_gpu * gf / 1e3 / peaks["tflops_sustained"],
+                               "layerwise_hbm_bound_images_per_s": peaks["hbm_gbs"] * 1e3 / ACT_MB_PER_IMAGE.get(args.variant, 1e9) / (args.hw / 256.0) ** 2,
+                               "peaks": peaks},
+            "kernels": kernels,
+            "plan": info,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def ctypes_void(x):
+    import ctypes
+    return ctypes.c_void_p(x)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,78 @@
+"""In-tree build of the native libraries (nvcc, sm_100a only).
+
+    python -m ggml_experiments_b200.build        # or: python ggml-experiments_b200/build.py
+
+Outputs (git-ignored, shipped to the GPU box by gpurun):
+    _build/libggml_b200.so      the drop-in ggml boundary + CUDA kernels   (include/ggml/ggml.h)
+    _build/libmobilevit_b200.so the host MobileViT program + its C ABI     (include/mobilevit_b200.h)
+    _build/mobilevit_cli        the reference's main() equivalent
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(HERE, "_build")
+INC = os.path.join(ROOT, "include")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-I" + INC,
+          "-I" + os.path.join(HERE, "csrc")]
+
+LIB_SOURCES = ["csrc/ggml_b200.cpp", "csrc/plan.cpp", "csrc/exec_exact.cu", "csrc/fuse.cpp", "csrc/fast_kernels.cu",
+               "csrc/gemm_tcgen05.cu", "csrc/debug_api.cu"]
+HOST_SOURCES = ["host/mobilevit.cpp"]
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _all_deps() -> list[str]:
+    deps = []
+    for base in (os.path.join(HERE, "csrc"), os.path.join(HERE, "host"), os.path.join(INC), os.path.join(INC, "ggml")):
+        for fn in os.listdir(base):
+            if fn.endswith((".h", ".cuh", ".cu", ".cpp")):
+                deps.append(os.path.join(base, fn))
+    return deps
+
+
+def _run(cmd: list[str]) -> None:
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+
+
+def build(force: bool = False, verbose_ptxas: bool = False) -> dict:
+    os.makedirs(OUT, exist_ok=True)
+    deps = _all_deps()
+    lib = os.path.join(OUT, "libggml_b200.so")
+    host = os.path.join(OUT, "libmobilevit_b200.so")
+    cli = os.path.join(OUT, "mobilevit_cli")
+    srcs = [os.path.join(HERE, s) for s in LIB_SOURCES if os.path.exists(os.path.join(HERE, s))]
+    if force or _newer(lib, deps):
+        objs = []
+        for s in srcs:  # one object per TU so an edit recompiles only that file
+            o = os.path.join(OUT, os.path.basename(s) + ".o")
+            if force or _newer(o, [s] + [d for d in deps if d.endswith((".h", ".cuh"))]):
+                extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+                _run([NVCC, *ARCH, *COMMON, *extra, "-c", s, "-o", o])
+            objs.append(o)
+        _run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-lcudart"])
+    if force or _newer(host, deps + [lib]):
+        _run([NVCC, *ARCH, *COMMON, "-shared", "-o", host, *[os.path.join(HERE, s) for s in HOST_SOURCES],
+              "-L" + OUT, "-lggml_b200", "-Xlinker", "-rpath,$ORIGIN"])
+    main_src = os.path.join(HERE, "host", "main.cpp")
+    if os.path.exists(main_src) and (force or _newer(cli, deps + [host])):
+        _run([NVCC, *ARCH, *COMMON, "-o", cli, main_src, "-L" + OUT, "-lmobilevit_b200", "-lggml_b200",
+              "-Xlinker", "-rpath,$ORIGIN"])
+    return {"lib": lib, "host": host, "cli": cli}
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose_ptxas="--ptxas" in sys.argv)

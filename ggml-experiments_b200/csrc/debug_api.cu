@@ -1,0 +1,65 @@
+// debug_api.cu -- host-buffer entry points that run ONE kernel of the fast path in isolation, so the parity
+// tests can check each kernel against the oracle / numpy before it is trusted inside a fused plan.
+#include <vector>
+
+#include "gemm_tcgen05.h"
+#include "internal.h"
+
+using namespace b200;
+
+namespace {
+struct DevBuf {
+    void * p = nullptr;
+    DevBuf(const void * host, size_t bytes) {
+        if (bytes == 0) return;
+        B200_CHECK(cudaMalloc(&p, bytes));
+        if (host) B200_CHECK(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+        else B200_CHECK(cudaMemset(p, 0, bytes));
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" int ggml_b200_debug_gemm(const uint16_t * A, const uint16_t * B, int M, int N, int K, const float * scale,
+                                    const float * shift, int act, const float * res32, float * out32, uint16_t * out16) {
+    ensure_device();
+    DevBuf dA(A, (size_t)M * K * 2), dB(B, (size_t)N * K * 2);
+    DevBuf dS(scale, scale ? (size_t)N * 4 : 0), dH(shift, shift ? (size_t)N * 4 : 0);
+    DevBuf dR(res32, res32 ? (size_t)M * N * 4 : 0);
+    DevBuf dO32(nullptr, out32 ? (size_t)M * N * 4 : 0), dO16(nullptr, out16 ? (size_t)M * N * 2 : 0);
+    GemmEpilogue ep;
+    ep.scale = (const float *)dS.p; ep.shift = (const float *)dH.p; ep.act = act;
+    ep.res32 = (const float *)dR.p; ep.ldr32 = N;
+    ep.out32 = (float *)dO32.p; ep.ld32 = N;
+    ep.out16 = (__half *)dO16.p; ep.ld16 = N;
+    GemmLaunch L;
+    if (!gemm_prepare(L, (const __half *)dA.p, K, (const __half *)dB.p, K, M, N, K, ep)) return 1;
+    cudaStream_t st = current_stream();
+    gemm_launch(L, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    if (out32) B200_CHECK(cudaMemcpy(out32, dO32.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    if (out16) B200_CHECK(cudaMemcpy(out16, dO16.p, (size_t)M * N * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int ggml_b200_debug_conv3x3(const uint16_t * x0, int C0, const uint16_t * x1, int C1, int Nimg, int H, int W,
+                                       const uint16_t * Wt, int OC, const float * scale, const float * shift, int act,
+                                       float * out32) {
+    ensure_device();
+    const size_t px = (size_t)Nimg * H * W;
+    DevBuf dX0(x0, px * C0 * 2), dX1(x1, C1 ? px * C1 * 2 : 0), dW(Wt, (size_t)OC * 9 * (C0 + C1) * 2);
+    DevBuf dS(scale, scale ? (size_t)OC * 4 : 0), dH(shift, shift ? (size_t)OC * 4 : 0);
+    DevBuf dO(nullptr, px * OC * 4);
+    GemmEpilogue ep;
+    ep.scale = (const float *)dS.p; ep.shift = (const float *)dH.p; ep.act = act;
+    ep.out32 = (float *)dO.p; ep.ld32 = OC;
+    GemmLaunch L;
+    if (!conv3x3_prepare(L, (const __half *)dX0.p, C0, (const __half *)dX1.p, C1, Nimg, H, W, (const __half *)dW.p, OC, ep)) return 1;
+    cudaStream_t st = current_stream();
+    gemm_launch(L, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    B200_CHECK(cudaMemcpy(out32, dO.p, px * OC * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}

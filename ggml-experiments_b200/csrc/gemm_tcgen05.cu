@@ -1,0 +1,458 @@
+// gemm_tcgen05.cu -- K1: GEMM / implicit-GEMM 3x3 convolution on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces ggml_conv_2d's im2col + ggml_mul_mat (main.cpp:798, [ggml-upstream] im2col(F16) + vec_dot_f16)
+// and the dense ggml_mul_mat linears (main.cpp:1022,1039,1056,1095,1134,1151) of the reference.
+//
+//   D[M,N] (f32, TMEM) = A[M,K] (f16, K-major, smem via TMA) x B[N,K]^T (f16, K-major, smem via TMA)
+//
+// * operands are f16 and accumulation is f32, exactly the rounding points of ggml's f16 conv path;
+// * one CTA computes one 128 x block_n output tile (UMMA M=128, N=block_n<=256, K=16 per instruction);
+// * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> BN scale/shift or bias -> SiLU -> residual -> vectorised stores);
+// * smem ring of `stages` x (A 128x64 + B block_n x 64) f16 tiles in the 128-byte swizzled K-major layout
+//   shared by TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA shared-memory descriptors;
+// * the 3x3 convolution walks K as (tap, source, 64-channel block): each step is one 4-D TMA box
+//   {64 ch, W, rows, images} shifted by the tap offset, with the hardware zero-filling the halo, so no
+//   im2col buffer ever exists; a second source tensor map implements ggml_concat (main.cpp:1219) for free.
+//
+// The memory-bound layers (K <= 128, N <= 64) get their overlap from co-resident CTAs (smem and TMEM are
+// sized so that >= 2 CTAs fit per SM), not from an intra-CTA epilogue pipeline.
+#include "gemm_tcgen05.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "internal.h"
+
+namespace b200 {
+
+static constexpr int kBlockM   = 128;
+static constexpr int kBlockK   = 64;   // 64 f16 = 128 bytes = one swizzle-128B row
+static constexpr int kThreads  = 192;  // 6 warps
+static constexpr int kMaxStage = 4;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap * map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap * map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap * map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap * map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (f16 operands, f32 accumulate), issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive f32 columns -> 32 registers per thread (thread = TMEM lane = output row)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float * v) {
+    uint32_t * r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor for a K-major tile in the canonical 128-byte-swizzle layout:
+// rows of 128 B, 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                         // descriptor version = 1
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute InstrDescriptor): c=f32, a=b=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int block_n) {
+    return (1u << 4) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a0,
+                                                           const __grid_constant__ CUtensorMap map_a1,
+                                                           const __grid_constant__ CUtensorMap map_b,
+                                                           const GemmLaunch::Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t * smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle-128B atoms need 1 KiB alignment
+    const int       a_bytes     = kBlockM * kBlockK * 2;
+    const int       b_bytes     = p.block_n * kBlockK * 2;
+    const int       stage_bytes = a_bytes + b_bytes;
+    uint64_t *      bars        = (uint64_t *)(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *      full_bar    = bars;
+    uint64_t *      empty_bar   = bars + kMaxStage;
+    uint64_t *      tmem_full   = bars + 2 * kMaxStage;
+    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 1);
+    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 2);
+    float *         s_shift     = s_scale + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM;
+    const int n0 = blockIdx.y * p.block_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_b);
+        if (p.cblk1 > 0) tma_prefetch_desc(&map_a1);
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(tmem_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.block_n; i += kThreads) {
+        const int n = n0 + i;
+        s_scale[i]  = (p.ep.scale && n < p.N) ? p.ep.scale[n] : 1.0f;
+        s_shift[i]  = (p.ep.shift && n < p.N) ? p.ep.shift[n] : 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cblk_tot = p.cblk0 + p.cblk1;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int img = 0, y0 = 0;
+            if (p.conv) {
+                const int hw = p.H * p.W;
+                img          = m0 / hw;
+                y0           = p.rows_per_tile ? (m0 % hw) / p.W : 0;
+            }
+            for (int kb = 0; kb < p.num_kb; kb++) {
+                const int      s  = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                if (!p.conv) {
+                    tma_load_2d(sa, &map_a0, kb * kBlockK, m0, fb);
+                    tma_load_2d(sb, &map_b, kb * kBlockK, n0, fb);
+                } else {
+                    const int tap = kb / cblk_tot, r = kb % cblk_tot;
+                    const int src = r >= p.cblk0;
+                    const int cb  = src ? r - p.cblk0 : r;
+                    const int kh = tap / 3, kw = tap % 3;
+                    tma_load_4d(sa, src ? &map_a1 : &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
+                    tma_load_3d(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.block_n);
+            for (int kb = 0; kb < p.num_kb; kb++) {
+                const int      s  = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                int rem;
+                if (!p.conv) {
+                    rem = p.K - kb * kBlockK;
+                } else {
+                    const int r   = kb % cblk_tot;
+                    const int src = r >= p.cblk0;
+                    rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
+                }
+                const int      ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
+                const uint64_t adesc  = make_smem_desc(sa);
+                const uint64_t bdesc  = make_smem_desc(sb);
+                for (int k = 0; k < ksteps; k++) {
+                    // advancing 16 f16 (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
+                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                umma_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
+            }
+            umma_commit(smem_u32(tmem_full));  // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q   = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int m   = m0 + row;
+        mbar_wait(smem_u32(tmem_full), 0);
+        tc_fence_after();
+        const GemmEpilogue & ep = p.ep;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            if (n0 + c0 >= p.N) break;  // warp-uniform
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (m < p.M) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int n = n0 + c0 + g * 8;
+                    if (n + 8 <= p.N) {
+                        float y[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float t = fmaf(v[g * 8 + j], s_scale[c0 + g * 8 + j], s_shift[c0 + g * 8 + j]);
+                            y[j]    = ep.act ? silu_f(t) : t;
+                        }
+                        if (ep.res32) {
+                            const float4 r0 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n);
+                            const float4 r1 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n + 4);
+                            y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
+                            y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+                        }
+                        if (ep.res16) {
+                            const uint4    rr = *reinterpret_cast<const uint4 *>(ep.res16 + (size_t)m * ep.ldr16 + n);
+                            const __half2 * h = reinterpret_cast<const __half2 *>(&rr);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float2 f = __half22float2(h[j]);
+                                y[2 * j] += f.x;
+                                y[2 * j + 1] += f.y;
+                            }
+                        }
+                        if (ep.out32) {
+                            float4 * o = reinterpret_cast<float4 *>(ep.out32 + (size_t)m * ep.ld32 + n);
+                            o[0]       = make_float4(y[0], y[1], y[2], y[3]);
+                            o[1]       = make_float4(y[4], y[5], y[6], y[7]);
+                        }
+                        if (ep.out16) {
+                            uint4      o;
+                            __half2 *  h = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                            *reinterpret_cast<uint4 *>(ep.out16 + (size_t)m * ep.ld16 + n) = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *                           p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        B200_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        if (!p || qr != cudaDriverEntryPointSuccess) B200_ABORT("cuTensorMapEncodeTiled is not available in this driver");
+        fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+// rank-`rank` f16 tensor map, dims/strides innermost first (strides in bytes for dims 1..rank-1), 128B swizzle
+static void make_map(CUtensorMap * map, const void * base, int rank, const uint64_t * dims, const uint64_t * strides_bytes,
+                     const uint32_t * box) {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) {
+        gdim[i] = dims[i];
+        bx[i]   = box[i];
+        es[i]   = 1;
+    }
+    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+    CUresult r = get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "libggml_b200: cuTensorMapEncodeTiled failed (%d): rank %d dims", (int)r, rank);
+        for (int i = 0; i < rank; i++) fprintf(stderr, " %llu", (unsigned long long)dims[i]);
+        fprintf(stderr, " box");
+        for (int i = 0; i < rank; i++) fprintf(stderr, " %u", box[i]);
+        fprintf(stderr, "\n");
+        abort();
+    }
+}
+
+static void choose_tiling(GemmLaunch & L, int N) {
+    GemmLaunch::Params & p = L.p;
+    p.n_tiles              = (N + 255) / 256;
+    int per                = (N + p.n_tiles - 1) / p.n_tiles;
+    p.block_n              = (per + 31) / 32 * 32;
+    p.tmem_cols            = p.block_n <= 32 ? 32 : p.block_n <= 64 ? 64 : p.block_n <= 128 ? 128 : 256;
+    const int stage_bytes  = kBlockM * kBlockK * 2 + p.block_n * kBlockK * 2;
+    int       stages       = (96 * 1024) / stage_bytes;  // keep <= ~100 KiB so two CTAs share an SM
+    if (stages > kMaxStage) stages = kMaxStage;
+    if (stages < 2) stages = 2;
+    if (stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;
+    p.stages     = stages;
+    L.smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStage + 2) * 8 + 2 * 256 * sizeof(float);
+}
+
+bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, int ldb, int M, int N, int K,
+                  const GemmEpilogue & ep) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (lda % 8) || (ldb % 8) || (K % 8)) return false;
+    if (((uintptr_t)A | (uintptr_t)B) & 15) return false;
+    L = GemmLaunch();
+    GemmLaunch::Params & p = L.p;
+    p.M = M; p.N = N; p.K = K;
+    p.conv   = 0;
+    p.num_kb = (K + kBlockK - 1) / kBlockK;
+    p.ep     = ep;
+    choose_tiling(L, N);
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        const uint64_t str[1]  = {(uint64_t)lda * 2};
+        const uint32_t box[2]  = {(uint32_t)kBlockK, (uint32_t)kBlockM};
+        make_map(&L.map_a0, A, 2, dims, str, box);
+        L.map_a1 = L.map_a0;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        const uint64_t str[1]  = {(uint64_t)ldb * 2};
+        const uint32_t box[2]  = {(uint32_t)kBlockK, (uint32_t)p.block_n};
+        make_map(&L.map_b, B, 2, dims, str, box);
+    }
+    L.grid = dim3((unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)p.n_tiles, 1);
+    return true;
+}
+
+bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x1, int C1, int Nimg, int H, int W,
+                     const __half * Wt, int OC, const GemmEpilogue & ep) {
+    if (Nimg <= 0 || H <= 0 || W <= 0 || OC % 8 || C0 % 8 || C1 % 8 || C0 <= 0) return false;
+    if (W > 128 || 128 % W) return false;
+    int box_h, box_n, rows_per_tile;
+    if (H * W >= 128) {
+        if ((H * W) % 128) return false;
+        box_h         = 128 / W;
+        box_n         = 1;
+        rows_per_tile = box_h;
+    } else {
+        if (128 % (H * W)) return false;
+        box_h         = H;
+        box_n         = 128 / (H * W);
+        rows_per_tile = 0;
+    }
+    L = GemmLaunch();
+    GemmLaunch::Params & p = L.p;
+    p.M = Nimg * H * W; p.N = OC; p.K = 9 * (C0 + C1);
+    p.conv = 1; p.H = H; p.W = W; p.rows_per_tile = rows_per_tile;
+    p.C0 = C0; p.C1 = C1;
+    p.cblk0  = (C0 + kBlockK - 1) / kBlockK;
+    p.cblk1  = C1 > 0 ? (C1 + kBlockK - 1) / kBlockK : 0;
+    p.num_kb = 9 * (p.cblk0 + p.cblk1);
+    p.ep     = ep;
+    choose_tiling(L, OC);
+    auto act_map = [&](CUtensorMap * map, const __half * x, int C) {
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        const uint64_t str[3]  = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+        const uint32_t box[4]  = {(uint32_t)kBlockK, (uint32_t)W, (uint32_t)box_h, (uint32_t)box_n};
+        make_map(map, x, 4, dims, str, box);
+    };
+    act_map(&L.map_a0, x0, C0);
+    if (C1 > 0) act_map(&L.map_a1, x1, C1); else L.map_a1 = L.map_a0;
+    {
+        const int      ict     = C0 + C1;
+        const uint64_t dims[3] = {(uint64_t)ict, 9, (uint64_t)OC};
+        const uint64_t str[2]  = {(uint64_t)ict * 2, (uint64_t)9 * ict * 2};
+        const uint32_t box[3]  = {(uint32_t)kBlockK, 1, (uint32_t)p.block_n};
+        make_map(&L.map_b, Wt, 3, dims, str, box);
+    }
+    L.grid = dim3((unsigned)((p.M + kBlockM - 1) / kBlockM), (unsigned)p.n_tiles, 1);
+    return true;
+}
+
+void gemm_launch(const GemmLaunch & L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    k_gemm_tcgen05<<<L.grid, kThreads, L.smem_bytes, st>>>(L.map_a0, L.map_a1, L.map_b, L.p);
+}
+
+}  // namespace b200

@@ -1,0 +1,58 @@
+// gemm_tcgen05.h -- host interface of the tcgen05/TMA GEMM + implicit-GEMM 3x3 convolution kernel (K1).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace b200 {
+
+// Fused epilogue applied to the f32 accumulator tile read back from TMEM:
+//   y = acc * scale[n] + shift[n]      (folded BatchNorm, or bias with scale == nullptr)
+//   y = silu(y)                        (act == 1)
+//   y += residual[m, n]                (f32 or f16 residual, optional)
+//   store f16 and/or f32, row-major with leading dimension ld*
+struct GemmEpilogue {
+    const float *  scale = nullptr;
+    const float *  shift = nullptr;
+    int            act   = 0;
+    const float *  res32 = nullptr;
+    int            ldr32 = 0;
+    const __half * res16 = nullptr;
+    int            ldr16 = 0;
+    __half *       out16 = nullptr;
+    int            ld16  = 0;
+    float *        out32 = nullptr;
+    int            ld32  = 0;
+};
+
+// A prepared launch: tensor maps are encoded once at plan time, the launch is then replayable / capturable.
+struct GemmLaunch {
+    CUtensorMap map_a0, map_a1, map_b;
+    struct Params {
+        int M, N, K;
+        int block_n, n_tiles, num_kb, stages, tmem_cols;
+        int conv;                   // 0: plain GEMM, 1: 3x3 stride-1 pad-1 implicit GEMM over NHWC
+        int H, W, rows_per_tile;    // conv: image rows covered by one 128-pixel tile (0 if a tile spans whole images)
+        int cblk0, cblk1, C0, C1;   // conv: 64-channel blocks / channels of source 0 and source 1 (concat fusion)
+        GemmEpilogue ep;
+    } p;
+    size_t smem_bytes;
+    dim3   grid;
+};
+
+// C[M,N] = A[M,K] * B[N,K]^T.  A, B f16, K contiguous (lda/ldb in elements, multiples of 8).
+bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, int ldb, int M, int N, int K,
+                  const GemmEpilogue & ep);
+
+// 3x3, stride 1, pad 1 convolution over NHWC f16 activations as an implicit GEMM:
+//   out[(n,y,x), oc] = sum_{kh,kw,ic} in[n, y+kh-1, x+kw-1, ic] * Wt[oc, kh, kw, ic]
+// The input channels may come from two tensors (x0: C0 channels, x1: C1 channels) = a fused ggml_concat.
+// Wt is [OC][3][3][C0+C1] f16.  Returns false if the shape cannot be tiled (W must divide 128 or 128 | W*k).
+bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x1, int C1, int Nimg, int H, int W,
+                     const __half * Wt, int OC, const GemmEpilogue & ep);
+
+void gemm_launch(const GemmLaunch & L, cudaStream_t st);
+
+}  // namespace b200

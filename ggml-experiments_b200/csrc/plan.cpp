@@ -1,0 +1,437 @@
+// plan.cpp -- device plans: lifecycle, liveness-based memory planner, transfers, CUDA-graph replay.
+//
+// Replaces upstream ggml's ggml_graph_compute (CPU thread pool + work buffer) for the reference's
+// ggml_graph_compute_with_ctx calls (main.cpp:640, rnn.cpp:158,311).
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "internal.h"
+
+namespace b200 {
+
+Runtime & runtime() {
+    static Runtime rt;
+    return rt;
+}
+
+void ensure_device() {
+    Runtime & rt = runtime();
+    if (rt.initialised) return;
+    int         n   = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0) {
+        fprintf(stderr,
+                "libggml_b200: no usable CUDA device (%s). This library has no CPU fallback: "
+                "ggml_graph_compute_with_ctx requires an sm_100a GPU.\n",
+                err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+        abort();
+    }
+    B200_CHECK(cudaSetDevice(rt.device));
+    cudaDeviceProp prop;
+    B200_CHECK(cudaGetDeviceProperties(&prop, rt.device));
+    if (prop.major != 10) {
+        fprintf(stderr, "libggml_b200: device %d is sm_%d%d; kernels are built for sm_100a only.\n", rt.device, prop.major,
+                prop.minor);
+        abort();
+    }
+    rt.sm_count = prop.multiProcessorCount;
+    B200_CHECK(cudaStreamCreateWithFlags(&rt.own_stream, cudaStreamNonBlocking));
+    const char * m = getenv("GGML_B200_MODE");
+    if (m) {
+        if (!strcmp(m, "exact")) rt.mode = GGML_B200_MODE_EXACT;
+        if (!strcmp(m, "fast")) rt.mode = GGML_B200_MODE_FAST;
+    }
+    const char * v = getenv("GGML_B200_VERBOSE");
+    rt.verbose     = v && atoi(v) > 0;
+    const char * g = getenv("GGML_B200_CUDA_GRAPH");
+    if (g) rt.use_cuda_graph = atoi(g) != 0;
+    rt.initialised = true;
+}
+
+cudaStream_t current_stream() {
+    Runtime & rt = runtime();
+    return rt.use_user_stream ? rt.user_stream : rt.own_stream;
+}
+
+// ---- arena planner: best-fit free list with coalescing -------------------------------------------------
+int64_t ArenaPlanner::alloc(int64_t bytes) {
+    bytes    = align_up(bytes > 0 ? bytes : 1);
+    int best = -1;
+    for (int i = 0; i < (int)free_list.size(); i++)
+        if (free_list[i].size >= bytes && (best < 0 || free_list[i].size < free_list[best].size)) best = i;
+    if (best >= 0) {
+        int64_t off = free_list[best].off;
+        free_list[best].off += bytes;
+        free_list[best].size -= bytes;
+        if (free_list[best].size == 0) free_list.erase(free_list.begin() + best);
+        return off;
+    }
+    // grow: if the last free block touches the end of the arena, extend it instead of leaving a hole
+    for (int i = 0; i < (int)free_list.size(); i++)
+        if (free_list[i].off + free_list[i].size == extent) {
+            int64_t off = free_list[i].off;
+            extent      = off + bytes;
+            free_list.erase(free_list.begin() + i);
+            return off;
+        }
+    int64_t off = extent;
+    extent += bytes;
+    return off;
+}
+
+void ArenaPlanner::release(int64_t off, int64_t bytes) {
+    bytes = align_up(bytes > 0 ? bytes : 1);
+    Block b{off, bytes};
+    // insert sorted, then coalesce with neighbours
+    size_t pos = 0;
+    while (pos < free_list.size() && free_list[pos].off < off) pos++;
+    free_list.insert(free_list.begin() + pos, b);
+    if (pos + 1 < free_list.size() && free_list[pos].off + free_list[pos].size == free_list[pos + 1].off) {
+        free_list[pos].size += free_list[pos + 1].size;
+        free_list.erase(free_list.begin() + pos + 1);
+    }
+    if (pos > 0 && free_list[pos - 1].off + free_list[pos - 1].size == free_list[pos].off) {
+        free_list[pos - 1].size += free_list[pos].size;
+        free_list.erase(free_list.begin() + pos);
+    }
+}
+
+void add_launch(Plan * plan, const char * kernel, Launch l, double flops, double bytes, std::string what) {
+    plan->launches.push_back(std::move(l));
+    LaunchMeta m;
+    m.kernel = kernel;
+    m.what   = std::move(what);
+    m.flops  = flops;
+    m.bytes  = bytes;
+    plan->meta.push_back(std::move(m));
+}
+
+bool is_view_op(enum ggml_op op) {
+    return op == GGML_OP_RESHAPE || op == GGML_OP_VIEW || op == GGML_OP_PERMUTE || op == GGML_OP_TRANSPOSE;
+}
+
+TView make_view(const ggml_tensor * t, void * dptr) {
+    TView v;
+    v.p = dptr;
+    for (int i = 0; i < 4; i++) {
+        v.ne[i] = t->ne[i];
+        v.nb[i] = (int64_t)t->nb[i];
+    }
+    v.type = (int)t->type;
+    return v;
+}
+
+void * device_ptr_of(Plan * plan, const ggml_tensor * t) {
+    auto it = plan->slots.find(t);
+    if (it == plan->slots.end() || it->second.dptr == nullptr) B200_ABORT("tensor '%s' (op %d) has no device buffer in this plan", t->name, (int)t->op);
+    return it->second.dptr;
+}
+
+// ---- plan registry ------------------------------------------------------------------------------------
+static std::mutex                               g_plans_mu;
+static std::multimap<ggml_context *, Plan *>    g_plans;
+static std::unordered_map<const ggml_tensor *, void *> g_external;  // leaf -> caller-owned device memory
+
+Plan::~Plan() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (void * p : owned_device) cudaFree(p);
+    for (void * p : pinned) cudaHostUnregister(p);
+}
+
+static uint64_t graph_signature(const ggml_cgraph * gf) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; };
+    mix((uint64_t)gf->n_nodes);
+    mix((uint64_t)gf->n_leafs);
+    for (int i = 0; i < gf->n_nodes; i++) {
+        const ggml_tensor * t = gf->nodes[i];
+        mix((uint64_t)(uintptr_t)t);
+        mix((uint64_t)t->op);
+        for (int d = 0; d < 4; d++) { mix((uint64_t)t->ne[d]); mix((uint64_t)t->nb[d]); }
+    }
+    mix((uint64_t)runtime().mode);
+    return h;
+}
+
+void destroy_plans_of(ggml_context * ctx) {
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    auto range = g_plans.equal_range(ctx);
+    for (auto it = range.first; it != range.second; ++it) delete it->second;
+    g_plans.erase(range.first, range.second);
+}
+
+static void try_pin(Plan * plan, void * p, size_t bytes) {
+    // Pin the host range of an input leaf / output shadow so the per-compute copies are true async DMA.
+    if (bytes < (64u << 10)) return;
+    uintptr_t lo = (uintptr_t)p & ~uintptr_t(4095);
+    uintptr_t hi = ((uintptr_t)p + bytes + 4095) & ~uintptr_t(4095);
+    cudaError_t e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault);
+    if (e == cudaSuccess) plan->pinned.push_back((void *)lo);
+    else (void)cudaGetLastError();  // already pinned / overlapping: harmless, copy still works
+}
+
+// Assign device memory to leafs; shared by both plan builders.
+//   * leafs of another context than the compute context, and ggml_new_f32 scalars, are CONSTANTS (weights):
+//     uploaded once when the plan is built.
+//   * leafs of the compute context, or flagged input/param, are INPUTS: uploaded on every compute
+//     (main.cpp:627-634 writes the image through ggml_get_data; rnn.cpp:303-310 rewrites id and state).
+static void place_leafs(Plan * plan, ggml_cgraph * gf) {
+    int64_t const_bytes = 0, input_bytes = 0;
+    auto    is_input    = [&](const ggml_tensor * t) {
+        if (t->flags & 0x100) return false;
+        if (t->flags & (GGML_TENSOR_FLAG_INPUT | GGML_TENSOR_FLAG_PARAM)) return true;
+        return t->ctx == plan->ctx;
+    };
+    std::vector<ggml_tensor *> roots;
+    for (int i = 0; i < gf->n_leafs; i++) {
+        ggml_tensor * t = gf->leafs[i];
+        if (t->view_src) continue;  // views of leafs alias their base
+        roots.push_back(t);
+        int64_t b = ArenaPlanner::align_up((int64_t)ggml_nelements(t) * (int64_t)ggml_type_size(t->type));
+        if (g_external.count(t)) continue;
+        if (is_input(t)) input_bytes += b; else const_bytes += b;
+    }
+    char * cpool = nullptr, * ipool = nullptr;
+    if (const_bytes) { B200_CHECK(cudaMalloc((void **)&cpool, const_bytes)); plan->owned_device.push_back(cpool); }
+    if (input_bytes) { B200_CHECK(cudaMalloc((void **)&ipool, input_bytes)); plan->owned_device.push_back(ipool); }
+    plan->weight_bytes = const_bytes;
+    int64_t coff = 0, ioff = 0;
+    cudaStream_t st = current_stream();
+    for (ggml_tensor * t : roots) {
+        Slot    s;
+        int64_t raw = (int64_t)ggml_nelements(t) * (int64_t)ggml_type_size(t->type);
+        int64_t b   = ArenaPlanner::align_up(raw);
+        s.bytes     = raw;
+        auto ext    = g_external.find(t);
+        if (ext != g_external.end()) {
+            s.kind = SLOT_EXTERNAL;
+            s.dptr = ext->second;
+        } else if (is_input(t)) {
+            s.kind = SLOT_INPUT;
+            s.dptr = ipool + ioff;
+            ioff += b;
+            if (!t->data) B200_ABORT("input leaf '%s' has no host data", t->name);
+            plan->uploads.push_back({t, s.dptr, (size_t)raw});
+            try_pin(plan, t->data, (size_t)raw);
+        } else {
+            s.kind = SLOT_CONST;
+            s.dptr = cpool + coff;
+            coff += b;
+            if (!t->data) B200_ABORT("constant leaf '%s' has no host data", t->name);
+            B200_CHECK(cudaMemcpyAsync(s.dptr, t->data, (size_t)raw, cudaMemcpyHostToDevice, st));
+        }
+        plan->slots[t] = s;
+    }
+    for (int i = 0; i < gf->n_leafs; i++) {
+        ggml_tensor * t = gf->leafs[i];
+        if (!t->view_src) continue;
+        Slot s;
+        s.kind = SLOT_ALIAS;
+        s.dptr = (char *)device_ptr_of(plan, t->view_src) + t->view_offs;
+        plan->slots[t] = s;
+    }
+    B200_CHECK(cudaStreamSynchronize(st));
+}
+
+Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
+    ensure_device();
+    uint64_t sig = graph_signature(gf);
+    if (gf->plan) {
+        Plan * p = (Plan *)gf->plan;
+        if (p->graph_sig == sig) return p;
+        // the graph was extended or the mode changed: rebuild
+        ggml_graph_release_plan(gf);
+    }
+    Plan * plan      = new Plan();
+    plan->ctx        = ctx;
+    plan->graph_sig  = sig;
+    plan->n_nodes_at_build = gf->n_nodes;
+    place_leafs(plan, gf);
+    bool fast_ok = false;
+    if (runtime().mode == GGML_B200_MODE_FAST) {
+        fast_ok = build_fast_plan(plan, gf);
+        if (!fast_ok && runtime().verbose)
+            fprintf(stderr, "libggml_b200: graph not recognised by the fused planner; using the per-node exact plan (still on device)\n");
+    }
+    if (!fast_ok) build_exact_plan(plan, gf);
+    plan->mode = fast_ok ? GGML_B200_MODE_FAST : GGML_B200_MODE_EXACT;
+    // host shadows for graph outputs
+    for (int i = 0; i < gf->n_nodes; i++) {
+        ggml_tensor * t = gf->nodes[i];
+        if (!(t->flags & GGML_TENSOR_FLAG_OUTPUT)) continue;
+        auto it = plan->slots.find(t);
+        if (it == plan->slots.end() || !it->second.dptr) continue;
+        if (!ggml_is_contiguous(t)) {
+            // a strided view as an output: mirror its base instead (rnn.cpp:239 `states` is a transpose)
+            ggml_tensor * base = t->view_src;
+            if (base && plan->slots.count(base) && !base->data) {
+                size_t bytes = (size_t)ggml_nelements(base) * ggml_type_size(base->type);
+                base->data   = arena_alloc(base->ctx, bytes, 64);
+                plan->downloads.push_back({base, plan->slots[base].dptr, bytes});
+            }
+            if (base && base->data) t->data = (char *)base->data + t->view_offs;
+            continue;
+        }
+        size_t bytes = (size_t)ggml_nelements(t) * ggml_type_size(t->type);
+        if (!t->data) t->data = arena_alloc(t->ctx, bytes, 4096);
+        plan->downloads.push_back({t, it->second.dptr, bytes});
+        try_pin(plan, t->data, bytes);
+    }
+    gf->plan = plan;
+    {
+        std::lock_guard<std::mutex> lk(g_plans_mu);
+        g_plans.insert({ctx, plan});
+    }
+    if (runtime().verbose)
+        fprintf(stderr, "libggml_b200: plan mode=%s nodes=%d launches=%zu arena=%.1f MiB (naive %.1f MiB) weights=%.1f MiB\n",
+                plan->mode == GGML_B200_MODE_FAST ? "fast" : "exact", gf->n_nodes, plan->launches.size(),
+                plan->arena_bytes / 1048576.0, plan->naive_bytes / 1048576.0, plan->weight_bytes / 1048576.0);
+    return plan;
+}
+
+void run_plan(Plan * plan) {
+    cudaStream_t st = current_stream();
+    if (plan->upload_inputs)
+        for (const Transfer & u : plan->uploads) B200_CHECK(cudaMemcpyAsync(u.dptr, u.t->data, u.bytes, cudaMemcpyHostToDevice, st));
+    Runtime & rt = runtime();
+    if (rt.use_cuda_graph && !plan->graph_failed && plan->launches.size() > 1) {
+        if (!plan->graph_exec) {
+            // capture the launch sequence once; replay afterwards (launch-bound inner loop -> one submit)
+            cudaStream_t cs;
+            B200_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g   = nullptr;
+            cudaError_t err = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (err == cudaSuccess) {
+                for (auto & l : plan->launches) l(cs);
+                err = cudaStreamEndCapture(cs, &g);
+            }
+            if (err == cudaSuccess && g) err = cudaGraphInstantiate(&plan->graph_exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (err != cudaSuccess || !plan->graph_exec) {
+                (void)cudaGetLastError();
+                plan->graph_failed = true;
+                plan->graph_exec   = nullptr;
+                if (rt.verbose) fprintf(stderr, "libggml_b200: CUDA graph capture failed (%s); launching directly\n", cudaGetErrorString(err));
+            }
+        }
+    }
+    if (plan->graph_exec) {
+        B200_CHECK(cudaGraphLaunch(plan->graph_exec, st));
+    } else {
+        for (auto & l : plan->launches) l(st);
+    }
+    B200_CHECK(cudaGetLastError());
+    if (plan->download_outputs) {
+        for (const Transfer & d : plan->downloads) B200_CHECK(cudaMemcpyAsync(d.t->data, d.dptr, d.bytes, cudaMemcpyDeviceToHost, st));
+        B200_CHECK(cudaStreamSynchronize(st));  // ggml semantics: results are readable when compute returns
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// ---- extension API -----------------------------------------------------------------------------------
+extern "C" void ggml_graph_release_plan(struct ggml_cgraph * gf) {
+    if (!gf->plan) return;
+    Plan * p = (Plan *)gf->plan;
+    {
+        std::lock_guard<std::mutex> lk(g_plans_mu);
+        for (auto it = g_plans.begin(); it != g_plans.end(); ++it)
+            if (it->second == p) { g_plans.erase(it); break; }
+    }
+    cudaDeviceSynchronize();
+    delete p;
+    gf->plan = nullptr;
+}
+
+extern "C" void ggml_b200_set_mode(enum ggml_b200_mode mode) { runtime().mode = (int)mode; }
+extern "C" int  ggml_b200_get_mode(void) { return runtime().mode; }
+
+extern "C" int ggml_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" void ggml_b200_set_device(int device) {
+    Runtime & rt = runtime();
+    if (rt.initialised && rt.device != device) B200_ABORT("ggml_b200_set_device must be called before the first compute (one process per GPU)");
+    rt.device = device;
+}
+extern "C" void ggml_b200_set_stream(void * stream) {
+    Runtime & rt       = runtime();
+    rt.user_stream     = (cudaStream_t)stream;
+    rt.use_user_stream = true;
+}
+extern "C" void * ggml_b200_get_stream(void) { ensure_device(); return (void *)current_stream(); }
+extern "C" void   ggml_b200_synchronize(void) { ensure_device(); B200_CHECK(cudaStreamSynchronize(current_stream())); }
+
+extern "C" void ggml_b200_tensor_set_device_data(struct ggml_tensor * leaf, void * device_ptr) {
+    GGML_ASSERT(leaf->op == GGML_OP_NONE && leaf->view_src == nullptr);
+    if (device_ptr) g_external[leaf] = device_ptr; else g_external.erase(leaf);
+}
+extern "C" void * ggml_b200_tensor_get_device_data(struct ggml_cgraph * gf, struct ggml_tensor * t) {
+    if (!gf->plan) return nullptr;
+    Plan * p = (Plan *)gf->plan;
+    auto it  = p->slots.find(t);
+    return it == p->slots.end() ? nullptr : it->second.dptr;
+}
+extern "C" void ggml_b200_graph_set_transfers(struct ggml_cgraph * gf, bool upload_inputs, bool download_outputs) {
+    if (!gf->plan) B200_ABORT("ggml_b200_graph_set_transfers: call ggml_b200_graph_prepare first");
+    Plan * p            = (Plan *)gf->plan;
+    p->upload_inputs    = upload_inputs;
+    p->download_outputs = download_outputs;
+}
+// Per-launch device times (CUDA events on the launching stream, direct launches -- not the CUDA-graph replay),
+// averaged over `reps` passes after one warm-up pass, written as a JSON array into buf.
+extern "C" int ggml_b200_graph_profile_json(struct ggml_cgraph * gf, int reps, char * buf, size_t cap) {
+    if (!gf->plan || reps < 1) return -1;
+    Plan *       p  = (Plan *)gf->plan;
+    cudaStream_t st = current_stream();
+    const size_t n  = p->launches.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto & e : ev) B200_CHECK(cudaEventCreate(&e));
+    std::vector<double> ms(n, 0.0);
+    for (int r = -1; r < reps; r++) {
+        B200_CHECK(cudaEventRecord(ev[0], st));
+        for (size_t i = 0; i < n; i++) {
+            p->launches[i](st);
+            B200_CHECK(cudaEventRecord(ev[i + 1], st));
+        }
+        B200_CHECK(cudaStreamSynchronize(st));
+        if (r < 0) continue;
+        for (size_t i = 0; i < n; i++) {
+            float t = 0;
+            B200_CHECK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            ms[i] += t;
+        }
+    }
+    for (auto & e : ev) cudaEventDestroy(e);
+    std::string out = "[";
+    char        tmp[512];
+    for (size_t i = 0; i < n; i++) {
+        snprintf(tmp, sizeof tmp, "%s{\"kernel\":\"%s\",\"what\":\"%.60s\",\"ms\":%.6f,\"flops\":%.0f,\"bytes\":%.0f}", i ? "," : "",
+                 p->meta[i].kernel, p->meta[i].what.c_str(), ms[i] / reps, p->meta[i].flops, p->meta[i].bytes);
+        out += tmp;
+    }
+    out += "]";
+    if (out.size() + 1 > cap) return (int)out.size() + 1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+extern "C" void ggml_b200_graph_plan_stats(struct ggml_cgraph * gf, struct ggml_b200_plan_stats * out) {
+    memset(out, 0, sizeof(*out));
+    if (!gf->plan) return;
+    Plan * p            = (Plan *)gf->plan;
+    out->mode           = p->mode;
+    out->n_graph_nodes  = p->n_nodes_at_build;
+    out->n_launches     = (int)p->launches.size();
+    out->n_folded       = p->n_folded;
+    out->arena_bytes    = p->arena_bytes;
+    out->naive_bytes    = p->naive_bytes;
+    out->weight_bytes   = p->weight_bytes;
+    out->used_cuda_graph = p->graph_exec != nullptr;
+}

@@ -1,0 +1,413 @@
+// mobilevit.cpp -- loader + batched graph builder + C ABI (include/mobilevit_b200.h).
+// See mobilevit.h for how this relates to /root/reference/mobilevit/main.cpp.
+#include "mobilevit.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+#include "mobilevit_b200.h"
+
+namespace mvit {
+
+static const char * kRoot = "tf_mobile_vi_t_model/mobilevit";
+
+// ------------------------------------------------------------------------------------------------------
+// loader: read_all_weights (main.cpp:872-942) + assign_weights (main.cpp:218-312)
+// ------------------------------------------------------------------------------------------------------
+static bool read_i32(std::ifstream & f, int32_t & v) { return (bool)f.read(reinterpret_cast<char *>(&v), 4); }
+
+static bool read_all_weights(model & m, std::ifstream & fin) {
+    // record layout: int32 name_len, name, int32 n_dims, int32 dims[n_dims] (TF order), f32 data.
+    // Unlike main.cpp:874-939 the loop ends at a clean EOF (no bogus trailing tensor).
+    std::vector<float> staging;
+    for (;;) {
+        int32_t name_len = 0, n_dims = 0;
+        if (!read_i32(fin, name_len)) break;
+        if (name_len <= 0 || name_len > 4096) return false;
+        std::string name((size_t)name_len, '\0');
+        if (!fin.read(&name[0], name_len)) return false;
+        if (!read_i32(fin, n_dims) || n_dims < 1 || n_dims > 4) return false;
+        int32_t dims[4] = {1, 1, 1, 1};
+        for (int i = 0; i < n_dims; i++)
+            if (!read_i32(fin, dims[i]) || dims[i] <= 0) return false;
+        // main.cpp:887-889: every tensor whose name contains "convolution" is stored as F16
+        const bool      is_f16 = name.find("convolution") != std::string::npos;
+        const ggml_type type   = is_f16 ? GGML_TYPE_F16 : GGML_TYPE_F32;
+        ggml_tensor *   t      = nullptr;  // ggml ne = TF dims reversed (main.cpp:905-917)
+        switch (n_dims) {
+            case 4: t = ggml_new_tensor_4d(m.ctx_w, type, dims[3], dims[2], dims[1], dims[0]); break;
+            case 3: t = ggml_new_tensor_3d(m.ctx_w, GGML_TYPE_F32, dims[2], dims[1], dims[0]); break;
+            case 2: t = ggml_new_tensor_2d(m.ctx_w, GGML_TYPE_F32, dims[1], dims[0]); break;
+            default: t = ggml_new_tensor_1d(m.ctx_w, GGML_TYPE_F32, dims[0]); break;
+        }
+        const size_t count = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
+        staging.resize(count);
+        if (!fin.read(reinterpret_cast<char *>(staging.data()), (std::streamsize)(count * sizeof(float)))) return false;
+        if (t->type == GGML_TYPE_F16) {
+            ggml_fp32_to_fp16_row(staging.data(), (ggml_fp16_t *)t->data, (int)count);  // main.cpp:928-932
+        } else {
+            memcpy(t->data, staging.data(), ggml_nbytes(t));
+        }
+        ggml_set_name(t, name.size() > 60 ? name.c_str() + (name.size() - 60) : name.c_str());
+        m.tensors[name] = t;
+        m.total_weights += (int64_t)count;
+    }
+    return !m.tensors.empty();
+}
+
+static ggml_tensor * need(const model & m, const std::string & name) {
+    auto it = m.tensors.find(name);
+    if (it == m.tensors.end()) {  // main.cpp:225 tensors.at() -> std::out_of_range -> terminate
+        fprintf(stderr, "mobilevit: weight file lacks tensor '%s'\n", name.c_str());
+        abort();
+    }
+    return it->second;
+}
+static bool has(const model & m, const std::string & name) { return m.tensors.count(name) != 0; }
+
+static void bind(const model & m, conv_layer & c, const std::string & path, bool use_normalization = true) {
+    c.kernel = need(m, path + "/convolution/kernel:0");
+    if (use_normalization) {
+        c.gamma           = need(m, path + "/normalization/gamma:0");
+        c.beta            = need(m, path + "/normalization/beta:0");
+        c.moving_mean     = need(m, path + "/normalization/moving_mean:0");
+        c.moving_variance = need(m, path + "/normalization/moving_variance:0");
+    }
+}
+static void bind(const model & m, inverted_residual & r, const std::string & path, int strides) {
+    r.strides = strides;
+    bind(m, r.expand_1x1, path + "/expand_1x1");
+    bind(m, r.conv_3x3, path + "/conv_3x3");
+    bind(m, r.reduce_1x1, path + "/reduce_1x1");
+}
+static void bind(const model & m, transformer_layer & t, const std::string & p) {
+    t.q_w    = need(m, p + "/attention/attention/query/kernel:0");  t.q_b    = need(m, p + "/attention/attention/query/bias:0");
+    t.k_w    = need(m, p + "/attention/attention/key/kernel:0");    t.k_b    = need(m, p + "/attention/attention/key/bias:0");
+    t.v_w    = need(m, p + "/attention/attention/value/kernel:0");  t.v_b    = need(m, p + "/attention/attention/value/bias:0");
+    t.o_w    = need(m, p + "/attention/output/dense/kernel:0");     t.o_b    = need(m, p + "/attention/output/dense/bias:0");
+    t.up_w   = need(m, p + "/intermediate/dense/kernel:0");         t.up_b   = need(m, p + "/intermediate/dense/bias:0");
+    t.down_w = need(m, p + "/output/dense/kernel:0");               t.down_b = need(m, p + "/output/dense/bias:0");
+    t.ln_before_g = need(m, p + "/layernorm_before/gamma:0");       t.ln_before_b = need(m, p + "/layernorm_before/beta:0");
+    t.ln_after_g  = need(m, p + "/layernorm_after/gamma:0");        t.ln_after_b  = need(m, p + "/layernorm_after/beta:0");
+}
+static void bind(const model & m, vit_block & b, const std::string & path) {
+    bind(m, b.downsampling, path + "/downsampling_layer", 2);  // main.cpp:397,434,471: ViT stages downsample by 2
+    bind(m, b.conv_kxk, path + "/conv_kxk");
+    bind(m, b.conv_1x1, path + "/conv_1x1", false);  // main.cpp:293: kernel only
+    for (int j = 0; has(m, path + "/transformer/layer." + std::to_string(j) + "/attention/attention/query/kernel:0"); j++) {
+        b.layers.emplace_back();
+        bind(m, b.layers.back(), path + "/transformer/layer." + std::to_string(j));
+    }
+    b.ln_g = need(m, path + "/layernorm/gamma:0");
+    b.ln_b = need(m, path + "/layernorm/beta:0");
+    bind(m, b.conv_projection, path + "/conv_projection");
+    bind(m, b.fusion, path + "/fusion");
+}
+
+bool model::load(const std::string & path) {
+    std::ifstream fin(path, std::ios::binary);
+    if (!fin) return false;  // main.cpp:316-318 only prints; a missing file is an error here
+    fin.seekg(0, std::ios::end);
+    const size_t file_bytes = (size_t)fin.tellg();
+    fin.seekg(0, std::ios::beg);
+    // weights arena: the reference uses a fixed 128 MiB (main.cpp:656); size it from the file instead
+    ggml_init_params params = {file_bytes + (size_t)(8u << 20), nullptr, false};
+    ctx_w                   = ggml_init(params);
+    if (!ctx_w) return false;
+    if (!read_all_weights(*this, fin)) return false;
+
+    const std::string root = kRoot;
+    bind(*this, conv_stem, root + "/conv_stem");
+    // mobile_net_layer 1 and 2 (main.cpp:334-391): first block of layer.1 has stride 2, all others stride 1
+    for (int i = 0; has(*this, root + "/encoder/layer.0/layer." + std::to_string(i) + "/expand_1x1/convolution/kernel:0"); i++) {
+        layer_1.emplace_back();
+        bind(*this, layer_1.back(), root + "/encoder/layer.0/layer." + std::to_string(i), 1);
+    }
+    for (int i = 0; has(*this, root + "/encoder/layer.1/layer." + std::to_string(i) + "/expand_1x1/convolution/kernel:0"); i++) {
+        layer_2.emplace_back();
+        bind(*this, layer_2.back(), root + "/encoder/layer.1/layer." + std::to_string(i), i == 0 ? 2 : 1);
+    }
+    bind(*this, layer_3, root + "/encoder/layer.2");
+    bind(*this, layer_4, root + "/encoder/layer.3");
+    bind(*this, layer_5, root + "/encoder/layer.4");
+    bind(*this, conv_1x1_exp, root + "/conv_1x1_exp");
+    return true;
+}
+
+model::~model() {
+    for (auto & kv : graphs) {
+        ggml_graph_release_plan(kv.second.gf);
+        ggml_free(kv.second.ctx);
+    }
+    if (ctx_w) ggml_free(ctx_w);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// graph builder
+// ------------------------------------------------------------------------------------------------------
+
+// [1-d per-channel parameter] -> broadcast over an activation of shape like `like` (W,H,C,N)
+static ggml_tensor * per_channel(ggml_context * ctx, ggml_tensor * p, ggml_tensor * like) {
+    return ggml_repeat(ctx, ggml_cont_4d(ctx, p, 1, 1, p->ne[0], 1), like);
+}
+
+// conv (+ inference BatchNorm, eps 1e-5) (+ SiLU): main.cpp:771-852
+ggml_tensor * conv_layer::forward(ggml_context * ctx, ggml_tensor * input, int stride, bool use_normalization,
+                                  bool use_activation, bool depthwise) const {
+    const int64_t oc = kernel->ne[0], ic = kernel->ne[1], kw = kernel->ne[2], kh = kernel->ne[3];
+    const int     pad = (int)(kw - 1) / 2;
+    // file layout (KH,KW,IC,OC) == ggml ne (OC,IC,KW,KH); ggml_conv_2d wants (KW,KH,IC,OC)
+    ggml_tensor * w   = ggml_cont_4d(ctx, ggml_permute(ctx, kernel, 3, 2, 0, 1), kw, kh, ic, oc);
+    ggml_tensor * out = depthwise ? ggml_conv_depthwise_2d(ctx, w, input, stride, stride, pad, pad, 1, 1)
+                                  : ggml_conv_2d(ctx, w, input, stride, stride, pad, pad, 1, 1);
+    if (use_normalization) {
+        // ((x - mean) / sqrt(var + eps)) * gamma + beta, unfused f32 as in main.cpp:809-846
+        out = ggml_sub(ctx, out, per_channel(ctx, moving_mean, out));
+        out = ggml_div(ctx, out, ggml_sqrt(ctx, ggml_add(ctx, per_channel(ctx, moving_variance, out), ggml_new_f32(ctx, 1.0e-5f))));
+        out = ggml_mul(ctx, out, per_channel(ctx, gamma, out));
+        out = ggml_add(ctx, out, per_channel(ctx, beta, out));
+    }
+    if (use_activation) out = ggml_silu(ctx, out);
+    return out;
+}
+
+// MobileNetV2 block: main.cpp:854-870.  The residual rule uses the real channel counts.
+ggml_tensor * inverted_residual::forward(ggml_context * ctx, ggml_tensor * inp) const {
+    ggml_tensor * x = expand_1x1.forward(ctx, inp, 1, true, true, false);
+    x               = conv_3x3.forward(ctx, x, strides, true, true, true);
+    x               = reduce_1x1.forward(ctx, x, 1, true, false, false);
+    if (strides == 1 && expand_1x1.in_channels() == reduce_1x1.out_channels()) x = ggml_add(ctx, x, inp);
+    return x;
+}
+
+// (W,H,C,N) -> (C, n_patches, ps*ps, N): main.cpp:721-747 with the batch carried in the slowest dim
+ggml_tensor * unfolding(ggml_context * ctx, ggml_tensor * features, int ps) {
+    const int64_t nw = features->ne[0], nh = features->ne[1], c = features->ne[2], n = features->ne[3];
+    GGML_ASSERT(nw % ps == 0);
+    GGML_ASSERT(nh % ps == 0);
+    const int64_t npw = nw / ps, nph = nh / ps;
+    ggml_tensor * p = ggml_reshape_4d(ctx, ggml_cont(ctx, features), ps, npw, ps, n * c * nph);
+    p               = ggml_permute(ctx, p, 0, 2, 1, 3);  // (pw, ph, npw, n*c*nph)
+    p               = ggml_reshape_4d(ctx, ggml_cont(ctx, p), ps * ps, npw * nph, c, n);
+    return ggml_cont(ctx, ggml_permute(ctx, p, 2, 1, 0, 3));  // (c, n_patches, ps*ps, n)
+}
+
+// (C, n_patches, ps*ps*N) -> (W,H,C,N): main.cpp:750-768 (which assumes a square map and N=1)
+ggml_tensor * folding(ggml_context * ctx, ggml_tensor * tokens, int ps, int npw, int nph, int batch) {
+    const int64_t c = tokens->ne[0], n_patches = tokens->ne[1];
+    GGML_ASSERT(n_patches == (int64_t)npw * nph);
+    ggml_tensor * f = ggml_reshape_4d(ctx, tokens, c, n_patches, ps * ps, batch);
+    f               = ggml_cont(ctx, ggml_permute(ctx, f, 2, 1, 0, 3));  // (ps*ps, n_patches, c, n)
+    f               = ggml_reshape_4d(ctx, f, ps, ps, npw, (int64_t)nph * c * batch);
+    f               = ggml_cont(ctx, ggml_permute(ctx, f, 0, 2, 1, 3));  // (ps, npw, ps, nph*c*n)
+    return ggml_reshape_4d(ctx, f, (int64_t)ps * npw, (int64_t)ps * nph, c, batch);
+}
+
+static ggml_tensor * layer_norm(ggml_context * ctx, ggml_tensor * x, ggml_tensor * g, ggml_tensor * b, float eps) {
+    // main.cpp:1002-1019: norm * gamma + beta, then cont
+    ggml_tensor * y = ggml_mul(ctx, ggml_norm(ctx, x, eps), ggml_repeat(ctx, ggml_reshape_3d(ctx, g, g->ne[0], 1, 1), x));
+    y               = ggml_add(ctx, y, ggml_repeat(ctx, ggml_reshape_3d(ctx, b, b->ne[0], 1, 1), x));
+    return ggml_cont(ctx, y);
+}
+
+static ggml_tensor * dense(ggml_context * ctx, ggml_tensor * x, ggml_tensor * w, ggml_tensor * b) {
+    // file kernel is (in,out) == ggml ne (out,in); mul_mat wants K=in fastest: main.cpp:1022-1035
+    ggml_tensor * y = ggml_mul_mat(ctx, ggml_cont(ctx, ggml_permute(ctx, w, 1, 0, 2, 3)), x);
+    return ggml_add(ctx, y, ggml_repeat(ctx, ggml_reshape_3d(ctx, b, b->ne[0], 1, 1), y));
+}
+
+static ggml_tensor * split_heads(ggml_context * ctx, ggml_tensor * x, int heads) {  // transpose_for_score, main.cpp:975-986
+    GGML_ASSERT(x->ne[0] % heads == 0);
+    x = ggml_reshape_4d(ctx, x, x->ne[0] / heads, heads, x->ne[1], x->ne[2]);
+    return ggml_permute(ctx, x, 0, 2, 1, 3);  // (d, L, heads, B)
+}
+
+// pre-LN transformer layer: main.cpp:988-1172.  hidden: (C, L, B) with B = patch_area * N
+ggml_tensor * transformer_layer::forward(ggml_context * ctx, ggml_tensor * hidden, float eps, int heads) const {
+    const float   scale = sqrtf(1.0f * (float)(hidden->ne[0] / heads));  // main.cpp:999, used as a divisor (:1076)
+    ggml_tensor * x     = layer_norm(ctx, hidden, ln_before_g, ln_before_b, eps);
+    ggml_tensor * k     = split_heads(ctx, dense(ctx, x, k_w, k_b), heads);
+    ggml_tensor * v     = split_heads(ctx, dense(ctx, x, v_w, v_b), heads);
+    ggml_tensor * q     = split_heads(ctx, dense(ctx, x, q_w, q_b), heads);
+    ggml_tensor * score = ggml_soft_max(ctx, ggml_div(ctx, ggml_mul_mat(ctx, k, q), ggml_new_f32(ctx, scale)));  // (L,L,h,B)
+    ggml_tensor * att   = ggml_mul_mat(ctx, ggml_cont(ctx, ggml_permute(ctx, v, 1, 0, 2, 3)), score);             // (d,L,h,B)
+    att                 = ggml_cont(ctx, ggml_permute(ctx, att, 0, 2, 1, 3));                                       // (d,h,L,B)
+    att                 = ggml_reshape_3d(ctx, att, hidden->ne[0], hidden->ne[1], hidden->ne[2]);
+    hidden              = ggml_add(ctx, hidden, dense(ctx, att, o_w, o_b));  // main.cpp:1095-1111
+    ggml_tensor * y     = layer_norm(ctx, hidden, ln_after_g, ln_after_b, eps);
+    y                   = ggml_silu(ctx, dense(ctx, y, up_w, up_b));     // main.cpp:1134-1148
+    y                   = dense(ctx, y, down_w, down_b);                 // main.cpp:1151-1163
+    return ggml_add(ctx, y, hidden);                                     // main.cpp:1165
+}
+
+// main.cpp:1174-1223
+ggml_tensor * vit_block::forward(ggml_context * ctx, ggml_tensor * inp, const hparams & hp) const {
+    ggml_tensor * residual = downsampling.forward(ctx, inp);
+    ggml_tensor * x        = conv_kxk.forward(ctx, residual, 1, true, true, false);
+    x                      = conv_1x1.forward(ctx, x, 1, false, false, false);
+    const int ps = hp.patch_size;
+    const int npw = (int)x->ne[0] / ps, nph = (int)x->ne[1] / ps, batch = (int)x->ne[3];
+    x = unfolding(ctx, x, ps);                                              // (C, L, ps*ps, N)
+    x = ggml_reshape_3d(ctx, x, x->ne[0], x->ne[1], x->ne[2] * x->ne[3]);   // (C, L, ps*ps*N)
+    for (const transformer_layer & l : layers) x = l.forward(ctx, x, hp.layer_norm_eps, hp.num_attention_heads);
+    x = layer_norm(ctx, x, ln_g, ln_b, hp.layer_norm_eps);
+    x = folding(ctx, x, ps, npw, nph, batch);
+    x = conv_projection.forward(ctx, x, 1, true, true, false);
+    return fusion.forward(ctx, ggml_concat(ctx, residual, x), 1, true, true, false);
+}
+
+// extract_features' graph (main.cpp:604-646) for a batch.  `images_hwc` has ne=(3,W,H,N): the HWC->CHW copy
+// the reference does on the host (main.cpp:627-634) is a permute+cont in the graph here.
+ggml_tensor * model::build_forward(ggml_context * ctx, ggml_tensor * images_hwc, ggml_tensor ** pooled) const {
+    ggml_tensor * x = ggml_cont(ctx, ggml_permute(ctx, images_hwc, 2, 0, 1, 3));  // (W,H,3,N)
+    x               = conv_stem.forward(ctx, x, 2, true, true, false);
+    for (const inverted_residual & r : layer_1) x = r.forward(ctx, x);
+    for (const inverted_residual & r : layer_2) x = r.forward(ctx, x);
+    x = layer_3.forward(ctx, x, hp);
+    x = layer_4.forward(ctx, x, hp);
+    x = layer_5.forward(ctx, x, hp);
+    x = conv_1x1_exp.forward(ctx, x, 1, true, true, false);
+    if (pooled) *pooled = ggml_b200_pool_mean_hw(ctx, x);
+    return x;
+}
+
+forward_graph & model::graph_for(int n, int h, int w) {
+    auto key = std::make_tuple(n, h, w);
+    auto it  = graphs.find(key);
+    if (it != graphs.end()) return it->second;
+    forward_graph g;
+    const size_t in_bytes  = (size_t)n * h * w * 3 * sizeof(float);
+    const size_t out_bytes = (size_t)n * conv_1x1_exp.out_channels() * ((size_t)(h / 32) * (w / 32) + 1) * sizeof(float);
+    // the compute arena only holds tensor records, the input staging area and the output shadows:
+    // intermediates live in the device plan's arena (the reference needs 1 GiB per image, main.cpp:605)
+    ggml_init_params params = {in_bytes + out_bytes + (size_t)(24u << 20), nullptr, false};
+    g.ctx                   = ggml_init(params);
+    GGML_ASSERT(g.ctx != nullptr);
+    g.gf        = ggml_new_graph(g.ctx);
+    g.input_hwc = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, 3, w, h, n);
+    ggml_set_name(g.input_hwc, "inp");
+    ggml_set_input(g.input_hwc);
+    g.features = build_forward(g.ctx, g.input_hwc, &g.pooled);
+    ggml_set_name(g.features, "features");
+    ggml_set_name(g.pooled, "pooled");
+    ggml_build_forward_expand(g.gf, g.features);
+    ggml_build_forward_expand(g.gf, g.pooled);
+    return graphs.emplace(key, g).first->second;
+}
+
+void model::release(int n, int h, int w) {
+    auto it = graphs.find(std::make_tuple(n, h, w));
+    if (it == graphs.end()) return;
+    ggml_graph_release_plan(it->second.gf);
+    ggml_free(it->second.ctx);
+    graphs.erase(it);
+}
+
+}  // namespace mvit
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+struct mvit_model {
+    mvit::model m;
+};
+
+static bool shape_ok(int n, int h, int w) { return n > 0 && h > 0 && w > 0 && h % 32 == 0 && w % 32 == 0; }
+
+extern "C" mvit_model * mvit_load(const char * path) {
+    mvit_model * h = new mvit_model();
+    if (!h->m.load(path)) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+extern "C" void    mvit_free(mvit_model * m) { delete m; }
+extern "C" int     mvit_num_tensors(const mvit_model * m) { return (int)m->m.tensors.size(); }
+extern "C" int64_t mvit_num_weights(const mvit_model * m) { return m->m.total_weights; }
+extern "C" int     mvit_out_channels(const mvit_model * m) { return m->m.conv_1x1_exp.out_channels(); }
+
+extern "C" int mvit_compute(mvit_model * m, int n, int h, int w);
+
+extern "C" int mvit_extract_features(mvit_model * m, const float * images_hwc, int n, int h, int w, float * features,
+                                     float * pooled) {
+    if (!m || !images_hwc || !shape_ok(n, h, w)) return 1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    memcpy(ggml_get_data(g.input_hwc), images_hwc, ggml_nbytes(g.input_hwc));
+    mvit_compute(m, n, h, w);
+    if (features) memcpy(features, ggml_get_data(g.features), ggml_nbytes(g.features));
+    if (pooled) memcpy(pooled, ggml_get_data(g.pooled), ggml_nbytes(g.pooled));
+    return 0;
+}
+
+extern "C" float * mvit_host_input(mvit_model * m, int n, int h, int w) {
+    if (!m || !shape_ok(n, h, w)) return nullptr;
+    return (float *)ggml_get_data(m->m.graph_for(n, h, w).input_hwc);
+}
+extern "C" int mvit_compute(mvit_model * m, int n, int h, int w) {
+    if (!m || !shape_ok(n, h, w)) return 1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    if (g.gf->plan) ggml_b200_graph_set_transfers(g.gf, true, true);
+    ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
+    return 0;
+}
+extern "C" const float * mvit_host_features(mvit_model * m, int n, int h, int w) {
+    if (!m || !shape_ok(n, h, w)) return nullptr;
+    return (const float *)ggml_get_data(m->m.graph_for(n, h, w).features);
+}
+extern "C" const float * mvit_host_pooled(mvit_model * m, int n, int h, int w) {
+    if (!m || !shape_ok(n, h, w)) return nullptr;
+    return (const float *)ggml_get_data(m->m.graph_for(n, h, w).pooled);
+}
+extern "C" int mvit_profile_json(mvit_model * m, int n, int h, int w, int reps, char * buf, size_t cap) {
+    if (mvit_prepare(m, n, h, w)) return -1;
+    return ggml_b200_graph_profile_json(m->m.graph_for(n, h, w).gf, reps, buf, cap);
+}
+
+extern "C" int mvit_prepare(mvit_model * m, int n, int h, int w) {
+    if (!m || !shape_ok(n, h, w)) return 1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    ggml_b200_graph_prepare(g.ctx, g.gf);
+    return 0;
+}
+extern "C" void * mvit_device_input(mvit_model * m, int n, int h, int w) {
+    if (mvit_prepare(m, n, h, w)) return nullptr;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    return ggml_b200_tensor_get_device_data(g.gf, g.input_hwc);
+}
+extern "C" void * mvit_device_features(mvit_model * m, int n, int h, int w) {
+    if (mvit_prepare(m, n, h, w)) return nullptr;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    return ggml_b200_tensor_get_device_data(g.gf, g.features);
+}
+extern "C" void * mvit_device_pooled(mvit_model * m, int n, int h, int w) {
+    if (mvit_prepare(m, n, h, w)) return nullptr;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    return ggml_b200_tensor_get_device_data(g.gf, g.pooled);
+}
+extern "C" int mvit_forward_device(mvit_model * m, int n, int h, int w) {
+    if (mvit_prepare(m, n, h, w)) return 1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    ggml_b200_graph_set_transfers(g.gf, false, false);
+    ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
+    return 0;
+}
+extern "C" void mvit_release(mvit_model * m, int n, int h, int w) {
+    if (m) m->m.release(n, h, w);
+}
+extern "C" int mvit_plan_info(mvit_model * m, int n, int h, int w, struct mvit_plan_info * out) {
+    if (mvit_prepare(m, n, h, w)) return 1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    ggml_b200_plan_stats s;
+    ggml_b200_graph_plan_stats(g.gf, &s);
+    out->mode         = s.mode;
+    out->graph_nodes  = s.n_graph_nodes;
+    out->launches     = s.n_launches;
+    out->arena_bytes  = s.arena_bytes;
+    out->naive_bytes  = s.naive_bytes;
+    out->weight_bytes = s.weight_bytes;
+    out->cuda_graph   = s.used_cuda_graph;
+    return 0;
+}

@@ -48,7 +48,7 @@ typedef uint16_t ggml_fp16_t; /* main.cpp:929 */
 enum ggml_type {            /* main.cpp:612,907-916; rnn.cpp:42,284 */
     GGML_TYPE_F32 = 0,
     GGML_TYPE_F16 = 1,
-    GGML_TYPE_I32 = 26,     /* same numeric value as upstream */
+    GGML_TYPE_I32 = 26,
     GGML_TYPE_COUNT
 };
 
@@ -240,10 +240,23 @@ struct ggml_b200_plan_stats {
     int     used_cuda_graph;
 };
 void ggml_b200_graph_plan_stats(struct ggml_cgraph * cgraph, struct ggml_b200_plan_stats * out);
+/* Per-launch device times of the plan as a JSON array [{kernel, what, ms, flops, bytes}...] (direct launches
+ * timed with CUDA events).  Returns 0, -1 if there is no plan, or the needed capacity if `cap` is too small. */
+int ggml_b200_graph_profile_json(struct ggml_cgraph * cgraph, int reps, char * buf, size_t cap);
 /* Build (or fetch) the plan without running it. */
 void ggml_b200_graph_prepare(struct ggml_context * ctx, struct ggml_cgraph * cgraph);
 
 const char * ggml_b200_version(void);
+
+/* ---- single-kernel test entry points (host buffers in/out; used by tests/ only) ----------------------
+ * f16 arrays are passed as uint16_t bit patterns.  Return 0 on success, 1 if the shape is not supported. */
+/* out[M,N] = epilogue(A[M,K] * B[N,K]^T): tcgen05 GEMM (K1).  scale/shift/res32/out32/out16 may be NULL. */
+int ggml_b200_debug_gemm(const uint16_t * A, const uint16_t * B, int M, int N, int K, const float * scale,
+                         const float * shift, int act, const float * res32, float * out32, uint16_t * out16);
+/* 3x3 stride-1 pad-1 conv over NHWC f16 (x0: C0 ch, optional x1: C1 ch = fused concat), Wt [OC][3][3][C0+C1] */
+int ggml_b200_debug_conv3x3(const uint16_t * x0, int C0, const uint16_t * x1, int C1, int n_img, int H, int W,
+                            const uint16_t * Wt, int OC, const float * scale, const float * shift, int act,
+                            float * out32);
 
 #ifdef __cplusplus
 }

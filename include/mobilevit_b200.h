@@ -1,0 +1,73 @@
+/*
+ * mobilevit_b200.h -- C ABI of the host-side MobileViT program (ggml-experiments_b200/host/mobilevit.cpp).
+ *
+ * The reference's entry points are C++ methods of `mobilevit_model` in /root/reference/mobilevit/main.cpp;
+ * this header flattens them to plain C so that ctypes / cgo / JNI can bind them:
+ *
+ *   mvit_load              <- load_model_v2 + read_all_weights + assign_weights   (main.cpp:218-515,872-942)
+ *   mvit_extract_features  <- mobilevit_model::extract_features                    (main.cpp:604-646)
+ *   mvit_free              <- ggml_free(model.ctx_w)                               (main.cpp:699)
+ *
+ * extract_features is generalised from the reference's hard-coded (256,256,3,1) input (main.cpp:612) to a
+ * batch of N images of H x W (multiples of 32).  The graph is still built from ggml_* calls
+ * (include/ggml/ggml.h) and runs through ggml_graph_compute_with_ctx on the GPU; there is no CPU path.
+ */
+#ifndef MOBILEVIT_B200_H
+#define MOBILEVIT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mvit_model mvit_model;
+
+/* Parse a weight file in the convert-tf-to-ggml.py layout. Returns NULL if the file cannot be opened or
+ * is malformed; aborts (std::out_of_range in the reference, main.cpp:225) if a required tensor is missing. */
+mvit_model * mvit_load(const char * weight_path);
+void         mvit_free(mvit_model * m);
+
+int     mvit_num_tensors(const mvit_model * m);   /* 313 for every variant */
+int64_t mvit_num_weights(const mvit_model * m);   /* floats in the file */
+int     mvit_out_channels(const mvit_model * m);  /* 640 / 384 / 320 for S / XS / XXS */
+
+/* images_hwc: N*H*W*3 floats in [0,1], HWC per image (sam_image_f32, main.cpp:22-27).
+ * features  : N*C*(H/32)*(W/32) floats, per image the ggml tensor ne=(W/32,H/32,C,1) the reference returns
+ *             (main.cpp:645), i.e. [N][C][H/32][W/32]; may be NULL.
+ * pooled    : N*C floats, mean of the feature map over space (the build's "logits"); may be NULL.
+ * Returns 0 on success, non-zero for invalid arguments (n <= 0, H or W not a multiple of 32). */
+int mvit_extract_features(mvit_model * m, const float * images_hwc, int n, int h, int w, float * features, float * pooled);
+
+/* ---- zero-copy host variant: the reference's own flow (write inp->data, compute, read output->data;
+ * main.cpp:627-634,640,703).  The host buffers belong to the library (pinned); valid until mvit_release. ---- */
+float * mvit_host_input(mvit_model * m, int n, int h, int w);      /* [N,H,W,3] f32, fill in place */
+int     mvit_compute(mvit_model * m, int n, int h, int w);         /* H2D + forward + D2H, synchronous */
+const float * mvit_host_features(mvit_model * m, int n, int h, int w);  /* [N,C,H/32,W/32] after mvit_compute */
+const float * mvit_host_pooled(mvit_model * m, int n, int h, int w);    /* [N,C] after mvit_compute */
+
+/* ---- device-resident variant (bench.py `value`): inputs/outputs stay in HBM -------------------------- */
+int    mvit_prepare(mvit_model * m, int n, int h, int w);           /* build graph + device plan; 0 on success */
+void * mvit_device_input(mvit_model * m, int n, int h, int w);      /* device ptr, [N,H,W,3] f32 */
+void * mvit_device_features(mvit_model * m, int n, int h, int w);   /* device ptr, [N,C,H/32,W/32] f32 */
+void * mvit_device_pooled(mvit_model * m, int n, int h, int w);     /* device ptr, [N,C] f32 */
+int    mvit_forward_device(mvit_model * m, int n, int h, int w);    /* async launch on the library stream */
+void   mvit_release(mvit_model * m, int n, int h, int w);           /* drop the cached graph/plan for a shape */
+
+struct mvit_plan_info {
+    int     mode;          /* 0 fast, 1 exact (enum ggml_b200_mode) */
+    int     graph_nodes;
+    int     launches;      /* kernel launches per forward */
+    int64_t arena_bytes;   /* device activation arena after liveness planning */
+    int64_t naive_bytes;   /* what keeping every intermediate alive (the reference's arena) would need */
+    int64_t weight_bytes;
+    int     cuda_graph;
+};
+int mvit_plan_info(mvit_model * m, int n, int h, int w, struct mvit_plan_info * out);
+/* JSON array of per-launch device times, see ggml_b200_graph_profile_json. */
+int mvit_profile_json(mvit_model * m, int n, int h, int w, int reps, char * buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,122 @@
+"""CPU tests: the oracle against the HF-torch golden fixtures (tests/golden, made by tests/gen_golden.py),
+op-level checks of the oracle against numpy, and weight-file round trips."""
+import os
+
+import numpy as np
+import pytest
+
+from ggml_experiments_b200 import weights as W
+from tests.util import parity_report
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("variant,hw", [("xxs", 256), ("xs", 256), ("s", 256), ("xxs", 128)])
+def test_oracle_matches_hf_golden(oracle, weight_files, variant, hw):
+    g = np.load(os.path.join(GOLD, f"hf_{variant}_{hw}.npz"))
+    m = oracle.OracleModel(weight_files[variant])
+    assert m.num_tensors == 313
+    imgs = W.synthetic_images(int(g["n_img"]), hw, hw, seed=7)
+    st = int(g["feat_stride"])
+    # pure-f32 mode == HF torch semantics: only accumulation-order noise is allowed
+    f32, p32 = m.forward(imgs, oracle.PURE_F32)
+    r = parity_report(f32[:, ::st], g["feat"], rtol=1e-4, atol_rms=1e-4)
+    assert r["violations"] == 0 and r["rel_l2"] < 2e-5, r
+    assert np.abs(p32 - g["pooled"]).max() < 1e-4
+    # ggml-faithful mode differs from HF only by the f16 rounding points of the conv path
+    f16, p16 = m.forward(imgs, 0)
+    r = parity_report(f16[:, ::st], g["feat"], rtol=5e-2, atol_rms=5e-2)
+    assert r["rel_l2"] < 6e-3, r
+    assert (p16.argmax(1) == g["pooled"].argmax(1)).all()
+
+
+def test_weight_counts_match_survey(weight_files, oracle):
+    # 313 tensors; 4 949 888 / 1 941 296 / 955 136 floats
+    expect = {"s": 4949888, "xs": 1941296, "xxs": 955136}
+    for v, n in expect.items():
+        m = oracle.OracleModel(weight_files[v])
+        assert (m.num_tensors, m.num_weights) == (313, n)
+
+
+def test_weight_file_roundtrip(tmp_path):
+    t = W.make_synthetic_weights("xxs", seed=3)
+    p = str(tmp_path / "w.ggml")
+    W.write_weight_file(p, t)
+    back = W.read_weight_file(p)
+    assert list(back.keys()) == list(t.keys())
+    for k in t:
+        assert back[k].shape == t[k].shape and np.array_equal(back[k], t[k])
+
+
+def test_reference_test_image_pattern():
+    # main.cpp:680-688: img[y*768 + x*3 + c] = ((y*768 + x*3 + c) % 256) / 255
+    img = W.synthetic_images(1)[0]
+    y, x, c = 17, 201, 2
+    assert img[y, x, c] == np.float32(((y * 768 + x * 3 + c) % 256) / 255.0)
+
+
+def test_oracle_unfold_fold_roundtrip_and_layout(oracle):
+    import ctypes
+    L = oracle.lib()
+    C, H, Wd, ps = 5, 8, 12, 2
+    x = np.arange(C * H * Wd, dtype=np.float32).reshape(C, H, Wd)
+    tok = np.empty(C * H * Wd, dtype=np.float32)
+    f32p = ctypes.POINTER(ctypes.c_float)
+    L.mvo_unfold(x.ctypes.data_as(f32p), C, H, Wd, ps, tok.ctypes.data_as(f32p))
+    tok = tok.reshape(ps * ps, (H // ps) * (Wd // ps), C)  # [P][L][C]
+    # HF MobileViTLayer.unfolding: patch p = (ph, pw), token l = (iph, ipw)
+    for p in range(4):
+        ph, pw = divmod(p, 2)
+        for l in (0, 5, 23):
+            iph, ipw = divmod(l, Wd // ps)
+            assert np.array_equal(tok[p, l], x[:, iph * ps + ph, ipw * ps + pw])
+    # fold is square-only in the reference (main.cpp:754)
+    C, H = 3, 8
+    x = np.random.default_rng(0).normal(size=(C, H, H)).astype(np.float32)
+    tok = np.empty_like(x).ravel()
+    back = np.empty_like(x)
+    L.mvo_unfold(x.ctypes.data_as(f32p), C, H, H, 2, tok.ctypes.data_as(f32p))
+    L.mvo_fold(tok.ctypes.data_as(f32p), C, (H // 2) ** 2, 2, back.ctypes.data_as(f32p))
+    assert np.array_equal(back, x)
+
+
+def test_oracle_conv_matches_numpy_f16_semantics(oracle):
+    import ctypes
+    L = oracle.lib()
+    f32p = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(1)
+    C, H, Wd, OC = 6, 9, 7, 5
+    x = rng.normal(size=(C, H, Wd)).astype(np.float32)
+    k = rng.normal(size=(3, 3, C, OC)).astype(np.float32)  # TF layout
+    for stride in (1, 2):
+        OH, OW = (H + 2 - 3) // stride + 1, (Wd + 2 - 3) // stride + 1
+        out = np.empty((OC, OH, OW), dtype=np.float32)
+        L.mvo_conv2d(x.ctypes.data_as(f32p), C, H, Wd, k.ctypes.data_as(f32p), 3, 3, OC, stride, out.ctypes.data_as(f32p), 0)
+        xr = x.astype(np.float16).astype(np.float64)
+        kr = k.astype(np.float16).astype(np.float64)
+        xp = np.pad(xr, ((0, 0), (1, 1), (1, 1)))
+        ref = np.zeros((OC, OH, OW))
+        for oy in range(OH):
+            for ox in range(OW):
+                patch = xp[:, oy * stride:oy * stride + 3, ox * stride:ox * stride + 3]  # [C,3,3]
+                ref[:, oy, ox] = np.einsum("chw,hwco->o", patch, kr)
+        assert np.abs(out - ref).max() < 1e-4
+
+
+def test_oracle_layernorm_softmax(oracle):
+    import ctypes
+    L = oracle.lib()
+    f32p = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(7, 24)).astype(np.float32)
+    g = rng.normal(size=24).astype(np.float32)
+    b = rng.normal(size=24).astype(np.float32)
+    y = np.empty_like(x)
+    L.mvo_layernorm(x.ctypes.data_as(f32p), 24, 7, g.ctypes.data_as(f32p), b.ctypes.data_as(f32p), 1e-5, y.ctypes.data_as(f32p))
+    xd = x.astype(np.float64)
+    ref = (xd - xd.mean(1, keepdims=True)) / np.sqrt(xd.var(1, keepdims=True) + 1e-5) * g + b
+    assert np.abs(y - ref).max() < 1e-5
+    s = x.copy()
+    L.mvo_softmax_rows(s.ctypes.data_as(f32p), 24, 7)
+    e = np.exp(xd - xd.max(1, keepdims=True))
+    assert np.abs(s - e / e.sum(1, keepdims=True)).max() < 1e-6
