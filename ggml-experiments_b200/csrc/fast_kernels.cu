@@ -1,0 +1,400 @@
+// fast_kernels.cu -- memory-bound kernels of the FAST plan: vectorised, coalesced NHWC f16 (SURVEY.md K2,K3,K5,K7,K9).
+// Rounding points follow ggml: conv inputs are f16, accumulation and BatchNorm/SiLU/LayerNorm/softmax are f32.
+#include "fast_kernels.h"
+
+#include "internal.h"
+
+namespace b200 {
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+struct alignas(16) Half8 {
+    __half2 h[4];
+};
+__device__ __forceinline__ void unpack8(const Half8 & v, float * f) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t     = __half22float2(v.h[i]);
+        f[2 * i]     = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ Half8 pack8(const float * f) {
+    Half8 v;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 stem: replaces ggml_conv_2d (im2col f16 + mul_mat) + BN chain + silu of conv_stem (main.cpp:618,771-852)
+// One thread = one output pixel, all OC channels (OC <= 32).  HBM-bound: 12 B/pixel in (x9 from L1/L2), 2*OC B out.
+// ---------------------------------------------------------------------------------------------------------
+template <int OC>
+__global__ void __launch_bounds__(256) k_stem(const float * __restrict__ x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N,
+                                              int H, int W, const __half * __restrict__ Wt, const float * __restrict__ scale,
+                                              const float * __restrict__ shift, int act, __half * __restrict__ out16,
+                                              float * __restrict__ out32) {
+    __shared__ float sw[27 * OC];  // [tap*3+ic][oc]
+    __shared__ float ss[OC], sh[OC];
+    for (int i = threadIdx.x; i < 27 * OC; i += blockDim.x) {
+        int k = i / OC, oc = i % OC;  // k = (kh*3+kw)*3+ic ; Wt is [oc][kh][kw][ic]
+        sw[i] = __half2float(Wt[oc * 27 + k]);
+    }
+    for (int i = threadIdx.x; i < OC; i += blockDim.x) {
+        ss[i] = scale ? scale[i] : 1.f;
+        sh[i] = shift ? shift[i] : 0.f;
+    }
+    __syncthreads();
+    const int     OH = H / 2, OW = W / 2;
+    const int64_t total = (int64_t)N * OH * OW;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(p % OW), oy = (int)((p / OW) % OH);
+        const int n  = (int)(p / ((int64_t)OW * OH));
+        float acc[OC];
+#pragma unroll
+        for (int o = 0; o < OC; o++) acc[o] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; kh++) {
+            const int iy = oy * 2 + kh - 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++) {
+                const int ix = ox * 2 + kw - 1;
+                if (ix < 0 || ix >= W) continue;
+                const float * px = x + n * sn + iy * sy + ix * sx;
+#pragma unroll
+                for (int ic = 0; ic < 3; ic++) {
+                    const float   v = __half2float(__float2half_rn(px[ic * sc]));  // ggml im2col rounds activations to f16
+                    const float * w = &sw[((kh * 3 + kw) * 3 + ic) * OC];
+#pragma unroll
+                    for (int o = 0; o < OC; o++) acc[o] = fmaf(v, w[o], acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < OC; o++) {
+            float y = fmaf(acc[o], ss[o], sh[o]);
+            acc[o]  = act ? silu_fast(y) : y;
+        }
+        if (out16) {
+            Half8 * o = reinterpret_cast<Half8 *>(out16 + p * OC);
+#pragma unroll
+            for (int g = 0; g < OC / 8; g++) o[g] = pack8(acc + g * 8);
+        }
+        if (out32) {
+            float4 * o = reinterpret_cast<float4 *>(out32 + p * OC);
+#pragma unroll
+            for (int g = 0; g < OC / 4; g++) o[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+        }
+    }
+}
+
+void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W, const __half * Wt, int OC,
+                 const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st) {
+    const int64_t total = (int64_t)N * (H / 2) * (W / 2);
+    int64_t       nb    = (total + 255) / 256;
+    const int64_t cap   = (int64_t)runtime().sm_count * 32;
+    const int     grid  = (int)(nb > cap ? cap : nb);
+    switch (OC) {
+        case 8: k_stem<8><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
+        case 16: k_stem<16><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
+        case 24: k_stem<24><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
+        case 32: k_stem<32><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
+        default: B200_ABORT("stem: unsupported OC %d", OC);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3 depthwise 3x3 + BN + SiLU: replaces ggml_conv_depthwise_2d + BN chain + silu (main.cpp:788,809-850).
+// thread = (8-channel group, output pixel); 128-bit loads/stores; adjacent threads -> adjacent channel groups of the
+// same pixel -> fully coalesced rows of C*2 bytes.  Per-thread weights/scale/shift live in registers across pixels.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dwconv(const __half * __restrict__ x, int N, int H, int W, int C, int stride,
+                                                const __half * __restrict__ Wt, const float * __restrict__ scale,
+                                                const float * __restrict__ shift, int act, __half * __restrict__ out) {
+    const int cgs = C / 8;                       // channel groups
+    const int cg  = threadIdx.x % cgs;           // blockDim.x is a multiple of cgs
+    const int ppb = blockDim.x / cgs;            // pixels per block-iteration
+    const int pl  = threadIdx.x / cgs;
+    const int OH = H / stride, OW = W / stride;  // pad 1, k 3: (H + 2 - 3)/s + 1 == H/s for even H (s=2) and == H (s=1)
+    float w[9][8], sc[8], sh[8];
+#pragma unroll
+    for (int t = 0; t < 9; t++) unpack8(*reinterpret_cast<const Half8 *>(Wt + t * C + cg * 8), w[t]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        sc[j] = scale ? scale[cg * 8 + j] : 1.f;
+        sh[j] = shift ? shift[cg * 8 + j] : 0.f;
+    }
+    const int64_t total = (int64_t)N * OH * OW;
+    for (int64_t p = (int64_t)blockIdx.x * ppb + pl; p < total; p += (int64_t)gridDim.x * ppb) {
+        const int ox = (int)(p % OW), oy = (int)((p / OW) % OH);
+        const int n  = (int)(p / ((int64_t)OW * OH));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; kh++) {
+            const int iy = oy * stride + kh - 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++) {
+                const int ix = ox * stride + kw - 1;
+                if (ix < 0 || ix >= W) continue;
+                float v[8];
+                unpack8(*reinterpret_cast<const Half8 *>(x + (((int64_t)n * H + iy) * W + ix) * C + cg * 8), v);
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(v[j], w[kh * 3 + kw][j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float y = fmaf(acc[j], sc[j], sh[j]);
+            acc[j]  = act ? silu_fast(y) : y;
+        }
+        *reinterpret_cast<Half8 *>(out + p * C + cg * 8) = pack8(acc);
+    }
+}
+
+void launch_dwconv(const __half * x, int N, int H, int W, int C, int stride, const __half * Wt, const float * scale,
+                   const float * shift, int act, __half * out16, cudaStream_t st) {
+    if (C % 8) B200_ABORT("dwconv: C %% 8 != 0");
+    const int cgs     = C / 8;
+    int       threads = (256 / cgs) * cgs;
+    if (threads == 0) threads = cgs;  // C > 2048 never happens here
+    const int     ppb   = threads / cgs;
+    const int64_t total = (int64_t)N * (H / stride) * (W / stride);
+    int64_t       nb    = (total + ppb - 1) / ppb;
+    const int64_t cap   = (int64_t)runtime().sm_count * 16;
+    const int     grid  = (int)(nb > cap ? cap : nb);
+    k_dwconv<<<grid, threads, 0, st>>>(x, N, H, W, C, stride, Wt, scale, shift, act, out16);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5 LayerNorm: replaces ggml_norm + mul(gamma) + add(beta) + cont (main.cpp:1002-1019,1114-1131,1192-1209).
+// One warp per row, the row lives in registers (C <= 512), two-pass mean / variance with warp-shuffle reductions.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_layernorm(const float * __restrict__ x, int64_t rows, int C, const float * __restrict__ gamma,
+                                                   const float * __restrict__ beta, float eps, __half * __restrict__ out16,
+                                                   float * __restrict__ out32) {
+    const int     lane = threadIdx.x & 31;
+    const int64_t row  = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float * xr = x + row * C;
+    constexpr int MAXV = 4;  // float4 per lane: C <= 512
+    float4        v[MAXV];
+    const int     nv = C / 4;  // C % 4 == 0 (channels are multiples of 8)
+    float         s  = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++) {
+        const int idx = lane + i * 32;
+        if (idx < nv) {
+            v[i] = reinterpret_cast<const float4 *>(xr)[idx];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float       s2   = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++) {
+        const int idx = lane + i * 32;
+        if (idx < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            s2 += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(s2) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; i++) {
+        const int idx = lane + i * 32;
+        if (idx < nv) {
+            const float4 g = reinterpret_cast<const float4 *>(gamma)[idx];
+            const float4 b = reinterpret_cast<const float4 *>(beta)[idx];
+            float4       y;
+            y.x = fmaf(v[i].x * rstd, g.x, b.x);
+            y.y = fmaf(v[i].y * rstd, g.y, b.y);
+            y.z = fmaf(v[i].z * rstd, g.z, b.z);
+            y.w = fmaf(v[i].w * rstd, g.w, b.w);
+            if (out32) reinterpret_cast<float4 *>(out32 + row * C)[idx] = y;
+            if (out16) {
+                __half2 * o = reinterpret_cast<__half2 *>(out16 + row * C) + idx * 2;
+                o[0]        = __floats2half2_rn(y.x, y.y);
+                o[1]        = __floats2half2_rn(y.z, y.w);
+            }
+        }
+    }
+}
+
+void launch_layernorm(const float * x, int64_t rows, int C, const float * gamma, const float * beta, float eps, __half * out16,
+                      float * out32, cudaStream_t st) {
+    if (C % 4 || C > 512) B200_ABORT("layernorm: unsupported C %d", C);
+    const int grid = (int)((rows + 7) / 8);
+    k_layernorm<<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out16, out32);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K7 attention, version 1 (CUDA cores, f32 math, online softmax).
+// Replaces mul_mat(K,Q) / sqrt(d) -> soft_max -> mul_mat(V^T, P) and the surrounding permutes/conts
+// (main.cpp:975-986,1073-1093).  One CTA = one (image, patch position, head); K and V of the sequence are staged
+// in shared memory as f32 in chunks of up to KCH keys; one thread owns one query row (q, o, m, l in registers).
+// ---------------------------------------------------------------------------------------------------------
+template <int DMAX>
+__global__ void __launch_bounds__(128) k_attention_v1(const __half * __restrict__ qkv, int N, int H, int W, int C, int heads,
+                                                      __half * __restrict__ out, int kch) {
+    extern __shared__ float smem_f[];
+    const int d    = C / heads;
+    const int npw = W / 2, nph = H / 2, L = npw * nph;
+    const int head = blockIdx.x % heads;
+    const int pp   = (blockIdx.x / heads) % 4;  // patch position ph*2+pw
+    const int n    = blockIdx.x / (heads * 4);
+    const int ph = pp >> 1, pw = pp & 1;
+    float * sK = smem_f;                 // [kch][d]
+    float * sV = smem_f + (size_t)kch * d;
+    const float   scale = rsqrtf((float)d);
+    const int64_t ld    = 3 * (int64_t)C;
+    auto tok = [&](int l) -> int64_t {  // token l of this sequence -> pixel row
+        const int iph = l / npw, ipw = l % npw;
+        return ((int64_t)n * H + (iph * 2 + ph)) * W + (ipw * 2 + pw);
+    };
+    for (int q0 = 0; q0 < L; q0 += blockDim.x) {
+        const int  qi     = q0 + threadIdx.x;
+        const bool active = qi < L;
+        float q[DMAX], o[DMAX];
+        float m = -INFINITY, l = 0.f;
+        if (active) {
+            const __half * qp = qkv + tok(qi) * ld + head * d;
+#pragma unroll
+            for (int e = 0; e < DMAX; e++) {
+                q[e] = e < d ? __half2float(qp[e]) * scale : 0.f;
+                o[e] = 0.f;
+            }
+        }
+        for (int k0 = 0; k0 < L; k0 += kch) {
+            const int kn = min(kch, L - k0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < kn * d; i += blockDim.x) {
+                const int      j = i / d, e = i % d;
+                const __half * kp = qkv + tok(k0 + j) * ld + C + head * d;
+                sK[i] = __half2float(kp[e]);
+                sV[i] = __half2float(kp[C + e]);
+            }
+            __syncthreads();
+            if (active) {
+                for (int j = 0; j < kn; j++) {
+                    const float * kr = sK + j * d;
+                    float         s  = 0.f;
+#pragma unroll
+                    for (int e = 0; e < DMAX; e++)
+                        if (e < d) s = fmaf(q[e], kr[e], s);
+                    const float mn = fmaxf(m, s);
+                    const float c  = __expf(m - mn);
+                    const float p  = __expf(s - mn);
+                    l              = l * c + p;
+                    m              = mn;
+                    const float * vr = sV + j * d;
+#pragma unroll
+                    for (int e = 0; e < DMAX; e++)
+                        if (e < d) o[e] = fmaf(o[e], c, p * vr[e]);
+                }
+            }
+        }
+        if (active) {
+            const float inv = 1.f / l;
+            __half *    op  = out + tok(qi) * (int64_t)C + head * d;
+#pragma unroll
+            for (int e = 0; e < DMAX; e++)
+                if (e < d) op[e] = __float2half_rn(o[e] * inv);
+        }
+    }
+}
+
+void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads, __half * out16, cudaStream_t st) {
+    const int d = C / heads;
+    const int L = (H / 2) * (W / 2);
+    int       kch = L < 256 ? L : 256;
+    size_t    smem = (size_t)2 * kch * d * sizeof(float);
+    const int grid = N * 4 * heads;
+    static bool attr = false;
+    if (!attr) {
+        B200_CHECK(cudaFuncSetAttribute(k_attention_v1<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_attention_v1<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    if (d <= 32) k_attention_v1<32><<<grid, 128, smem, st>>>(qkv, N, H, W, C, heads, out16, kch);
+    else if (d <= 64) k_attention_v1<64><<<grid, 128, smem, st>>>(qkv, N, H, W, C, heads, out16, kch);
+    else B200_ABORT("attention: head dim %d > 64", d);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_add(const float4 * __restrict__ a, const float4 * __restrict__ b, int64_t n4, float4 * __restrict__ o32,
+                      __half2 * __restrict__ o16) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = a[i], y = b[i];
+        const float4 z = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        if (o32) o32[i] = z;
+        if (o16) {
+            o16[2 * i]     = __floats2half2_rn(z.x, z.y);
+            o16[2 * i + 1] = __floats2half2_rn(z.z, z.w);
+        }
+    }
+}
+void launch_add(const float * a, const float * b, int64_t n, float * out32, __half * out16, cudaStream_t st) {
+    if (n % 4) B200_ABORT("add: n %% 4 != 0");
+    const int64_t n4 = n / 4;
+    int64_t       nb = (n4 + 255) / 256;
+    const int64_t cap = (int64_t)runtime().sm_count * 16;
+    k_add<<<(int)(nb > cap ? cap : nb), 256, 0, st>>>((const float4 *)a, (const float4 *)b, n4, (float4 *)out32, (__half2 *)out16);
+}
+
+// NHWC -> [W,H,C,N] f32 via a 32x32 smem transpose of (pixel, channel) per image
+__global__ void k_nhwc_to_nchw(const __half * __restrict__ x16, const float * __restrict__ x32, int HW, int C, float * __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int     n  = blockIdx.z;
+    const int     p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int64_t base = (int64_t)n * HW * C;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        float     v = 0.f;
+        if (p < HW && c < C) v = x32 ? x32[base + (int64_t)p * C + c] : __half2float(x16[base + (int64_t)p * C + c]);
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        if (p < HW && c < C) out[base + (int64_t)c * HW + p] = tile[threadIdx.x][r];
+    }
+}
+void launch_nhwc_to_nchw(const __half * x16, const float * x32, int N, int H, int W, int C, float * out, cudaStream_t st) {
+    const int HW = H * W;
+    dim3      grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    k_nhwc_to_nchw<<<grid, block, 0, st>>>(x16, x32, HW, C, out);
+}
+
+__global__ void k_pool_mean(const __half * __restrict__ x16, const float * __restrict__ x32, int HW, int C, float * __restrict__ out) {
+    const int n = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int64_t base = (int64_t)n * HW * C + c;
+    float         s    = 0.f;
+    for (int p = 0; p < HW; p++) s += x32 ? x32[base + (int64_t)p * C] : __half2float(x16[base + (int64_t)p * C]);
+    out[(int64_t)n * C + c] = s / (float)HW;
+}
+void launch_pool_mean(const __half * x16, const float * x32, int N, int HW, int C, float * out, cudaStream_t st) {
+    dim3 grid((C + 127) / 128, N);
+    k_pool_mean<<<grid, 128, 0, st>>>(x16, x32, HW, C, out);
+}
+
+}  // namespace b200

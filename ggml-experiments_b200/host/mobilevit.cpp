@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 
@@ -260,15 +261,24 @@ ggml_tensor * vit_block::forward(ggml_context * ctx, ggml_tensor * inp, const hp
 
 // extract_features' graph (main.cpp:604-646) for a batch.  `images_hwc` has ne=(3,W,H,N): the HWC->CHW copy
 // the reference does on the host (main.cpp:627-634) is a permute+cont in the graph here.
-ggml_tensor * model::build_forward(ggml_context * ctx, ggml_tensor * images_hwc, ggml_tensor ** pooled) const {
+ggml_tensor * model::build_forward(ggml_context * ctx, ggml_tensor * images_hwc, ggml_tensor ** pooled,
+                                   std::vector<ggml_tensor *> * stages) const {
+    auto tap = [&](ggml_tensor * t) { if (stages) stages->push_back(t); };
     ggml_tensor * x = ggml_cont(ctx, ggml_permute(ctx, images_hwc, 2, 0, 1, 3));  // (W,H,3,N)
     x               = conv_stem.forward(ctx, x, 2, true, true, false);
+    tap(x);
     for (const inverted_residual & r : layer_1) x = r.forward(ctx, x);
+    tap(x);
     for (const inverted_residual & r : layer_2) x = r.forward(ctx, x);
+    tap(x);
     x = layer_3.forward(ctx, x, hp);
+    tap(x);
     x = layer_4.forward(ctx, x, hp);
+    tap(x);
     x = layer_5.forward(ctx, x, hp);
+    tap(x);
     x = conv_1x1_exp.forward(ctx, x, 1, true, true, false);
+    tap(x);
     if (pooled) *pooled = ggml_b200_pool_mean_hw(ctx, x);
     return x;
 }
@@ -279,7 +289,10 @@ forward_graph & model::graph_for(int n, int h, int w) {
     if (it != graphs.end()) return it->second;
     forward_graph g;
     const size_t in_bytes  = (size_t)n * h * w * 3 * sizeof(float);
-    const size_t out_bytes = (size_t)n * conv_1x1_exp.out_channels() * ((size_t)(h / 32) * (w / 32) + 1) * sizeof(float);
+    size_t out_bytes = (size_t)n * conv_1x1_exp.out_channels() * ((size_t)(h / 32) * (w / 32) + 1) * sizeof(float);
+    const char * dbg = getenv("MVIT_DEBUG_STAGES");
+    const bool   debug_stages = dbg && atoi(dbg) > 0;
+    if (debug_stages) out_bytes += (size_t)n * h * w * 16 * sizeof(float);  // all stage taps together are < 16 floats per input pixel
     // the compute arena only holds tensor records, the input staging area and the output shadows:
     // intermediates live in the device plan's arena (the reference needs 1 GiB per image, main.cpp:605)
     ggml_init_params params = {in_bytes + out_bytes + (size_t)(24u << 20), nullptr, false};
@@ -289,11 +302,13 @@ forward_graph & model::graph_for(int n, int h, int w) {
     g.input_hwc = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, 3, w, h, n);
     ggml_set_name(g.input_hwc, "inp");
     ggml_set_input(g.input_hwc);
-    g.features = build_forward(g.ctx, g.input_hwc, &g.pooled);
+    g.features = build_forward(g.ctx, g.input_hwc, &g.pooled, &g.stages);
     ggml_set_name(g.features, "features");
     ggml_set_name(g.pooled, "pooled");
     ggml_build_forward_expand(g.gf, g.features);
     ggml_build_forward_expand(g.gf, g.pooled);
+    if (debug_stages)
+        for (ggml_tensor * t : g.stages) ggml_build_forward_expand(g.gf, t);  // marks them as outputs -> host shadows
     return graphs.emplace(key, g).first->second;
 }
 
@@ -364,6 +379,19 @@ extern "C" const float * mvit_host_pooled(mvit_model * m, int n, int h, int w) {
 extern "C" int mvit_profile_json(mvit_model * m, int n, int h, int w, int reps, char * buf, size_t cap) {
     if (mvit_prepare(m, n, h, w)) return -1;
     return ggml_b200_graph_profile_json(m->m.graph_for(n, h, w).gf, reps, buf, cap);
+}
+
+// debug: copy stage tap `idx` (0 stem, 1..5 layers, 6 exp) as [N][C][H][W] floats; needs MVIT_DEBUG_STAGES=1 and a compute
+extern "C" int64_t mvit_debug_stage(mvit_model * m, int n, int h, int w, int idx, float * out, int64_t cap_floats, int64_t * ne4) {
+    if (!m || !shape_ok(n, h, w)) return -1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    if (idx < 0 || idx >= (int)g.stages.size()) return -1;
+    ggml_tensor * t = g.stages[idx];
+    for (int i = 0; i < 4; i++) ne4[i] = t->ne[i];
+    const int64_t cnt = ggml_nelements(t);
+    if (!t->data || cnt > cap_floats) return -2;
+    memcpy(out, t->data, (size_t)cnt * sizeof(float));
+    return cnt;
 }
 
 extern "C" int mvit_prepare(mvit_model * m, int n, int h, int w) {

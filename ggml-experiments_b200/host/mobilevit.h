@@ -62,6 +62,7 @@ struct forward_graph {
     ggml_tensor *  input_hwc = nullptr;  // ne = (3, W, H, N): the caller's HWC images, uploaded as they are
     ggml_tensor *  features  = nullptr;  // ne = (W/32, H/32, C, N)
     ggml_tensor *  pooled    = nullptr;  // ne = (1, 1, C, N)
+    std::vector<ggml_tensor *> stages;   // stem, layer_1..layer_5, conv_1x1_exp outputs (debug taps, MVIT_DEBUG_STAGES=1)
 };
 
 struct model {  // mobilevit_model, main.cpp:202-213
@@ -76,7 +77,8 @@ struct model {  // mobilevit_model, main.cpp:202-213
 
     bool            load(const std::string & path);                  // load_model_v2, main.cpp:314-515
     forward_graph & graph_for(int n, int h, int w);                  // builds (once) the batched forward graph
-    ggml_tensor *   build_forward(ggml_context * ctx, ggml_tensor * images_hwc, ggml_tensor ** pooled) const;
+    ggml_tensor *   build_forward(ggml_context * ctx, ggml_tensor * images_hwc, ggml_tensor ** pooled,
+                                  std::vector<ggml_tensor *> * stages = nullptr) const;
     void            release(int n, int h, int w);
     ~model();
 };

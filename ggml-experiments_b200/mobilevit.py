@@ -79,6 +79,9 @@ def lib_mobilevit() -> ctypes.CDLL:
         L.mvit_compute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.mvit_profile_json.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_char_p, ctypes.c_size_t]
+        L.mvit_debug_stage.restype = ctypes.c_int64
+        L.mvit_debug_stage.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p,
+                                       ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
         L.mvit_release.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.mvit_plan_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PlanInfo)]
         _mv = L
@@ -137,6 +140,16 @@ class MobileViT:
         f = np.ctypeslib.as_array(self._L.mvit_host_features(self._h, n, h, w), shape=(n, c, h // 32, w // 32))
         p = np.ctypeslib.as_array(self._L.mvit_host_pooled(self._h, n, h, w), shape=(n, c))
         return f, p
+
+    def debug_stage(self, n, h, w, idx) -> np.ndarray:
+        """Stage tap idx as [N,C,H,W] (needs MVIT_DEBUG_STAGES=1 in the environment before the shape is first used)."""
+        ne = (ctypes.c_int64 * 4)()
+        cap = n * h * w * 16
+        buf = np.empty(cap, dtype=np.float32)
+        cnt = self._L.mvit_debug_stage(self._h, n, h, w, idx, buf.ctypes.data_as(_f32p), cap, ne)
+        if cnt < 0:
+            raise RuntimeError(f"mvit_debug_stage rc={cnt}")
+        return buf[:cnt].reshape(ne[3], ne[2], ne[1], ne[0]).copy()
 
     def profile(self, n, h, w, reps: int = 3) -> list:
         import json

@@ -67,6 +67,11 @@ int mvit_plan_info(mvit_model * m, int n, int h, int w, struct mvit_plan_info * 
 /* JSON array of per-launch device times, see ggml_b200_graph_profile_json. */
 int mvit_profile_json(mvit_model * m, int n, int h, int w, int reps, char * buf, size_t cap);
 
+/* Debug tap (tests only): with the environment variable MVIT_DEBUG_STAGES=1 set before the first use of a shape,
+ * the outputs of stem (0), encoder layers 1..5 (1..5) and conv_1x1_exp (6) are kept as graph outputs; this copies
+ * one of them as [N][C][H][W] floats and its ggml ne into ne4.  Returns the element count, <0 on error. */
+int64_t mvit_debug_stage(mvit_model * m, int n, int h, int w, int idx, float * out, int64_t cap_floats, int64_t * ne4);
+
 #ifdef __cplusplus
 }
 #endif
