@@ -244,26 +244,207 @@ void launch_layernorm(const float * x, int64_t rows, int C, const float * gamma,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K7 attention, version 1 (CUDA cores, f32 math, online softmax).
-// Replaces mul_mat(K,Q) / sqrt(d) -> soft_max -> mul_mat(V^T, P) and the surrounding permutes/conts
-// (main.cpp:975-986,1073-1093).  One CTA = one (image, patch position, head); K and V of the sequence are staged
-// in shared memory as f32 in chunks of up to KCH keys; one thread owns one query row (q, o, m, l in registers).
+// K7 attention: replaces mul_mat(K,Q) / sqrt(d) -> soft_max -> mul_mat(V^T, P) and the surrounding
+// permutes/conts (main.cpp:975-986,1073-1093).
+//
+// qkv layout (written by the QKV GEMM against zero-padded weights): [token][3][heads][DP] f16, DP = head dim
+// rounded up to 16, padding lanes are exact zeros, so every per-head row is a 16-byte aligned MMA operand.
+// A sequence = the (H/2)*(W/2) pixels sharing (y%2, x%2) of one image: the unfold is only index arithmetic.
+//
+// k_attention_mma: flash-style, one warp = 16 query rows, S = Q K^T and O += P V on the tensor cores through
+// mma.sync.m16n8k16 (f16 in, f32 accumulate), softmax in registers in the accumulator layout with quad shuffles.
+// (mma.sync, not tcgen05: L <= 1024, d <= 64 tiles are far below a UMMA 128xN tile; see DESIGN.md.)
+// k_attention_v1 (CUDA cores) remains for sequence lengths that are not a multiple of 16.
 // ---------------------------------------------------------------------------------------------------------
-template <int DMAX>
-__global__ void __launch_bounds__(128) k_attention_v1(const __half * __restrict__ qkv, int N, int H, int W, int C, int heads,
-                                                      __half * __restrict__ out, int kch) {
-    extern __shared__ float smem_f[];
-    const int d    = C / heads;
-    const int npw = W / 2, nph = H / 2, L = npw * nph;
+__device__ __forceinline__ void ldmatrix_x4(uint32_t * r, const void * p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t * r, const void * p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_16816(float * c, const uint32_t * a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void * dst, const void * src) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+constexpr int kAttnQB = 128;  // queries per CTA (8 warps x 16)
+constexpr int kAttnLK = 256;  // keys staged in shared memory at a time
+
+template <int DP>
+__global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict__ qkv, int H, int W, int C, int heads, int d,
+                                                       __half * __restrict__ out, float sl2, int lk) {
+    constexpr int LDS = DP + 8;  // padded smem row (halves): conflict-free ldmatrix
+    constexpr int KS  = DP / 16; // k-steps of Q K^T
+    constexpr int DT  = DP / 8;  // n-tiles of P V
+    extern __shared__ __align__(16) unsigned char smem_attn[];
+    __half * sQ = reinterpret_cast<__half *>(smem_attn);
+    __half * sK = sQ + kAttnQB * LDS;
+    __half * sV = sK + lk * LDS;  // lk = min(L, kAttnLK) keys staged at a time
+
+    const int npw = W >> 1, nph = H >> 1, L = npw * nph;
     const int head = blockIdx.x % heads;
-    const int pp   = (blockIdx.x / heads) % 4;  // patch position ph*2+pw
+    const int pp   = (blockIdx.x / heads) & 3;
     const int n    = blockIdx.x / (heads * 4);
     const int ph = pp >> 1, pw = pp & 1;
-    float * sK = smem_f;                 // [kch][d]
+    const int64_t ld = 3 * (int64_t)heads * DP;
+    auto tok = [&](int l) -> int64_t {
+        const int iph = l / npw, ipw = l - iph * npw;
+        return ((int64_t)n * H + (iph * 2 + ph)) * W + (ipw * 2 + pw);
+    };
+    const int q0 = blockIdx.y * kAttnQB;
+    const int nq = min(kAttnQB, L - q0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = threadIdx.x; i < nq * (DP / 8); i += blockDim.x) {
+        const int r = i / (DP / 8), c = i % (DP / 8);
+        cp_async16(sQ + r * LDS + c * 8, qkv + tok(q0 + r) * ld + head * DP + c * 8);
+    }
+
+    const bool warp_active = warp * 16 < nq;
+    uint32_t qf[KS][4];
+    float    o[DT][4];
+    float    m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < DT; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+
+    for (int kc0 = 0; kc0 < L; kc0 += kAttnLK) {
+        const int nk = min(kAttnLK, L - kc0);
+        __syncthreads();  // previous chunk fully consumed
+        for (int i = threadIdx.x; i < nk * (DP / 8); i += blockDim.x) {
+            const int      r = i / (DP / 8), c = i % (DP / 8);
+            const __half * src = qkv + tok(kc0 + r) * ld + (heads + head) * DP + c * 8;
+            cp_async16(sK + r * LDS + c * 8, src);
+            cp_async16(sV + r * LDS + c * 8, src + heads * DP);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (!warp_active) continue;
+        if (kc0 == 0) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) ldmatrix_x4(qf[ks], sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
+        }
+        for (int kb = 0; kb < nk; kb += 64) {
+            const int ntile = min(64, nk - kb) >> 3;  // 8-key tiles in this block (multiple of 2)
+            float     s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+                for (int np = 0; np < 4; np++) {
+                    if (np * 2 < ntile) {
+                        uint32_t b[4];
+                        ldmatrix_x4(b, sK + (kb + (np * 2 + (lane >> 4)) * 8 + (lane & 7)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+                        mma_16816(s[np * 2], qf[ks], b[0], b[1]);
+                        mma_16816(s[np * 2 + 1], qf[ks], b[2], b[3]);
+                    }
+                }
+            }
+            // ---- online softmax (rows g and g+8 of this warp's 16 queries) ----
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < ntile) {
+                    mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+                    mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
+                }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            }
+            float corr[2], mb[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const float mn = fmaxf(m[r], mx[r]);
+                corr[r]        = exp2f((m[r] - mn) * sl2);
+                m[r]           = mn;
+                mb[r]          = mn * sl2;
+                l[r] *= corr[r];
+            }
+#pragma unroll
+            for (int i = 0; i < DT; i++) {
+                o[i][0] *= corr[0]; o[i][1] *= corr[0];
+                o[i][2] *= corr[1]; o[i][3] *= corr[1];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < ntile) {
+                    s[i][0] = exp2f(fmaf(s[i][0], sl2, -mb[0]));
+                    s[i][1] = exp2f(fmaf(s[i][1], sl2, -mb[0]));
+                    s[i][2] = exp2f(fmaf(s[i][2], sl2, -mb[1]));
+                    s[i][3] = exp2f(fmaf(s[i][3], sl2, -mb[1]));
+                    l[0] += s[i][0] + s[i][1];
+                    l[1] += s[i][2] + s[i][3];
+                }
+            // ---- O += P V ----
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                if (kk * 2 < ntile) {
+                    uint32_t a[4];
+                    a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+                    a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+                    a[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+                    a[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+                    for (int dp = 0; dp < DT / 2; dp++) {
+                        uint32_t b[4];
+                        ldmatrix_x4_trans(b, sV + (kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + (dp * 2 + (lane >> 4)) * 8);
+                        mma_16816(o[dp * 2], a, b[0], b[1]);
+                        mma_16816(o[dp * 2 + 1], a, b[2], b[3]);
+                    }
+                }
+            }
+        }
+    }
+    if (!warp_active) return;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+        l[r] = 1.f / l[r];
+    }
+    const int     qa = q0 + warp * 16 + g, qb = qa + 8;
+    __half *      oa = out + tok(qa) * (int64_t)C + head * d;
+    __half *      ob = out + tok(qb) * (int64_t)C + head * d;
+#pragma unroll
+    for (int i = 0; i < DT; i++) {
+        const int col = i * 8 + 2 * t;
+        if (col < d) {
+            *reinterpret_cast<__half2 *>(oa + col) = __floats2half2_rn(o[i][0] * l[0], o[i][1] * l[0]);
+            *reinterpret_cast<__half2 *>(ob + col) = __floats2half2_rn(o[i][2] * l[1], o[i][3] * l[1]);
+        }
+    }
+}
+
+// CUDA-core fallback for sequence lengths that are not a multiple of 16 (tiny feature maps); same qkv layout.
+template <int DMAX>
+__global__ void __launch_bounds__(128) k_attention_v1(const __half * __restrict__ qkv, int H, int W, int C, int heads, int d, int dp,
+                                                      __half * __restrict__ out, int kch) {
+    extern __shared__ float smem_f[];
+    const int npw = W / 2, nph = H / 2, L = npw * nph;
+    const int head = blockIdx.x % heads;
+    const int pp   = (blockIdx.x / heads) % 4;
+    const int n    = blockIdx.x / (heads * 4);
+    const int ph = pp >> 1, pw = pp & 1;
+    float * sK = smem_f;
     float * sV = smem_f + (size_t)kch * d;
     const float   scale = rsqrtf((float)d);
-    const int64_t ld    = 3 * (int64_t)C;
-    auto tok = [&](int l) -> int64_t {  // token l of this sequence -> pixel row
+    const int64_t ld    = 3 * (int64_t)heads * dp;
+    auto tok = [&](int l) -> int64_t {
         const int iph = l / npw, ipw = l % npw;
         return ((int64_t)n * H + (iph * 2 + ph)) * W + (ipw * 2 + pw);
     };
@@ -273,7 +454,7 @@ __global__ void __launch_bounds__(128) k_attention_v1(const __half * __restrict_
         float q[DMAX], o[DMAX];
         float m = -INFINITY, l = 0.f;
         if (active) {
-            const __half * qp = qkv + tok(qi) * ld + head * d;
+            const __half * qp = qkv + tok(qi) * ld + head * dp;
 #pragma unroll
             for (int e = 0; e < DMAX; e++) {
                 q[e] = e < d ? __half2float(qp[e]) * scale : 0.f;
@@ -285,9 +466,9 @@ __global__ void __launch_bounds__(128) k_attention_v1(const __half * __restrict_
             __syncthreads();
             for (int i = threadIdx.x; i < kn * d; i += blockDim.x) {
                 const int      j = i / d, e = i % d;
-                const __half * kp = qkv + tok(k0 + j) * ld + C + head * d;
+                const __half * kp = qkv + tok(k0 + j) * ld + (heads + head) * dp;
                 sK[i] = __half2float(kp[e]);
-                sV[i] = __half2float(kp[C + e]);
+                sV[i] = __half2float(kp[heads * dp + e]);
             }
             __syncthreads();
             if (active) {
@@ -319,21 +500,42 @@ __global__ void __launch_bounds__(128) k_attention_v1(const __half * __restrict_
     }
 }
 
+int attention_padded_head_dim(int d) { return (d + 15) / 16 * 16; }
+
 void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads, __half * out16, cudaStream_t st) {
-    const int d = C / heads;
-    const int L = (H / 2) * (W / 2);
-    int       kch = L < 256 ? L : 256;
-    size_t    smem = (size_t)2 * kch * d * sizeof(float);
-    const int grid = N * 4 * heads;
+    const int d  = C / heads;
+    const int dp = attention_padded_head_dim(d);
+    const int L  = (H / 2) * (W / 2);
+    if (dp > 64) B200_ABORT("attention: head dim %d > 64", d);
     static bool attr = false;
     if (!attr) {
         B200_CHECK(cudaFuncSetAttribute(k_attention_v1<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         B200_CHECK(cudaFuncSetAttribute(k_attention_v1<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_attention_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_attention_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_attention_mma<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_attention_mma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr = true;
     }
-    if (d <= 32) k_attention_v1<32><<<grid, 128, smem, st>>>(qkv, N, H, W, C, heads, out16, kch);
-    else if (d <= 64) k_attention_v1<64><<<grid, 128, smem, st>>>(qkv, N, H, W, C, heads, out16, kch);
-    else B200_ABORT("attention: head dim %d > 64", d);
+    if (L % 16 == 0 && getenv("GGML_B200_ATTN_V1") == nullptr) {
+        const int    warps = L >= kAttnQB ? 8 : L / 16;
+        const int    lk    = L < kAttnLK ? L : kAttnLK;
+        const size_t smem  = (size_t)(kAttnQB + 2 * lk) * (dp + 8) * sizeof(__half);
+        dim3         grid(N * 4 * heads, (L + kAttnQB - 1) / kAttnQB);
+        const float  sl2 = 1.4426950408889634f / sqrtf((float)d);  // log2(e) / sqrt(d)
+        switch (dp) {
+            case 16: k_attention_mma<16><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
+            case 32: k_attention_mma<32><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
+            case 48: k_attention_mma<48><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
+            default: k_attention_mma<64><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
+        }
+        return;
+    }
+    const int    kch  = L < 256 ? L : 256;
+    const size_t smem = (size_t)2 * kch * d * sizeof(float);
+    const int    grid = N * 4 * heads;
+    if (d <= 32) k_attention_v1<32><<<grid, 128, smem, st>>>(qkv, H, W, C, heads, d, dp, out16, kch);
+    else k_attention_v1<64><<<grid, 128, smem, st>>>(qkv, H, W, C, heads, d, dp, out16, kch);
 }
 
 // ---------------------------------------------------------------------------------------------------------

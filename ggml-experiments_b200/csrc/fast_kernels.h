@@ -23,8 +23,10 @@ void launch_layernorm(const float * x, int64_t rows, int C, const float * gamma,
                       float * out32, cudaStream_t st);
 
 // K7: softmax(Q K^T / sqrt(d)) V for every (image, patch position, head).
-// qkv: f16 [N*H*W, 3*C] in pixel order (q | k | v); a sequence is the (H/2)*(W/2) pixels that share the same
-// (y%2, x%2) -- the reference's unfold (main.cpp:721-747) is never materialised.  out: f16 [N*H*W, C].
+// qkv: f16 [N*H*W][3][heads][DP] in pixel order, DP = attention_padded_head_dim(C/heads), zero padded; a sequence is
+// the (H/2)*(W/2) pixels that share the same (y%2, x%2) -- the reference's unfold (main.cpp:721-747) is never
+// materialised.  out: f16 [N*H*W, C] (unpadded).
+int attention_padded_head_dim(int d);
 void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads, __half * out16, cudaStream_t st);
 
 // elementwise residual add: out = a + b (f32), optional f16 copy

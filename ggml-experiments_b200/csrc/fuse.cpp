@@ -410,10 +410,11 @@ struct Planner {
                     const int C = (int)t->ne[0];
                     REQUIRE(in->C == C && in->H % 2 == 0 && in->W % 2 == 0 && (C / am.heads) <= 64);
                     REQUIRE(t->ne[1] == (in->H / 2) * (in->W / 2) && t->ne[2] == 4 * in->N);
-                    FVal * qkv = new_val(in->N, in->H, in->W, 3 * C);
+                    FVal * qkv = new_val(in->N, in->H, in->W, 3 * am.heads * attention_padded_head_dim(C / am.heads));
                     FNode * nq = new_node(FK_QKV, qkv, "qkv");
                     nq->in.push_back(in);
                     nq->wq = am.wq; nq->wk = am.wk; nq->wv = am.wv; nq->bq = am.bq; nq->bk = am.bk; nq->bv = am.bv;
+                    nq->heads = am.heads;
                     FVal * ctx = new_val(in->N, in->H, in->W, C);
                     FNode * na = new_node(FK_ATTN, ctx, "attention");
                     na->in.push_back(qkv);
@@ -497,16 +498,20 @@ struct Planner {
                     plan->n_folded += 4;
                 } break;
                 case FK_QKV: {
-                    const int C = (int)n->wq->ne[0], IN = (int)n->wq->ne[1];
-                    std::vector<uint16_t> wt((size_t)3 * C * IN);
-                    std::vector<float>    bias(3 * C);
+                    // rows ordered [q|k|v][head][DP]: each head padded to DP = 16-multiple with zero rows / zero bias, so the
+                    // GEMM itself writes the 16-byte aligned, zero-padded per-head layout the attention kernel consumes
+                    const int C = (int)n->wq->ne[0], IN = (int)n->wq->ne[1], heads = n->heads;
+                    const int d = C / heads, dp = attention_padded_head_dim(d);
+                    std::vector<uint16_t> wt((size_t)3 * heads * dp * IN, 0);
+                    std::vector<float>    bias((size_t)3 * heads * dp, 0.f);
                     const ggml_tensor * ws[3] = {n->wq, n->wk, n->wv};
                     const ggml_tensor * bs[3] = {n->bq, n->bk, n->bv};
                     for (int s = 0; s < 3; s++) {
                         const float * src = (const float *)ws[s]->data;
                         for (int o = 0; o < C; o++) {
-                            for (int i = 0; i < IN; i++) wt[((size_t)s * C + o) * IN + i] = ggml_fp32_to_fp16(src[(size_t)i * C + o]);
-                            bias[s * C + o] = ((const float *)bs[s]->data)[o];
+                            const size_t row = ((size_t)s * heads + o / d) * dp + o % d;
+                            for (int i = 0; i < IN; i++) wt[row * IN + i] = ggml_fp32_to_fp16(src[(size_t)i * C + o]);
+                            bias[row] = ((const float *)bs[s]->data)[o];
                         }
                     }
                     n->c_w     = pool.add(wt.data(), wt.size() * 2);
@@ -754,8 +759,8 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const int N = qkv->N, H = qkv->H, W = qkv->W, C = o->C, heads = n->heads;
                 __half * o16 = o->p16;
                 const double L = (double)(H / 2) * (W / 2);
-                add_launch(plan, "attention_v1", [=](cudaStream_t st) { launch_attention(q, N, H, W, C, heads, o16, st); }, 4.0 * N * 4 * L * L * C,
-                           (double)qkv->rows() * 4 * C * 2, what);
+                add_launch(plan, "attention_mma_flash", [=](cudaStream_t st) { launch_attention(q, N, H, W, C, heads, o16, st); }, 4.0 * N * 4 * L * L * C,
+                           (double)qkv->rows() * (qkv->C + C) * 2, what);
             } break;
             case FK_ADD: {
                 const float *a = n->in[0]->p32, *b = n->in[1]->p32;
