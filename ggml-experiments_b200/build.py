@@ -71,7 +71,30 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> dict:
     if os.path.exists(main_src) and (force or _newer(cli, deps + [host])):
         _run([NVCC, *ARCH, *COMMON, "-o", cli, main_src, "-L" + OUT, "-lmobilevit_b200", "-lggml_b200",
               "-Xlinker", "-rpath,$ORIGIN"])
-    return {"lib": lib, "host": host, "cli": cli}
+    out = {"lib": lib, "host": host, "cli": cli}
+    out.update(build_reference_programs(force))
+    return out
+
+
+REFERENCE = "/root/reference"
+
+
+def build_reference_programs(force: bool = False) -> dict:
+    """Drop-in proof: compile the UNMODIFIED reference programs, from where they lie under /root/reference, against
+    include/ and link them with libggml_b200.so instead of upstream ggml's objects (mobilevit/Makefile:7-20).
+    Only possible in the dev container (the GPU box has no /root/reference; the built binaries travel with the repo)."""
+    res = {}
+    progs = {"ref_main_b200": (os.path.join(REFERENCE, "mobilevit", "main.cpp"), ["-I" + REFERENCE]),
+             "ref_rnn_b200": (os.path.join(REFERENCE, "rnn_text_gen", "rnn_text_generation.cpp"), [])}
+    for name, (src, extra) in progs.items():
+        if not os.path.exists(src):
+            continue
+        exe = os.path.join(OUT, name)
+        if force or _newer(exe, [src, os.path.join(OUT, "libggml_b200.so"), os.path.join(INC, "ggml", "ggml.h")]):
+            _run(["g++", "-O2", "-std=c++17", "-w", "-I" + INC, *extra, src, "-o", exe, "-L" + OUT, "-lggml_b200",
+                  "-Wl,-rpath,$ORIGIN"])
+        res[name] = exe
+    return res
 
 
 if __name__ == "__main__":

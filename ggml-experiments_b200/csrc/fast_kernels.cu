@@ -46,11 +46,11 @@ __global__ void __launch_bounds__(256) k_stem(const float * __restrict__ x, int6
         sh[i] = shift ? shift[i] : 0.f;
     }
     __syncthreads();
-    const int     OH = H / 2, OW = W / 2;
-    const int64_t total = (int64_t)N * OH * OW;
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(p % OW), oy = (int)((p / OW) % OH);
-        const int n  = (int)(p / ((int64_t)OW * OH));
+    const int OH = H / 2, OW = W / 2;
+    const int total = N * OH * OW;  // < 2^31 pixels
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        const int ox = p % OW, r_ = p / OW;
+        const int oy = r_ % OH, n = r_ / OH;
         float acc[OC];
 #pragma unroll
         for (int o = 0; o < OC; o++) acc[o] = 0.f;
@@ -78,12 +78,12 @@ __global__ void __launch_bounds__(256) k_stem(const float * __restrict__ x, int6
             acc[o]  = act ? silu_fast(y) : y;
         }
         if (out16) {
-            Half8 * o = reinterpret_cast<Half8 *>(out16 + p * OC);
+            Half8 * o = reinterpret_cast<Half8 *>(out16 + (int64_t)p * OC);
 #pragma unroll
             for (int g = 0; g < OC / 8; g++) o[g] = pack8(acc + g * 8);
         }
         if (out32) {
-            float4 * o = reinterpret_cast<float4 *>(out32 + p * OC);
+            float4 * o = reinterpret_cast<float4 *>(out32 + (int64_t)p * OC);
 #pragma unroll
             for (int g = 0; g < OC / 4; g++) o[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
         }
@@ -110,14 +110,26 @@ void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc
 // thread = (8-channel group, output pixel); 128-bit loads/stores; adjacent threads -> adjacent channel groups of the
 // same pixel -> fully coalesced rows of C*2 bytes.  Per-thread weights/scale/shift live in registers across pixels.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_dwconv(const __half * __restrict__ x, int N, int H, int W, int C, int stride,
-                                                const __half * __restrict__ Wt, const float * __restrict__ scale,
-                                                const float * __restrict__ shift, int act, __half * __restrict__ out) {
-    const int cgs = C / 8;                       // channel groups
-    const int cg  = threadIdx.x % cgs;           // blockDim.x is a multiple of cgs
-    const int ppb = blockDim.x / cgs;            // pixels per block-iteration
-    const int pl  = threadIdx.x / cgs;
-    const int OH = H / stride, OW = W / stride;  // pad 1, k 3: (H + 2 - 3)/s + 1 == H/s for even H (s=2) and == H (s=1)
+// A block owns a strip of TW output columns x TH output rows of one image; a thread owns one (column, channel group)
+// and walks down the strip with the 3x3 input window in registers, so each output row costs 3 (stride 1) or 6
+// (stride 2) new 128-bit loads instead of 9; the x-neighbour overlap between threads is served by L1.
+template <int STRIDE>
+__global__ void __launch_bounds__(256) k_dwconv(const __half * __restrict__ x, int H, int W, int C, const __half * __restrict__ Wt,
+                                                const float * __restrict__ scale, const float * __restrict__ shift, int act,
+                                                __half * __restrict__ out, int TW, int TH, int tiles_x, int tiles_y) {
+    const int cgs = C >> 3;                  // 8-channel groups
+    const int cg  = threadIdx.x % cgs;       // blockDim.x == cgs * TW
+    const int xl  = threadIdx.x / cgs;
+    const int OH = H / STRIDE, OW = W / STRIDE;  // pad 1, k 3
+    int       b  = blockIdx.x;
+    const int tx = b % tiles_x;
+    b /= tiles_x;
+    const int ty = b % tiles_y;
+    const int n  = b / tiles_y;
+    const int ox = tx * TW + xl;
+    if (ox >= OW) return;
+    const int oy0 = ty * TH, oy1 = min(OH, oy0 + TH);
+
     float w[9][8], sc[8], sh[8];
 #pragma unroll
     for (int t = 0; t < 9; t++) unpack8(*reinterpret_cast<const Half8 *>(Wt + t * C + cg * 8), w[t]);
@@ -126,48 +138,77 @@ __global__ void __launch_bounds__(256) k_dwconv(const __half * __restrict__ x, i
         sc[j] = scale ? scale[cg * 8 + j] : 1.f;
         sh[j] = shift ? shift[cg * 8 + j] : 0.f;
     }
-    const int64_t total = (int64_t)N * OH * OW;
-    for (int64_t p = (int64_t)blockIdx.x * ppb + pl; p < total; p += (int64_t)gridDim.x * ppb) {
-        const int ox = (int)(p % OW), oy = (int)((p / OW) % OH);
-        const int n  = (int)(p / ((int64_t)OW * OH));
+    const __half * xin  = x + (int64_t)n * H * W * C + cg * 8;
+    __half *       outp = out + (int64_t)n * OH * OW * C + cg * 8;
+    const int  ix1 = ox * STRIDE, ix0 = ix1 - 1, ix2 = ix1 + 1;
+    const bool v0 = ix0 >= 0, v2 = ix2 < W;
+    Half8 zero;
+#pragma unroll
+    for (int i = 0; i < 4; i++) zero.h[i] = __floats2half2_rn(0.f, 0.f);
+    auto load_row = [&](int iy, Half8 * r) {
+        if (iy < 0 || iy >= H) {
+            r[0] = zero; r[1] = zero; r[2] = zero;
+        } else {
+            const __half * row = xin + (int64_t)iy * W * C;
+            r[0] = v0 ? *reinterpret_cast<const Half8 *>(row + ix0 * C) : zero;
+            r[1] = *reinterpret_cast<const Half8 *>(row + ix1 * C);
+            r[2] = v2 ? *reinterpret_cast<const Half8 *>(row + ix2 * C) : zero;
+        }
+    };
+    Half8 win[3][3];
+    load_row(oy0 * STRIDE - 1, win[0]);
+    if (STRIDE == 1) load_row(oy0, win[1]);
+    for (int oy = oy0; oy < oy1; oy++) {
+        if (STRIDE == 1) {
+            load_row(oy + 1, win[2]);
+        } else {
+            load_row(oy * 2, win[1]);
+            load_row(oy * 2 + 1, win[2]);
+        }
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = 0.f;
 #pragma unroll
-        for (int kh = 0; kh < 3; kh++) {
-            const int iy = oy * stride + kh - 1;
-            if (iy < 0 || iy >= H) continue;
+        for (int kh = 0; kh < 3; kh++)
 #pragma unroll
             for (int kw = 0; kw < 3; kw++) {
-                const int ix = ox * stride + kw - 1;
-                if (ix < 0 || ix >= W) continue;
                 float v[8];
-                unpack8(*reinterpret_cast<const Half8 *>(x + (((int64_t)n * H + iy) * W + ix) * C + cg * 8), v);
+                unpack8(win[kh][kw], v);
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc[j] = fmaf(v[j], w[kh * 3 + kw][j], acc[j]);
             }
-        }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             float y = fmaf(acc[j], sc[j], sh[j]);
             acc[j]  = act ? silu_fast(y) : y;
         }
-        *reinterpret_cast<Half8 *>(out + p * C + cg * 8) = pack8(acc);
+        *reinterpret_cast<Half8 *>(outp + ((int64_t)oy * OW + ox) * C) = pack8(acc);
+#pragma unroll
+        for (int kw = 0; kw < 3; kw++) {
+            if (STRIDE == 1) {
+                win[0][kw] = win[1][kw];
+                win[1][kw] = win[2][kw];
+            } else {
+                win[0][kw] = win[2][kw];
+            }
+        }
     }
 }
 
 void launch_dwconv(const __half * x, int N, int H, int W, int C, int stride, const __half * Wt, const float * scale,
                    const float * shift, int act, __half * out16, cudaStream_t st) {
-    if (C % 8) B200_ABORT("dwconv: C %% 8 != 0");
-    const int cgs     = C / 8;
-    int       threads = (256 / cgs) * cgs;
-    if (threads == 0) threads = cgs;  // C > 2048 never happens here
-    const int     ppb   = threads / cgs;
-    const int64_t total = (int64_t)N * (H / stride) * (W / stride);
-    int64_t       nb    = (total + ppb - 1) / ppb;
-    const int64_t cap   = (int64_t)runtime().sm_count * 16;
-    const int     grid  = (int)(nb > cap ? cap : nb);
-    k_dwconv<<<grid, threads, 0, st>>>(x, N, H, W, C, stride, Wt, scale, shift, act, out16);
+    if (C % 8 || H % stride || W % stride) B200_ABORT("dwconv: unsupported shape C=%d H=%d W=%d stride=%d", C, H, W, stride);
+    const int cgs = C / 8;
+    const int OH = H / stride, OW = W / stride;
+    int TW = 256 / cgs;
+    if (TW < 1) TW = 1;
+    if (TW > OW) TW = OW;
+    if (cgs * TW > 256) B200_ABORT("dwconv: C=%d too wide", C);
+    const int TH      = OH < 16 ? OH : 16;
+    const int tiles_x = (OW + TW - 1) / TW, tiles_y = (OH + TH - 1) / TH;
+    const int grid    = N * tiles_x * tiles_y;
+    if (stride == 1) k_dwconv<1><<<grid, cgs * TW, 0, st>>>(x, H, W, C, Wt, scale, shift, act, out16, TW, TH, tiles_x, tiles_y);
+    else k_dwconv<2><<<grid, cgs * TW, 0, st>>>(x, H, W, C, Wt, scale, shift, act, out16, TW, TH, tiles_x, tiles_y);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -6,7 +6,8 @@
 //   D[M,N] (f32, TMEM) = A[M,K] (f16, K-major, smem via TMA) x B[N,K]^T (f16, K-major, smem via TMA)
 //
 // * operands are f16 and accumulation is f32, exactly the rounding points of ggml's f16 conv path;
-// * one CTA computes one 128 x block_n output tile (UMMA M=128, N=block_n<=256, K=16 per instruction);
+// * persistent CTAs (1-2 per SM) loop over 128 x block_n output tiles (UMMA M=128, N=block_n<=256, K=16 per
+//   instruction) with two accumulator stages in TMEM, so the epilogue of tile i overlaps the TMA+MMA of tile i+1;
 // * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
 //   (tcgen05.ld -> BN scale/shift or bias -> SiLU -> residual -> vectorised stores);
 // * smem ring of `stages` x (A 128x64 + B block_n x 64) f16 tiles in the 128-byte swizzled K-major layout
@@ -15,8 +16,6 @@
 //   {64 ch, W, rows, images} shifted by the tap offset, with the hardware zero-filling the halo, so no
 //   im2col buffer ever exists; a second source tensor map implements ggml_concat (main.cpp:1219) for free.
 //
-// The memory-bound layers (K <= 128, N <= 64) get their overlap from co-resident CTAs (smem and TMEM are
-// sized so that >= 2 CTAs fit per SM), not from an intra-CTA epilogue pipeline.
 #include "gemm_tcgen05.h"
 
 #include <cstdio>
@@ -42,6 +41,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -148,6 +150,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                                                            const __grid_constant__ CUtensorMap map_a1,
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const GemmLaunch::Params p) {
+    // Persistent CTA: blockIdx.y fixes the N tile, blockIdx.x strides over the M tiles.  Three decoupled pipelines:
+    //   smem ring   full/empty[stages]   TMA producer  <-> MMA issuer      (runs continuously across tiles)
+    //   TMEM ring   tmem_full/empty[2]   MMA issuer    <-> epilogue warps  (tile i+1 accumulates while tile i drains)
     extern __shared__ uint8_t smem_raw[];
     uint8_t * smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle-128B atoms need 1 KiB alignment
     const int       a_bytes     = kBlockM * kBlockK * 2;
@@ -156,14 +161,15 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     uint64_t *      bars        = (uint64_t *)(smem + (size_t)p.stages * stage_bytes);
     uint64_t *      full_bar    = bars;
     uint64_t *      empty_bar   = bars + kMaxStage;
-    uint64_t *      tmem_full   = bars + 2 * kMaxStage;
-    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 1);
-    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 2);
+    uint64_t *      tmem_full   = bars + 2 * kMaxStage;      // [2]
+    uint64_t *      tmem_empty  = bars + 2 * kMaxStage + 2;  // [2]
+    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 4);
+    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 5);
     float *         s_shift     = s_scale + 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBlockM;
     const int n0 = blockIdx.y * p.block_n;
+    const int num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
@@ -173,7 +179,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(tmem_full), 1);
+        for (int a = 0; a < 2; a++) {
+            mbar_init(smem_u32(&tmem_full[a]), 1);
+            mbar_init(smem_u32(&tmem_empty[a]), 4);  // one arrive per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -192,30 +201,34 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int img = 0, y0 = 0;
-            if (p.conv) {
-                const int hw = p.H * p.W;
-                img          = m0 / hw;
-                y0           = p.rows_per_tile ? (m0 % hw) / p.W : 0;
-            }
-            for (int kb = 0; kb < p.num_kb; kb++) {
-                const int      s  = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                const uint32_t fb = smem_u32(&full_bar[s]);
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
-                mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                if (!p.conv) {
-                    tma_load_2d(sa, &map_a0, kb * kBlockK, m0, fb);
-                    tma_load_2d(sb, &map_b, kb * kBlockK, n0, fb);
-                } else {
-                    const int tap = kb / cblk_tot, r = kb % cblk_tot;
-                    const int src = r >= p.cblk0;
-                    const int cb  = src ? r - p.cblk0 : r;
-                    const int kh = tap / 3, kw = tap % 3;
-                    tma_load_4d(sa, src ? &map_a1 : &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
-                    tma_load_3d(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
+            uint32_t it = 0;  // k-block counter across all tiles of this CTA
+            for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+                const int m0 = tile * kBlockM;
+                int img = 0, y0 = 0;
+                if (p.conv) {
+                    const int hw = p.H * p.W;
+                    img          = m0 / hw;
+                    y0           = p.rows_per_tile ? (m0 % hw) / p.W : 0;
+                }
+                for (int kb = 0; kb < p.num_kb; kb++, it++) {
+                    const int      s  = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                    if (!p.conv) {
+                        tma_load_2d(sa, &map_a0, kb * kBlockK, m0, fb);
+                        tma_load_2d(sb, &map_b, kb * kBlockK, n0, fb);
+                    } else {
+                        const int tap = kb / cblk_tot, r = kb % cblk_tot;
+                        const int src = r >= p.cblk0;
+                        const int cb  = src ? r - p.cblk0 : r;
+                        const int kh = tap / 3, kw = tap % 3;
+                        tma_load_4d(sa, src ? &map_a1 : &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
+                        tma_load_3d(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
+                    }
                 }
             }
         }
@@ -224,87 +237,103 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         // ===================== MMA issuer (single thread) =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.block_n);
-            for (int kb = 0; kb < p.num_kb; kb++) {
-                const int      s  = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
+                const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+                mbar_wait(smem_u32(&tmem_empty[acc]), aph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
-                int rem;
-                if (!p.conv) {
-                    rem = p.K - kb * kBlockK;
-                } else {
-                    const int r   = kb % cblk_tot;
-                    const int src = r >= p.cblk0;
-                    rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
+                const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
+                for (int kb = 0; kb < p.num_kb; kb++, it++) {
+                    const int      s  = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    int rem;
+                    if (!p.conv) {
+                        rem = p.K - kb * kBlockK;
+                    } else {
+                        const int r   = kb % cblk_tot;
+                        const int src = r >= p.cblk0;
+                        rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
+                    }
+                    const int      ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
+                    const uint64_t adesc  = make_smem_desc(sa);
+                    const uint64_t bdesc  = make_smem_desc(sb);
+                    for (int k = 0; k < ksteps; k++) {
+                        // advancing 16 f16 (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
+                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
                 }
-                const int      ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
-                const uint64_t adesc  = make_smem_desc(sa);
-                const uint64_t bdesc  = make_smem_desc(sb);
-                for (int k = 0; k < ksteps; k++) {
-                    // advancing 16 f16 (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                }
-                umma_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
+                umma_commit(smem_u32(&tmem_full[acc]));  // accumulator complete
             }
-            umma_commit(smem_u32(tmem_full));  // accumulator complete
         }
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int q   = warp & 3;  // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;
-        const int m   = m0 + row;
-        mbar_wait(smem_u32(tmem_full), 0);
-        tc_fence_after();
         const GemmEpilogue & ep = p.ep;
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-            if (n0 + c0 >= p.N) break;  // warp-uniform
-            float v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (m < p.M) {
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
+            const int      m   = tile * kBlockM + row;
+            const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+            mbar_wait(smem_u32(&tmem_full[acc]), aph);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                if (n0 + c0 >= p.N) break;  // warp-uniform
+                float v[32];
+                tmem_ld_32x32(tmem_d + (uint32_t)c0, v);
+                if (m < p.M) {
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int n = n0 + c0 + g * 8;
-                    if (n + 8 <= p.N) {
-                        float y[8];
+                    for (int g = 0; g < 4; g++) {
+                        const int n = n0 + c0 + g * 8;
+                        if (n + 8 <= p.N) {
+                            float y[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float t = fmaf(v[g * 8 + j], s_scale[c0 + g * 8 + j], s_shift[c0 + g * 8 + j]);
-                            y[j]    = ep.act ? silu_f(t) : t;
-                        }
-                        if (ep.res32) {
-                            const float4 r0 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n);
-                            const float4 r1 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n + 4);
-                            y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
-                            y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
-                        }
-                        if (ep.res16) {
-                            const uint4    rr = *reinterpret_cast<const uint4 *>(ep.res16 + (size_t)m * ep.ldr16 + n);
-                            const __half2 * h = reinterpret_cast<const __half2 *>(&rr);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const float2 f = __half22float2(h[j]);
-                                y[2 * j] += f.x;
-                                y[2 * j + 1] += f.y;
+                            for (int j = 0; j < 8; j++) {
+                                float tt = fmaf(v[g * 8 + j], s_scale[c0 + g * 8 + j], s_shift[c0 + g * 8 + j]);
+                                y[j]     = ep.act ? silu_f(tt) : tt;
                             }
-                        }
-                        if (ep.out32) {
-                            float4 * o = reinterpret_cast<float4 *>(ep.out32 + (size_t)m * ep.ld32 + n);
-                            o[0]       = make_float4(y[0], y[1], y[2], y[3]);
-                            o[1]       = make_float4(y[4], y[5], y[6], y[7]);
-                        }
-                        if (ep.out16) {
-                            uint4      o;
-                            __half2 *  h = reinterpret_cast<__half2 *>(&o);
+                            if (ep.res32) {
+                                const float4 r0 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n);
+                                const float4 r1 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n + 4);
+                                y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
+                                y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+                            }
+                            if (ep.res16) {
+                                const uint4    rr = *reinterpret_cast<const uint4 *>(ep.res16 + (size_t)m * ep.ldr16 + n);
+                                const __half2 * h = reinterpret_cast<const __half2 *>(&rr);
 #pragma unroll
-                            for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
-                            *reinterpret_cast<uint4 *>(ep.out16 + (size_t)m * ep.ld16 + n) = o;
+                                for (int j = 0; j < 4; j++) {
+                                    const float2 f = __half22float2(h[j]);
+                                    y[2 * j] += f.x;
+                                    y[2 * j + 1] += f.y;
+                                }
+                            }
+                            if (ep.out32) {
+                                float4 * o = reinterpret_cast<float4 *>(ep.out32 + (size_t)m * ep.ld32 + n);
+                                o[0]       = make_float4(y[0], y[1], y[2], y[3]);
+                                o[1]       = make_float4(y[4], y[5], y[6], y[7]);
+                            }
+                            if (ep.out16) {
+                                uint4      o;
+                                __half2 *  h = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                                *reinterpret_cast<uint4 *>(ep.out16 + (size_t)m * ep.ld16 + n) = o;
+                            }
                         }
                     }
                 }
             }
+            // this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_32x32): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
         }
     }
     tc_fence_before();
@@ -363,14 +392,25 @@ static void choose_tiling(GemmLaunch & L, int N) {
     p.n_tiles              = (N + 255) / 256;
     int per                = (N + p.n_tiles - 1) / p.n_tiles;
     p.block_n              = (per + 31) / 32 * 32;
-    p.tmem_cols            = p.block_n <= 32 ? 32 : p.block_n <= 64 ? 64 : p.block_n <= 128 ? 128 : 256;
+    // two accumulator stages in TMEM (tile i+1 accumulates while tile i drains); power-of-two column count >= 32
+    const int need         = 2 * p.block_n;
+    p.tmem_cols            = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const int stage_bytes  = kBlockM * kBlockK * 2 + p.block_n * kBlockK * 2;
-    int       stages       = (96 * 1024) / stage_bytes;  // keep <= ~100 KiB so two CTAs share an SM
+    // block_n <= 128 -> 256 TMEM columns -> two CTAs can share an SM: keep each under ~100 KiB of smem
+    const int budget       = p.block_n <= 128 ? 96 * 1024 : 192 * 1024;
+    int       stages       = budget / stage_bytes;
     if (stages > kMaxStage) stages = kMaxStage;
     if (stages < 2) stages = 2;
-    if (stages > p.num_kb) stages = p.num_kb < 1 ? 1 : p.num_kb;
     p.stages     = stages;
-    L.smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStage + 2) * 8 + 2 * 256 * sizeof(float);
+    L.ctas_per_sm = p.block_n <= 128 ? 2 : 1;
+    L.smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStage + 5) * 8 + 2 * 256 * sizeof(float);
+}
+
+static void choose_grid(GemmLaunch & L) {
+    const int num_m_tiles = (L.p.M + kBlockM - 1) / kBlockM;
+    int       per_n       = (L.ctas_per_sm * runtime().sm_count) / L.p.n_tiles;
+    if (per_n < 1) per_n = 1;
+    L.grid = dim3((unsigned)(num_m_tiles < per_n ? num_m_tiles : per_n), (unsigned)L.p.n_tiles, 1);
 }
 
 bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, int ldb, int M, int N, int K,
@@ -397,7 +437,7 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
         const uint32_t box[2]  = {(uint32_t)kBlockK, (uint32_t)p.block_n};
         make_map(&L.map_b, B, 2, dims, str, box);
     }
-    L.grid = dim3((unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)p.n_tiles, 1);
+    choose_grid(L);
     return true;
 }
 
@@ -442,7 +482,7 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
         const uint32_t box[3]  = {(uint32_t)kBlockK, 1, (uint32_t)p.block_n};
         make_map(&L.map_b, Wt, 3, dims, str, box);
     }
-    L.grid = dim3((unsigned)((p.M + kBlockM - 1) / kBlockM), (unsigned)p.n_tiles, 1);
+    choose_grid(L);
     return true;
 }
 

@@ -39,6 +39,7 @@ struct GemmLaunch {
         GemmEpilogue ep;
     } p;
     size_t smem_bytes;
+    int    ctas_per_sm;
     dim3   grid;
 };
 

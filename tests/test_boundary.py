@@ -75,3 +75,17 @@ def test_compute_without_gpu_fails_loudly(weight_files):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode != 0
     assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/mobilevit/main.cpp"), reason="reference sources not present")
+def test_unmodified_reference_programs_compile_and_link_against_the_boundary(tmp_path):
+    """mobilevit/main.cpp and rnn_text_gen/rnn_text_generation.cpp, untouched, build against include/ + libggml_b200.so."""
+    import ggml_experiments_b200 as G
+    lib_dir = os.path.dirname(G.native_paths()["ggml"])
+    inc = os.path.join(ROOT, "include")
+    for src, extra in (("/root/reference/mobilevit/main.cpp", ["-I/root/reference"]),
+                       ("/root/reference/rnn_text_gen/rnn_text_generation.cpp", [])):
+        exe = str(tmp_path / (os.path.basename(src) + ".bin"))
+        r = subprocess.run(["g++", "-O0", "-std=c++17", "-w", "-I" + inc, *extra, src, "-o", exe, "-L" + lib_dir, "-lggml_b200"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]

@@ -141,3 +141,26 @@ def test_fast_mode_matches_oracle(G, oracle, weight_files, variant, n, hw):
     assert r["violations"] <= r["n"] * 1e-4, r
     assert r["rel_l2"] < 5e-3, r
     assert t["agree"] == 1.0, t
+
+
+def test_unmodified_reference_main_runs_on_libggml_b200(G, oracle, weight_files, tmp_path):
+    """The reference's own main.cpp (compiled untouched against our headers, linked with libggml_b200.so) classifies
+    its built-in test image (main.cpp:680-688); the 10 values it prints (main.cpp:703) must match the oracle."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    exe = os.path.join(os.path.dirname(G.native_paths()["ggml"]), "ref_main_b200")
+    if not os.path.exists(exe):
+        pytest.skip("ref_main_b200 not built (needs /root/reference at build time)")
+    shutil.copy(weight_files["s"], tmp_path / "weight.ggml")  # main.cpp:665 loads "weight.ggml" from the cwd
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=dict(os.environ, GGML_B200_VERBOSE="1"))
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "output feature shape: : Dims: (8, 8, 640)" in r.stdout
+    line = r.stdout.strip().splitlines()[-1]
+    vals = [float(v) for v in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", line)]
+    assert len(vals) == 10, line
+    ref_f, _ = oracle.OracleModel(weight_files["s"]).forward(W.synthetic_images(1, 256, 256))
+    ref = np.concatenate([ref_f[0, :5, 0, 0], ref_f[0, -5:, 0, 0]])
+    print("reference main.cpp printed:", vals, "oracle:", ref.tolist(), r.stderr[-300:])
+    assert np.abs(np.array(vals) - ref).max() < 3e-2
