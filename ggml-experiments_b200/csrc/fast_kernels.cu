@@ -6,7 +6,17 @@
 
 namespace b200 {
 
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op instead of two (see gemm_tcgen05.cu::silu_f)
+__device__ __forceinline__ float silu_fast(float x) {
+#ifdef GGML_B200_SILU_EXACT
+    return __fdividef(x, 1.0f + __expf(-x));
+#else
+    const float h = 0.5f * x;
+    float       t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+#endif
+}
 
 struct alignas(16) Half8 {
     __half2 h[4];

@@ -680,7 +680,14 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     // ---- emit launches ----
     for (FNode * n : P.order) {
         FVal * o = n->out;
-        const std::string what = n->name;
+        std::string what = n->name;
+        {
+            char shp[160];
+            const FVal * i0 = n->in.empty() ? nullptr : n->in[0];
+            snprintf(shp, sizeof shp, " in[%dx%dx%dx%d] out[%dx%dx%dx%d]%s%s%s%s", i0 ? i0->N : 0, i0 ? i0->H : 0, i0 ? i0->W : 0, i0 ? i0->C : 0,
+                     o->N, o->H, o->W, o->C, n->act ? " silu" : "", n->res ? " +res" : "", o->need16 ? " f16" : "", o->need32 ? " f32" : "");
+            what += shp;
+        }
         switch (n->kind) {
             case FK_INPUT: {
                 o->p32 = (float *)device_ptr_of(plan, n->leaf);

@@ -28,7 +28,7 @@ namespace b200 {
 
 static constexpr int kBlockM   = 128;
 static constexpr int kBlockK   = 64;   // 64 f16 = 128 bytes = one swizzle-128B row
-static constexpr int kThreads  = 192;  // 6 warps
+static constexpr int kThreads  = 320;  // 10 warps: TMA, MMA, 2 x 4 epilogue
 static constexpr int kMaxStage = 4;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -141,7 +141,20 @@ __device__ __forceinline__ uint32_t make_idesc(int block_n) {
     return (1u << 4) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU with ONE transcendental: x*sigmoid(x) = h + h*tanh(h), h = x/2 (MUFU.TANH; the exp+rcp form costs two MUFU ops
+// and ~9 instructions per element, which made the SiLU epilogues XU/issue-bound: profiles/README.md).
+// tanh.approx.f32 has ~2^-11 relative error, i.e. the result is good to about one f16 ulp -- the precision the value
+// is stored at anyway.  -DGGML_B200_SILU_EXACT restores x / (1 + exp(-x)).
+__device__ __forceinline__ float silu_f(float x) {
+#ifdef GGML_B200_SILU_EXACT
+    return __fdividef(x, 1.0f + __expf(-x));
+#else
+    const float h = 0.5f * x;
+    float       t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
@@ -153,8 +166,12 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     // Persistent CTA: blockIdx.y fixes the N tile, blockIdx.x strides over the M tiles.  Three decoupled pipelines:
     //   smem ring   full/empty[stages]   TMA producer  <-> MMA issuer      (runs continuously across tiles)
     //   TMEM ring   tmem_full/empty[2]   MMA issuer    <-> epilogue warps  (tile i+1 accumulates while tile i drains)
+    // Two epilogue warp groups (warps 2-5 / 6-9) own one TMEM accumulator stage each and alternate tiles, so the
+    // SiLU/convert/store work of consecutive tiles overlaps and each SM sub-partition always has epilogue warps to issue.
     extern __shared__ uint8_t smem_raw[];
-    uint8_t * smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle-128B atoms need 1 KiB alignment
+    // swizzle-128B atoms need 1 KiB alignment; offset arithmetic (not a uintptr_t round trip) keeps the pointer in the
+    // shared address space for the compiler (LDS/STS instead of generic LD/ST)
+    uint8_t * smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int       a_bytes     = kBlockM * kBlockK * 2;
     const int       b_bytes     = p.block_n * kBlockK * 2;
     const int       stage_bytes = a_bytes + b_bytes;
@@ -273,13 +290,15 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
-        const int q   = warp & 3;  // TMEM lane quadrant this warp may access
+        const int      q     = warp & 3;          // TMEM lane quadrant this warp may access
+        const uint32_t group = (warp - 2) >> 2;   // 0: even local tiles / accumulator 0, 1: odd tiles / accumulator 1
         const int row = q * 32 + lane;
         const GemmEpilogue & ep = p.ep;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
+            if ((t & 1u) != group) continue;
             const int      m   = tile * kBlockM + row;
-            const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+            const uint32_t acc = group, aph = (t >> 1) & 1u;
             mbar_wait(smem_u32(&tmem_full[acc]), aph);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
@@ -396,13 +415,13 @@ static void choose_tiling(GemmLaunch & L, int N) {
     const int need         = 2 * p.block_n;
     p.tmem_cols            = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const int stage_bytes  = kBlockM * kBlockK * 2 + p.block_n * kBlockK * 2;
-    // block_n <= 128 -> 256 TMEM columns -> two CTAs can share an SM: keep each under ~100 KiB of smem
-    const int budget       = p.block_n <= 128 ? 96 * 1024 : 192 * 1024;
+    // TMEM (512 columns) and shared memory (~220 KiB usable) decide how many persistent CTAs share an SM
+    L.ctas_per_sm          = p.block_n <= 64 ? 3 : p.block_n <= 128 ? 2 : 1;
+    const int budget       = (216 * 1024) / L.ctas_per_sm - 4096;
     int       stages       = budget / stage_bytes;
     if (stages > kMaxStage) stages = kMaxStage;
     if (stages < 2) stages = 2;
     p.stages     = stages;
-    L.ctas_per_sm = p.block_n <= 128 ? 2 : 1;
     L.smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStage + 5) * 8 + 2 * 256 * sizeof(float);
 }
 

@@ -410,9 +410,9 @@ extern "C" int ggml_b200_graph_profile_json(struct ggml_cgraph * gf, int reps, c
     }
     for (auto & e : ev) cudaEventDestroy(e);
     std::string out = "[";
-    char        tmp[512];
+    char        tmp[768];
     for (size_t i = 0; i < n; i++) {
-        snprintf(tmp, sizeof tmp, "%s{\"kernel\":\"%s\",\"what\":\"%.60s\",\"ms\":%.6f,\"flops\":%.0f,\"bytes\":%.0f}", i ? "," : "",
+        snprintf(tmp, sizeof tmp, "%s{\"kernel\":\"%s\",\"what\":\"%.120s\",\"ms\":%.6f,\"flops\":%.0f,\"bytes\":%.0f}", i ? "," : "",
                  p->meta[i].kernel, p->meta[i].what.c_str(), ms[i] / reps, p->meta[i].flops, p->meta[i].bytes);
         out += tmp;
     }
