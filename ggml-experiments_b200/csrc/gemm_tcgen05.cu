@@ -30,6 +30,7 @@ static constexpr int kBlockM   = 128;
 static constexpr int kBlockK   = 64;   // 64 f16 = 128 bytes = one swizzle-128B row
 static constexpr int kThreads  = 320;  // 10 warps: TMA, MMA, 2 x 4 epilogue
 static constexpr int kMaxStage = 4;
+static constexpr int kCtrlBytes = 3072;  // barriers + TMEM slot + per-column scale/shift, padded to keep 1 KiB alignment
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -83,6 +84,25 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap * ma
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
+}
+// smem tile -> global through the TMA engine (full-line writes, M/N tails clipped by the tensor map)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap * map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap * map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -162,6 +182,9 @@ __device__ __forceinline__ float silu_f(float x) {
 __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a0,
                                                            const __grid_constant__ CUtensorMap map_a1,
                                                            const __grid_constant__ CUtensorMap map_b,
+                                                           const __grid_constant__ CUtensorMap map_o16,
+                                                           const __grid_constant__ CUtensorMap map_o32,
+                                                           const __grid_constant__ CUtensorMap map_r32,
                                                            const GemmLaunch::Params p) {
     // Persistent CTA: blockIdx.y fixes the N tile, blockIdx.x strides over the M tiles.  Three decoupled pipelines:
     //   smem ring   full/empty[stages]   TMA producer  <-> MMA issuer      (runs continuously across tiles)
@@ -180,9 +203,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     uint64_t *      empty_bar   = bars + kMaxStage;
     uint64_t *      tmem_full   = bars + 2 * kMaxStage;      // [2]
     uint64_t *      tmem_empty  = bars + 2 * kMaxStage + 2;  // [2]
-    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 4);
-    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 5);
+    uint64_t *      res_full    = bars + 2 * kMaxStage + 4;  // [2] residual slab landed (per epilogue group)
+    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 6);
+    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 7);
     float *         s_shift     = s_scale + 256;
+    // epilogue staging (per epilogue warp group): 128 rows x 128 B tiles in the TMA 128B-swizzle layout
+    uint8_t *       stage_base  = smem + (size_t)p.stages * stage_bytes + kCtrlBytes;
+    const int       stg16_bytes = p.ep.out16 ? kBlockM * 128 : 0;      // 64 f16 columns per row
+    const int       stg32_bytes = (p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0;  // 2 x 32 f32 columns per row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * p.block_n;
@@ -192,6 +220,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_b);
         if (p.cblk1 > 0) tma_prefetch_desc(&map_a1);
+        if (p.ep.out16) tma_prefetch_desc(&map_o16);
+        if (p.ep.out32) tma_prefetch_desc(&map_o32);
+        if (p.ep.res32) tma_prefetch_desc(&map_r32);
         for (int s = 0; s < p.stages; s++) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -199,6 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         for (int a = 0; a < 2; a++) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
             mbar_init(smem_u32(&tmem_empty[a]), 4);  // one arrive per epilogue warp
+            mbar_init(smem_u32(&res_full[a]), 1);
         }
         fence_barrier_init();
     }
@@ -289,40 +321,70 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         }
         __syncwarp();
     } else {
-        // ===================== epilogue: TMEM -> registers -> global =====================
-        const int      q     = warp & 3;          // TMEM lane quadrant this warp may access
-        const uint32_t group = (warp - 2) >> 2;   // 0: even local tiles / accumulator 0, 1: odd tiles / accumulator 1
-        const int row = q * 32 + lane;
+        // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
+        // A thread owns one output row (TMEM lane).  Writing rows straight to global costs one 16-byte wavefront per
+        // lane (32 per instruction) and made output-heavy layers LSU-bound; instead each group stages a
+        // 128 x 64-column slab in shared memory (128-byte swizzle: conflict-free) and one thread hands it to the TMA.
+        const int      q      = warp & 3;          // TMEM lane quadrant this warp may access
+        const uint32_t group  = (warp - 2) >> 2;   // 0: even local tiles / accumulator 0, 1: odd tiles / accumulator 1
+        const int      row    = q * 32 + lane;
+        const bool     leader = (warp - 2) % 4 == 0 && lane == 0;
         const GemmEpilogue & ep = p.ep;
-        uint32_t t = 0;
+        const uint32_t stg16 = smem_u32(stage_base + (size_t)group * (stg16_bytes + stg32_bytes));
+        const uint32_t stg32 = stg16 + (uint32_t)stg16_bytes;
+        const uint32_t swz   = (uint32_t)(row & 7);
+        const uint32_t rbar  = smem_u32(&res_full[group]);
+        uint32_t t = 0, ri = 0;
         for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
             if ((t & 1u) != group) continue;
-            const int      m   = tile * kBlockM + row;
+            const int      m0  = tile * kBlockM;
+            const int      m   = m0 + row;
             const uint32_t acc = group, aph = (t >> 1) & 1u;
             mbar_wait(smem_u32(&tmem_full[acc]), aph);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-                if (n0 + c0 >= p.N) break;  // warp-uniform
-                float v[32];
-                tmem_ld_32x32(tmem_d + (uint32_t)c0, v);
-                if (m < p.M) {
+            for (int cc = 0; cc < p.block_n; cc += 64) {
+                if (n0 + cc >= p.N) break;  // group-uniform
+                // the previous slab of this group must have been read out by the TMA before it is overwritten
+                if (leader) tma_store_wait_read();
+                named_bar_sync(1 + group, 128);
+                if (ep.res32) {
+                    // the f32 residual slab(s) of this chunk land in the staging buffer and are updated in place
+                    if (leader) {
+                        const bool two = cc + 32 < p.block_n && n0 + cc + 32 < p.N;
+                        mbar_expect_tx(rbar, (uint32_t)(kBlockM * 128 * (two ? 2 : 1)));
+                        tma_load_2d(stg32, &map_r32, n0 + cc, m0, rbar);
+                        if (two) tma_load_2d(stg32 + kBlockM * 128, &map_r32, n0 + cc + 32, m0, rbar);
+                    }
+                }
+                bool res_ready = !ep.res32;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const int c0 = cc + half * 32;
+                    if (c0 >= p.block_n || n0 + c0 >= p.N) break;  // group-uniform
+                    float v[32];
+                    tmem_ld_32x32(tmem_d + (uint32_t)c0, v);
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         const int n = n0 + c0 + g * 8;
-                        if (n + 8 <= p.N) {
-                            float y[8];
+                        float y[8];
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                float tt = fmaf(v[g * 8 + j], s_scale[c0 + g * 8 + j], s_shift[c0 + g * 8 + j]);
-                                y[j]     = ep.act ? silu_f(tt) : tt;
+                        for (int j = 0; j < 8; j++) {
+                            float tt = fmaf(v[g * 8 + j], s_scale[c0 + g * 8 + j], s_shift[c0 + g * 8 + j]);
+                            y[j]     = ep.act ? silu_f(tt) : tt;
+                        }
+                        if (ep.res32) {
+                            if (!res_ready) {
+                                mbar_wait(rbar, ri & 1u);
+                                res_ready = true;
                             }
-                            if (ep.res32) {
-                                const float4 r0 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n);
-                                const float4 r1 = *reinterpret_cast<const float4 *>(ep.res32 + (size_t)m * ep.ldr32 + n + 4);
-                                y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
-                                y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
-                            }
+                            const uint32_t base = stg32 + (uint32_t)half * (kBlockM * 128) + (uint32_t)row * 128;
+                            const float4 r0 = ld_shared_f4(base + (((uint32_t)(2 * g) ^ swz) << 4));
+                            const float4 r1 = ld_shared_f4(base + (((uint32_t)(2 * g + 1) ^ swz) << 4));
+                            y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w;
+                            y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+                        }
+                        if (m < p.M && n + 8 <= p.N) {
                             if (ep.res16) {
                                 const uint4    rr = *reinterpret_cast<const uint4 *>(ep.res16 + (size_t)m * ep.ldr16 + n);
                                 const __half2 * h = reinterpret_cast<const __half2 *>(&rr);
@@ -333,20 +395,35 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                                     y[2 * j + 1] += f.y;
                                 }
                             }
-                            if (ep.out32) {
-                                float4 * o = reinterpret_cast<float4 *>(ep.out32 + (size_t)m * ep.ld32 + n);
-                                o[0]       = make_float4(y[0], y[1], y[2], y[3]);
-                                o[1]       = make_float4(y[4], y[5], y[6], y[7]);
-                            }
-                            if (ep.out16) {
-                                uint4      o;
-                                __half2 *  h = reinterpret_cast<__half2 *>(&o);
+                        }
+                        if (ep.out32) {  // slab `half`: row-major 32 floats = 8 x 16 B chunks, chunk index XOR (row % 8)
+                            const uint32_t base = stg32 + (uint32_t)half * (kBlockM * 128) + (uint32_t)row * 128;
+                            st_shared_v4(base + (((uint32_t)(2 * g) ^ swz) << 4), __float_as_uint(y[0]), __float_as_uint(y[1]),
+                                         __float_as_uint(y[2]), __float_as_uint(y[3]));
+                            st_shared_v4(base + (((uint32_t)(2 * g + 1) ^ swz) << 4), __float_as_uint(y[4]), __float_as_uint(y[5]),
+                                         __float_as_uint(y[6]), __float_as_uint(y[7]));
+                        }
+                        if (ep.out16) {  // 64 halves per row = 8 chunks; this 8-column group is chunk half*4+g
+                            uint32_t h[4];
 #pragma unroll
-                                for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
-                                *reinterpret_cast<uint4 *>(ep.out16 + (size_t)m * ep.ld16 + n) = o;
+                            for (int j = 0; j < 4; j++) {
+                                __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                                h[j]       = *reinterpret_cast<uint32_t *>(&hh);
                             }
+                            st_shared_v4(stg16 + (uint32_t)row * 128 + (((uint32_t)(half * 4 + g) ^ swz) << 4), h[0], h[1], h[2], h[3]);
                         }
                     }
+                }
+                ri += ep.res32 ? 1u : 0u;
+                fence_proxy_async();             // generic-proxy smem writes -> visible to the TMA (async proxy)
+                named_bar_sync(1 + group, 128);
+                if (leader) {
+                    if (ep.out16) tma_store_2d(&map_o16, stg16, n0 + cc, m0);
+                    if (ep.out32) {
+                        tma_store_2d(&map_o32, stg32, n0 + cc, m0);
+                        if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_2d(&map_o32, stg32 + kBlockM * 128, n0 + cc + 32, m0);
+                    }
+                    tma_store_commit();
                 }
             }
             // this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_32x32): hand the accumulator back
@@ -354,6 +431,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
         }
+        if (leader) tma_store_wait_all();  // all bulk stores of this group have been written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -384,7 +462,7 @@ static encode_tiled_fn get_encode() {
 
 // rank-`rank` f16 tensor map, dims/strides innermost first (strides in bytes for dims 1..rank-1), 128B swizzle
 static void make_map(CUtensorMap * map, const void * base, int rank, const uint64_t * dims, const uint64_t * strides_bytes,
-                     const uint32_t * box) {
+                     const uint32_t * box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; i++) {
@@ -393,7 +471,7 @@ static void make_map(CUtensorMap * map, const void * base, int rank, const uint6
         es[i]   = 1;
     }
     for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
-    CUresult r = get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
+    CUresult r = get_encode()(map, dtype, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -408,21 +486,55 @@ static void make_map(CUtensorMap * map, const void * base, int rank, const uint6
 
 static void choose_tiling(GemmLaunch & L, int N) {
     GemmLaunch::Params & p = L.p;
-    p.n_tiles              = (N + 255) / 256;
+    // Output-heavy shapes (K small against N) are epilogue-bound: 128-column tiles let two CTAs (16 epilogue warps)
+    // share an SM, and re-reading the small A operand from L2 is cheap.  Otherwise one tile spans N (<= 256) so A is
+    // read exactly once.  With several N tiles the tile width is a multiple of the 64-column store slab.
+    const int max_bn       = (N > 128 && 2 * p.K <= N) ? 128 : 256;
+    p.n_tiles              = (N + max_bn - 1) / max_bn;
     int per                = (N + p.n_tiles - 1) / p.n_tiles;
-    p.block_n              = (per + 31) / 32 * 32;
+    p.block_n              = p.n_tiles > 1 ? (per + 63) / 64 * 64 : (per + 31) / 32 * 32;
     // two accumulator stages in TMEM (tile i+1 accumulates while tile i drains); power-of-two column count >= 32
     const int need         = 2 * p.block_n;
     p.tmem_cols            = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const int stage_bytes  = kBlockM * kBlockK * 2 + p.block_n * kBlockK * 2;
+    const int staging      = 2 * ((p.ep.out16 ? kBlockM * 128 : 0) + ((p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0));
     // TMEM (512 columns) and shared memory (~220 KiB usable) decide how many persistent CTAs share an SM
-    L.ctas_per_sm          = p.block_n <= 64 ? 3 : p.block_n <= 128 ? 2 : 1;
-    const int budget       = (216 * 1024) / L.ctas_per_sm - 4096;
-    int       stages       = budget / stage_bytes;
+    int stages = 0;
+    for (L.ctas_per_sm = p.block_n <= 128 ? 2 : 1; L.ctas_per_sm >= 1; L.ctas_per_sm--) {
+        const int budget = (216 * 1024) / L.ctas_per_sm - 1024 - kCtrlBytes - staging;
+        stages           = budget / stage_bytes;
+        if (stages >= 2 || L.ctas_per_sm == 1) break;
+    }
     if (stages > kMaxStage) stages = kMaxStage;
-    if (stages < 2) stages = 2;
+    if (stages < 1) stages = 1;
     p.stages     = stages;
-    L.smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStage + 5) * 8 + 2 * 256 * sizeof(float);
+    L.smem_bytes = 1024 + (size_t)stages * stage_bytes + kCtrlBytes + staging;
+}
+
+// output tensor maps for the TMA-store epilogue: 128-row x 128-byte boxes, 128B swizzle
+static void make_output_maps(GemmLaunch & L) {
+    const GemmEpilogue & ep = L.p.ep;
+    L.map_o16 = L.map_a0;
+    L.map_o32 = L.map_a0;
+    L.map_r32 = L.map_a0;
+    if (ep.res32) {
+        const uint64_t dims[2] = {(uint64_t)L.p.N, (uint64_t)L.p.M};
+        const uint64_t str[1]  = {(uint64_t)ep.ldr32 * 4};
+        const uint32_t box[2]  = {32, (uint32_t)kBlockM};
+        make_map(&L.map_r32, ep.res32, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    }
+    if (ep.out16) {
+        const uint64_t dims[2] = {(uint64_t)L.p.N, (uint64_t)L.p.M};
+        const uint64_t str[1]  = {(uint64_t)ep.ld16 * 2};
+        const uint32_t box[2]  = {64, (uint32_t)kBlockM};
+        make_map(&L.map_o16, ep.out16, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    }
+    if (ep.out32) {
+        const uint64_t dims[2] = {(uint64_t)L.p.N, (uint64_t)L.p.M};
+        const uint64_t str[1]  = {(uint64_t)ep.ld32 * 4};
+        const uint32_t box[2]  = {32, (uint32_t)kBlockM};
+        make_map(&L.map_o32, ep.out32, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    }
 }
 
 static void choose_grid(GemmLaunch & L) {
@@ -456,6 +568,7 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
         const uint32_t box[2]  = {(uint32_t)kBlockK, (uint32_t)p.block_n};
         make_map(&L.map_b, B, 2, dims, str, box);
     }
+    make_output_maps(L);
     choose_grid(L);
     return true;
 }
@@ -501,6 +614,7 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
         const uint32_t box[3]  = {(uint32_t)kBlockK, 1, (uint32_t)p.block_n};
         make_map(&L.map_b, Wt, 3, dims, str, box);
     }
+    make_output_maps(L);
     choose_grid(L);
     return true;
 }
@@ -508,10 +622,10 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
 void gemm_launch(const GemmLaunch & L, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_gemm_tcgen05<<<L.grid, kThreads, L.smem_bytes, st>>>(L.map_a0, L.map_a1, L.map_b, L.p);
+    k_gemm_tcgen05<<<L.grid, kThreads, L.smem_bytes, st>>>(L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
 }
 
 }  // namespace b200

@@ -29,7 +29,7 @@ struct GemmEpilogue {
 
 // A prepared launch: tensor maps are encoded once at plan time, the launch is then replayable / capturable.
 struct GemmLaunch {
-    CUtensorMap map_a0, map_a1, map_b;
+    CUtensorMap map_a0, map_a1, map_b, map_o16, map_o32, map_r32;
     struct Params {
         int M, N, K;
         int block_n, n_tiles, num_kb, stages, tmem_cols;
