@@ -1,0 +1,207 @@
+// dwconv_tma.cu -- K3: depthwise 3x3 + BatchNorm + SiLU over NHWC f16 (replaces ggml_conv_depthwise_2d + BN chain +
+// silu, main.cpp:788,809-850; [ggml-upstream] im2col(F16) + per-channel dot with f32 accumulation).
+//
+// HBM-bound (AI ~3.4 flop/B).  The register-window version was latency-bound (one 8-warp CTA per SM, ~12 KB of loads
+// in flight); here the memory-level parallelism comes from the TMA instead of from threads:
+//   * persistent CTAs; a tile = TH x TW output pixels x 64 channels of one image;
+//   * one thread issues a 4-D TMA box {64 ch, TW*s+2, TH*s+2, 1} for the NEXT tile into the other half of a
+//     double buffer while all threads compute the current one; the image border (pad 1) is the TMA's zero fill,
+//     so the inner loop has no bounds checks;
+//   * thread = (8-channel group, column[, row split]); 128-bit conflict-free LDS, f32 accumulate, fused
+//     scale/shift + SiLU, 128-bit coalesced stores (8 lanes = one pixel's 128 bytes).
+#include "gemm_tcgen05.h"
+#include "internal.h"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ uint32_t dw_smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dw_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t dw_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity) {
+    if (dw_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!dw_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();  // a protocol bug must trap, not hang the GPU
+    }
+}
+__device__ __forceinline__ void dw_tma_load_4d(uint32_t dst, const CUtensorMap * map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ float dw_silu(float x) {
+    const float h = 0.5f * x;
+    float       t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+struct alignas(16) H8 {
+    __half2 h[4];
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) k_dwconv_tma(const __grid_constant__ CUtensorMap map_x, const DwLaunch::Params p) {
+    extern __shared__ __align__(128) unsigned char dw_smem[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    const uint32_t box_bytes = (uint32_t)p.box_w * p.box_h * 128u;
+    const uint32_t sbase     = dw_smem_u32(dw_smem);
+
+    const int cg = threadIdx.x & 7;
+    const int xl = (threadIdx.x >> 3) % p.TW;
+    const int rs = (threadIdx.x >> 3) / p.TW;
+    const int rows_per = p.TH / p.RS;
+
+    if (threadIdx.x == 0) {
+        dw_mbar_init(dw_smem_u32(&full_bar[0]), 1);
+        dw_mbar_init(dw_smem_u32(&full_bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int buf) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int cb = t % p.cblocks;
+        const int n  = t / p.cblocks;
+        const uint32_t bar = dw_smem_u32(&full_bar[buf]);
+        dw_mbar_expect_tx(bar, box_bytes);
+        dw_tma_load_4d(sbase + (uint32_t)buf * box_bytes, &map_x, cb * 64, tx * p.TW * STRIDE - 1, ty * p.TH * STRIDE - 1, n, bar);
+    };
+
+    uint32_t it = 0;
+    if (threadIdx.x == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+        const int buf  = it & 1;
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < p.ntiles) issue(next, buf ^ 1);  // buffer buf^1 was released by the barrier below
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int cb = t % p.cblocks;
+        const int n  = t / p.cblocks;
+        const int c0 = cb * 64 + cg * 8;
+        const int ox = tx * p.TW + xl;
+        const bool lane_ok = c0 < p.C && ox < p.OW;
+
+        float w[9][8], sc[8], sh[8];
+        if (lane_ok) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const H8 v = *reinterpret_cast<const H8 *>(p.Wt + (size_t)k * p.C + c0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 f = __half22float2(v.h[j]);
+                    w[k][2 * j] = f.x; w[k][2 * j + 1] = f.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                sc[j] = p.scale ? p.scale[c0 + j] : 1.f;
+                sh[j] = p.shift ? p.shift[c0 + j] : 0.f;
+            }
+        }
+        dw_mbar_wait(dw_smem_u32(&full_bar[buf]), (it >> 1) & 1u);
+        if (lane_ok) {
+            const unsigned char * tile_smem = dw_smem + (size_t)buf * box_bytes + cg * 16;
+            for (int r = 0; r < rows_per; r++) {
+                const int oyl = rs * rows_per + r;
+                const int oy  = ty * p.TH + oyl;
+                if (oy >= p.OH) break;
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+                for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 3; kw++) {
+                        const H8 v = *reinterpret_cast<const H8 *>(tile_smem + ((size_t)(oyl * STRIDE + kh) * p.box_w + (xl * STRIDE + kw)) * 128);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float2 f = __half22float2(v.h[j]);
+                            acc[2 * j]     = fmaf(f.x, w[kh * 3 + kw][2 * j], acc[2 * j]);
+                            acc[2 * j + 1] = fmaf(f.y, w[kh * 3 + kw][2 * j + 1], acc[2 * j + 1]);
+                        }
+                    }
+                H8 o;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float y0 = fmaf(acc[2 * j], sc[2 * j], sh[2 * j]);
+                    float y1 = fmaf(acc[2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]);
+                    if (p.act) { y0 = dw_silu(y0); y1 = dw_silu(y1); }
+                    o.h[j] = __floats2half2_rn(y0, y1);
+                }
+                *reinterpret_cast<H8 *>(p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.C + c0) = o;
+            }
+        }
+        __syncthreads();  // every thread is done with buffer `buf`: it may be refilled by the issue of the next iteration
+    }
+}
+
+}  // namespace
+
+bool dw_prepare(DwLaunch & L, const __half * x, int N, int H, int W, int C, int stride, const __half * Wt, const float * scale,
+                const float * shift, int act, __half * out) {
+    if (C % 8 || H % stride || W % stride || (stride != 1 && stride != 2)) return false;
+    L = DwLaunch();
+    DwLaunch::Params & p = L.p;
+    p.N = N; p.H = H; p.W = W; p.C = C; p.stride = stride;
+    p.OH = H / stride; p.OW = W / stride;
+    p.TW = p.OW >= 32 && stride == 1 ? 32 : (p.OW >= 16 ? 16 : (p.OW >= 8 ? 8 : (p.OW >= 4 ? 4 : (p.OW >= 2 ? 2 : 1))));
+    p.RS = 32 / p.TW;  // 256 threads = 8 channel groups x TW columns x RS row splits
+    if (p.RS < 1) p.RS = 1;
+    int th = stride == 1 ? 8 : 4;
+    if (th < p.RS) th = p.RS;
+    while (th > p.OH && th > p.RS) th /= 2;
+    if (th % p.RS) th = p.RS;
+    p.TH = th;
+    p.tiles_x = (p.OW + p.TW - 1) / p.TW;
+    p.tiles_y = (p.OH + p.TH - 1) / p.TH;
+    p.cblocks = (C + 63) / 64;
+    p.box_w   = p.TW * stride + 2;
+    p.box_h   = p.TH * stride + 2;
+    p.ntiles  = N * p.cblocks * p.tiles_y * p.tiles_x;
+    p.act = act; p.Wt = Wt; p.scale = scale; p.shift = shift; p.out = out;
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t str[3]  = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    const uint32_t box[4]  = {64, (uint32_t)p.box_w, (uint32_t)p.box_h, 1};
+    if (p.box_w > 256 || p.box_h > 256) return false;
+    tma_encode(&L.map_x, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    L.smem_bytes = (size_t)2 * p.box_w * p.box_h * 128;
+    const int per_sm = L.smem_bytes <= 100 * 1024 ? 2 : 1;
+    const int cap    = per_sm * runtime().sm_count;
+    L.grid           = p.ntiles < cap ? p.ntiles : cap;
+    return true;
+}
+
+void dw_launch(const DwLaunch & L, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        B200_CHECK(cudaFuncSetAttribute(k_dwconv_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_dwconv_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    const int threads = 8 * L.p.TW * L.p.RS;
+    if (L.p.stride == 1) k_dwconv_tma<1><<<L.grid, threads, L.smem_bytes, st>>>(L.map_x, L.p);
+    else k_dwconv_tma<2><<<L.grid, threads, L.smem_bytes, st>>>(L.map_x, L.p);
+}
+
+}  // namespace b200

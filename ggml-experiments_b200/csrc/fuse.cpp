@@ -714,8 +714,14 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const float *scale = P.pool.ptr<float>(n->c_scale), *shift = P.pool.ptr<float>(n->c_shift);
                 const int N = in->N, H = in->H, W = in->W, C = in->C, stride = n->stride, act = n->act;
                 __half * o16 = o->p16;
-                add_launch(plan, "dwconv3x3_bn_silu", [=](cudaStream_t st) { launch_dwconv(x, N, H, W, C, stride, wt, scale, shift, act, o16, st); },
-                           2.0 * o->rows() * C * 9, ((double)in->rows() + (double)o->rows()) * C * 2, what);
+                auto DL = std::make_shared<DwLaunch>();
+                if (getenv("GGML_B200_DW_V1") == nullptr && dw_prepare(*DL, x, N, H, W, C, stride, wt, scale, shift, act, o16)) {
+                    add_launch(plan, "dwconv3x3_tma_bn_silu", [DL](cudaStream_t st) { dw_launch(*DL, st); }, 2.0 * o->rows() * C * 9,
+                               ((double)in->rows() + (double)o->rows()) * C * 2, what);
+                } else {
+                    add_launch(plan, "dwconv3x3_bn_silu", [=](cudaStream_t st) { launch_dwconv(x, N, H, W, C, stride, wt, scale, shift, act, o16, st); },
+                               2.0 * o->rows() * C * 9, ((double)in->rows() + (double)o->rows()) * C * 2, what);
+                }
             } break;
             case FK_CONV1: case FK_LINEAR: case FK_QKV: {
                 FVal * in = n->in[0];

@@ -460,6 +460,21 @@ static encode_tiled_fn get_encode() {
     return fn;
 }
 
+void tma_encode(CUtensorMap * map, const void * base, CUtensorMapDataType dtype, int rank, const uint64_t * dims,
+                const uint64_t * strides_bytes, const uint32_t * box, CUtensorMapSwizzle swizzle) {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) {
+        gdim[i] = dims[i];
+        bx[i]   = box[i];
+        es[i]   = 1;
+    }
+    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+    CUresult r = get_encode()(map, dtype, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) B200_ABORT("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
+}
+
 // rank-`rank` f16 tensor map, dims/strides innermost first (strides in bytes for dims 1..rank-1), 128B swizzle
 static void make_map(CUtensorMap * map, const void * base, int rank, const uint64_t * dims, const uint64_t * strides_bytes,
                      const uint32_t * box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {

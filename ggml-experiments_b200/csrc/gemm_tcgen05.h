@@ -56,4 +56,26 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
 
 void gemm_launch(const GemmLaunch & L, cudaStream_t st);
 
+// generic cuTensorMapEncodeTiled wrapper (dims/strides innermost first; strides in bytes for dims 1..rank-1)
+void tma_encode(CUtensorMap * map, const void * base, CUtensorMapDataType dtype, int rank, const uint64_t * dims,
+                const uint64_t * strides_bytes, const uint32_t * box, CUtensorMapSwizzle swizzle);
+
+// K3 depthwise 3x3 (stride 1|2, pad 1) + BN scale/shift + SiLU over NHWC f16, input tiles staged by TMA
+struct DwLaunch {
+    CUtensorMap map_x;
+    struct Params {
+        int N, H, W, C, OH, OW, stride;
+        int TW, TH, RS, tiles_x, tiles_y, cblocks, box_w, box_h, ntiles, act;
+        const __half * Wt;     // [3][3][C]
+        const float *  scale;  // [C] or null
+        const float *  shift;
+        __half *       out;    // [N, OH, OW, C]
+    } p;
+    size_t smem_bytes;
+    int    grid;
+};
+bool dw_prepare(DwLaunch & L, const __half * x, int N, int H, int W, int C, int stride, const __half * Wt, const float * scale,
+                const float * shift, int act, __half * out);
+void dw_launch(const DwLaunch & L, cudaStream_t st);
+
 }  // namespace b200
