@@ -231,6 +231,7 @@ struct ConvArgs {
     float * dst;   // [OW,OH,OC,N]
     int64_t M, N, K;  // M = OC, N = OW*OH, K = IC*KH*KW
     int     OW, OH, KW, KH, s0, s1, p0, p1, d0, d1;
+    int     round_act;  // 0 in EXACT_F32 mode
 };
 struct ConvLoader {
     const ConvArgs & g;
@@ -251,7 +252,8 @@ struct ConvLoader {
         int64_t ox = n % g.OW, oy = n / g.OW;
         int64_t ix = ox * g.s0 + kw * g.d0 - g.p0, iy = oy * g.s1 + kh * g.d1 - g.p1;
         if (ix < 0 || ix >= g.x.ne[0] || iy < 0 || iy >= g.x.ne[1]) return 0.f;
-        return round_f16(*(const float *)(px + ix * g.x.nb[0] + iy * g.x.nb[1] + ic * g.x.nb[2]));
+        const float v = *(const float *)(px + ix * g.x.nb[0] + iy * g.x.nb[1] + ic * g.x.nb[2]);
+        return g.round_act ? round_f16(v) : v;
     }
     __device__ void store(int64_t m, int64_t n, float v) const { pc[n + g.N * m] = v; }
 };
@@ -358,6 +360,7 @@ struct DwArgs {
     V4      w, x;
     float * dst;
     int     OW, OH, KW, KH, s0, s1, p0, p1, d0, d1;
+    int     round_act;
     int64_t C, Nb, total;
 };
 __global__ void k_dwconv(DwArgs g) {
@@ -374,7 +377,8 @@ __global__ void k_dwconv(DwArgs g) {
                 int64_t ix = ox * g.s0 + kw * g.d0 - g.p0;
                 if (ix < 0 || ix >= g.x.ne[0]) continue;
                 float wv = round_f16(load_as_f32(g.w.p + kw * g.w.nb[0] + kh * g.w.nb[1] + c * g.w.nb[3], g.w.type));
-                float xv = round_f16(*(const float *)(g.x.p + ix * g.x.nb[0] + iy * g.x.nb[1] + c * g.x.nb[2] + n * g.x.nb[3]));
+                float xv = *(const float *)(g.x.p + ix * g.x.nb[0] + iy * g.x.nb[1] + c * g.x.nb[2] + n * g.x.nb[3]);
+                if (g.round_act) xv = round_f16(xv);
                 s        = fmaf(wv, xv, s);
             }
         }
@@ -498,7 +502,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                 g.dst = (float *)d;
                 g.M = t->ne[0]; g.N = t->ne[1]; g.K = t->src[0]->ne[0];
                 g.ne2 = t->ne[2];
-                g.round_b = t->src[0]->type == GGML_TYPE_F16;
+                g.round_b = t->src[0]->type == GGML_TYPE_F16 && runtime().mode != GGML_B200_MODE_EXACT_F32;
                 dim3 grid((unsigned)((g.M + 63) / 64), (unsigned)((g.N + 63) / 64), (unsigned)(t->ne[2] * t->ne[3]));
                 const double nb = (double)(t->ne[2] * t->ne[3]);
                 add_launch(plan, "exact_mul_mat", [=](cudaStream_t st) { k_tiled_gemm<MulMatArgs, MulMatLoader><<<grid, 256, 0, st>>>(g); },
@@ -514,6 +518,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                 g.M = t->ne[2]; g.N = t->ne[0] * t->ne[1]; g.K = t->src[0]->ne[2] * g.KW * g.KH;
                 g.s0 = t->op_params[0]; g.s1 = t->op_params[1]; g.p0 = t->op_params[2]; g.p1 = t->op_params[3];
                 g.d0 = t->op_params[4]; g.d1 = t->op_params[5];
+                g.round_act = runtime().mode != GGML_B200_MODE_EXACT_F32;
                 dim3 grid((unsigned)((g.M + 63) / 64), (unsigned)((g.N + 63) / 64), (unsigned)t->ne[3]);
                 add_launch(plan, "exact_conv_2d", [=](cudaStream_t st) { k_tiled_gemm<ConvArgs, ConvLoader><<<grid, 256, 0, st>>>(g); },
                            2.0 * g.M * g.N * g.K * (double)t->ne[3], (double)ggml_nbytes(t) + (double)ggml_nbytes(t->src[1]) + (double)ggml_nbytes(t->src[0]));
@@ -527,6 +532,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                 g.KW = (int)t->src[0]->ne[0]; g.KH = (int)t->src[0]->ne[1];
                 g.s0 = t->op_params[0]; g.s1 = t->op_params[1]; g.p0 = t->op_params[2]; g.p1 = t->op_params[3];
                 g.d0 = t->op_params[4]; g.d1 = t->op_params[5];
+                g.round_act = runtime().mode != GGML_B200_MODE_EXACT_F32;
                 int grid = grid_for(ne);
                 add_launch(plan, "exact_conv_depthwise_2d", [=](cudaStream_t st) { k_dwconv<<<grid, 256, 0, st>>>(g); },
                            2.0 * (double)ne * g.KW * g.KH, (double)ggml_nbytes(t) + (double)ggml_nbytes(t->src[1]));

@@ -40,6 +40,7 @@ void ensure_device() {
     const char * m = getenv("GGML_B200_MODE");
     if (m) {
         if (!strcmp(m, "exact")) rt.mode = GGML_B200_MODE_EXACT;
+        if (!strcmp(m, "exact_f32")) rt.mode = GGML_B200_MODE_EXACT_F32;
         if (!strcmp(m, "fast")) rt.mode = GGML_B200_MODE_FAST;
     }
     const char * v = getenv("GGML_B200_VERBOSE");
@@ -255,7 +256,7 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
             fprintf(stderr, "libggml_b200: graph not recognised by the fused planner; using the per-node exact plan (still on device)\n");
     }
     if (!fast_ok) build_exact_plan(plan, gf);
-    plan->mode = fast_ok ? GGML_B200_MODE_FAST : GGML_B200_MODE_EXACT;
+    plan->mode = fast_ok ? GGML_B200_MODE_FAST : (runtime().mode == GGML_B200_MODE_EXACT_F32 ? GGML_B200_MODE_EXACT_F32 : GGML_B200_MODE_EXACT);
     // host shadows for graph outputs
     for (int i = 0; i < gf->n_nodes; i++) {
         ggml_tensor * t = gf->nodes[i];

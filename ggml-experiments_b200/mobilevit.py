@@ -88,7 +88,7 @@ def lib_mobilevit() -> ctypes.CDLL:
     return _mv
 
 
-FAST, EXACT = 0, 1
+FAST, EXACT, EXACT_F32 = 0, 1, 2
 
 
 def set_mode(mode: int) -> None:

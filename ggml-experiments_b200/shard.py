@@ -1,0 +1,33 @@
+"""Multi-GPU sharding of the batch: images are independent (attention never crosses images,
+main.cpp:976-983), so a batch splits into contiguous per-rank sub-batches; weights are replicated; there is NO device
+collective on the data path -- only a final host-side gather of the per-image logits.
+
+`torch.distributed` is used as plumbing (gloo on CPU for the tests, nccl/gloo under torchrun on the GPU box)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced split: the first (n_total % world) ranks get one extra image."""
+    base, extra = divmod(n_total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_rows(local: np.ndarray, n_total: int, rank: int, world: int, dist=None, dst: int = 0):
+    """Host-side gather of per-image rows ([n_local, ...]) to rank `dst`; returns the full array there, None elsewhere.
+    Ragged shards are padded to the largest shard for the collective and trimmed afterwards."""
+    if world == 1:
+        return local
+    import torch
+    counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    mx = max(counts)
+    pad = np.zeros((mx,) + local.shape[1:], dtype=local.dtype)
+    pad[: local.shape[0]] = local
+    t = torch.from_numpy(pad)
+    out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, out, dst=dst)
+    if rank != dst:
+        return None
+    return np.concatenate([o.numpy()[:c] for o, c in zip(out, counts)], axis=0)

@@ -11,6 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libmvit_oracle.so")
 PURE_F32 = 1
+NO_ACT_ROUND = 2
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 

@@ -30,6 +30,8 @@
 
 #define MVO_MAX_TENSORS 512
 #define MVO_FLAG_PURE_F32 1 /* skip every f16 rounding point: == HF torch f32 semantics */
+#define MVO_FLAG_NO_ACT_ROUND 2 /* weights stay f16-rounded (as loaded, main.cpp:928-932) but activations are not rounded:
+                                  a smooth function, used to validate the GPU EXACT_F32 mode to max-abs 1e-3 */
 
 /* ------------------------------------------------------------------------------------------------
  * fp16 rounding: [ggml] GGML_FP32_TO_FP16 on x86 with F16C = _cvtss_sh(x, 0) (round-to-nearest-even)
@@ -279,6 +281,7 @@ void mvo_gemm(int M, int N, int K, const float *A, int lda, const float *B, int 
 void mvo_conv2d(const float *x, int C, int H, int W, const float *k_tf, int KH, int KW, int OC, int stride,
                 float *out, int flags) {
     const int pure = flags & MVO_FLAG_PURE_F32;
+    const int pure_act = flags & (MVO_FLAG_PURE_F32 | MVO_FLAG_NO_ACT_ROUND);
     const int p = (KW - 1) / 2;
     const int OH = (H + 2 * p - (KH - 1) - 1) / stride + 1;
     const int OW = (W + 2 * p - (KW - 1) - 1) / stride + 1;
@@ -310,7 +313,7 @@ void mvo_conv2d(const float *x, int C, int H, int W, const float *k_tf, int KH, 
                     }
                 }
             }
-    round_f16_array(col, col, (size_t)K * P, pure);
+    round_f16_array(col, col, (size_t)K * P, pure_act);
     mvo_gemm(OC, (int)P, K, wk, K, col, (int)P, out, (int)P);
     free(col);
     free(wk);
@@ -325,7 +328,7 @@ void mvo_dwconv2d(const float *x, int C, int H, int W, const float *k_tf, int KH
     const int OH = (H + 2 * p - (KH - 1) - 1) / stride + 1;
     const int OW = (W + 2 * p - (KW - 1) - 1) / stride + 1;
     float *xr = (float *)malloc((size_t)C * H * W * sizeof(float));
-    round_f16_array(x, xr, (size_t)C * H * W, pure);
+    round_f16_array(x, xr, (size_t)C * H * W, flags & (MVO_FLAG_PURE_F32 | MVO_FLAG_NO_ACT_ROUND));
     for (int c = 0; c < C; c++) {
         float wk[49];
         for (int kh = 0; kh < KH; kh++)

@@ -89,3 +89,20 @@ def test_unmodified_reference_programs_compile_and_link_against_the_boundary(tmp
         r = subprocess.run(["g++", "-O0", "-std=c++17", "-w", "-I" + inc, *extra, src, "-o", exe, "-L" + lib_dir, "-lggml_b200"],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_product_never_imports_or_links_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package or include/ may import, call or link it."""
+    pkg = os.path.join(ROOT, "ggml-experiments_b200")
+    banned = ("import oracle", "from oracle", "mvo_", "libmvit_oracle", "oracle/")
+    for top in (pkg, os.path.join(ROOT, "include")):
+        for base, _, files in os.walk(top):
+            if "_build" in base or "__pycache__" in base:
+                continue
+            for fn in files:
+                if fn.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                    text = open(os.path.join(base, fn)).read()
+                    for tok in banned:
+                        assert tok not in text, f"{fn} references the oracle ({tok})"
+    out = subprocess.run(["ldd", os.path.join(pkg, "_build", "libggml_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
