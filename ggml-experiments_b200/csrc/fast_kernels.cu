@@ -40,13 +40,18 @@ __device__ __forceinline__ Half8 pack8(const float * f) {
 // K2 stem: replaces ggml_conv_2d (im2col f16 + mul_mat) + BN chain + silu of conv_stem (main.cpp:618,771-852)
 // One thread = one output pixel, all OC channels (OC <= 32).  HBM-bound: 12 B/pixel in (x9 from L1/L2), 2*OC B out.
 // ---------------------------------------------------------------------------------------------------------
+// Block = 16 x 32 output pixels of one image (thread = 2 pixels, rows ty and ty+8).  The 33 x 65 x 3 input patch is
+// staged once in shared memory (coalesced, rounded to f16 like ggml's im2col), weights are broadcast LDS.128 reads
+// shared by both pixels of the thread.
 template <int OC>
 __global__ void __launch_bounds__(256) k_stem(const float * __restrict__ x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N,
                                               int H, int W, const __half * __restrict__ Wt, const float * __restrict__ scale,
                                               const float * __restrict__ shift, int act, __half * __restrict__ out16,
-                                              float * __restrict__ out32) {
-    __shared__ float sw[27 * OC];  // [tap*3+ic][oc]
+                                              float * __restrict__ out32, int tiles_x, int tiles_y) {
+    constexpr int TH = 16, TW = 32, IH = 2 * TH + 1, IW = 2 * TW + 1, IWS = IW * 3 + 1;
+    __shared__ __align__(16) float sw[27 * OC];  // [tap*3+ic][oc]
     __shared__ float ss[OC], sh[OC];
+    __shared__ float sx_[IH * IWS];
     for (int i = threadIdx.x; i < 27 * OC; i += blockDim.x) {
         int k = i / OC, oc = i % OC;  // k = (kh*3+kw)*3+ic ; Wt is [oc][kh][kw][ic]
         sw[i] = __half2float(Wt[oc * 27 + k]);
@@ -55,62 +60,75 @@ __global__ void __launch_bounds__(256) k_stem(const float * __restrict__ x, int6
         ss[i] = scale ? scale[i] : 1.f;
         sh[i] = shift ? shift[i] : 0.f;
     }
-    __syncthreads();
     const int OH = H / 2, OW = W / 2;
-    const int total = N * OH * OW;  // < 2^31 pixels
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-        const int ox = p % OW, r_ = p / OW;
-        const int oy = r_ % OH, n = r_ / OH;
-        float acc[OC];
+    int       b  = blockIdx.x;
+    const int tx0 = (b % tiles_x) * TW; b /= tiles_x;
+    const int ty0 = (b % tiles_y) * TH;
+    const int n   = b / tiles_y;
+    const int iy0 = 2 * ty0 - 1, ix0 = 2 * tx0 - 1;
+    const float * xn = x + n * sn;
+    for (int i = threadIdx.x; i < IH * IW * 3; i += blockDim.x) {
+        const int c = i % 3, xx = (i / 3) % IW, yy = i / (3 * IW);
+        const int iy = iy0 + yy, ix = ix0 + xx;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __half2float(__float2half_rn(xn[iy * sy + ix * sx + c * sc]));  // ggml im2col rounds to f16
+        sx_[yy * IWS + xx * 3 + c] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float acc[2][OC];
 #pragma unroll
-        for (int o = 0; o < OC; o++) acc[o] = 0.f;
+    for (int o = 0; o < OC; o++) acc[0][o] = acc[1][o] = 0.f;
 #pragma unroll
-        for (int kh = 0; kh < 3; kh++) {
-            const int iy = oy * 2 + kh - 1;
-            if (iy < 0 || iy >= H) continue;
+    for (int kh = 0; kh < 3; kh++)
 #pragma unroll
-            for (int kw = 0; kw < 3; kw++) {
-                const int ix = ox * 2 + kw - 1;
-                if (ix < 0 || ix >= W) continue;
-                const float * px = x + n * sn + iy * sy + ix * sx;
+        for (int kw = 0; kw < 3; kw++)
 #pragma unroll
-                for (int ic = 0; ic < 3; ic++) {
-                    const float   v = __half2float(__float2half_rn(px[ic * sc]));  // ggml im2col rounds activations to f16
-                    const float * w = &sw[((kh * 3 + kw) * 3 + ic) * OC];
+            for (int ic = 0; ic < 3; ic++) {
+                const float v0 = sx_[(2 * ty + kh) * IWS + (2 * tx + kw) * 3 + ic];
+                const float v1 = sx_[(2 * (ty + 8) + kh) * IWS + (2 * tx + kw) * 3 + ic];
+                const float4 * w4 = reinterpret_cast<const float4 *>(&sw[((kh * 3 + kw) * 3 + ic) * OC]);
 #pragma unroll
-                    for (int o = 0; o < OC; o++) acc[o] = fmaf(v, w[o], acc[o]);
+                for (int o4 = 0; o4 < OC / 4; o4++) {
+                    const float4 w = w4[o4];
+                    acc[0][4 * o4 + 0] = fmaf(v0, w.x, acc[0][4 * o4 + 0]); acc[1][4 * o4 + 0] = fmaf(v1, w.x, acc[1][4 * o4 + 0]);
+                    acc[0][4 * o4 + 1] = fmaf(v0, w.y, acc[0][4 * o4 + 1]); acc[1][4 * o4 + 1] = fmaf(v1, w.y, acc[1][4 * o4 + 1]);
+                    acc[0][4 * o4 + 2] = fmaf(v0, w.z, acc[0][4 * o4 + 2]); acc[1][4 * o4 + 2] = fmaf(v1, w.z, acc[1][4 * o4 + 2]);
+                    acc[0][4 * o4 + 3] = fmaf(v0, w.w, acc[0][4 * o4 + 3]); acc[1][4 * o4 + 3] = fmaf(v1, w.w, acc[1][4 * o4 + 3]);
                 }
             }
-        }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int oy = ty0 + ty + 8 * r, ox = tx0 + tx;
+        if (oy >= OH || ox >= OW) continue;
 #pragma unroll
         for (int o = 0; o < OC; o++) {
-            float y = fmaf(acc[o], ss[o], sh[o]);
-            acc[o]  = act ? silu_fast(y) : y;
+            float y   = fmaf(acc[r][o], ss[o], sh[o]);
+            acc[r][o] = act ? silu_fast(y) : y;
         }
+        const int64_t p = ((int64_t)n * OH + oy) * OW + ox;
         if (out16) {
-            Half8 * o = reinterpret_cast<Half8 *>(out16 + (int64_t)p * OC);
+            Half8 * o = reinterpret_cast<Half8 *>(out16 + p * OC);
 #pragma unroll
-            for (int g = 0; g < OC / 8; g++) o[g] = pack8(acc + g * 8);
+            for (int g = 0; g < OC / 8; g++) o[g] = pack8(acc[r] + g * 8);
         }
         if (out32) {
-            float4 * o = reinterpret_cast<float4 *>(out32 + (int64_t)p * OC);
+            float4 * o = reinterpret_cast<float4 *>(out32 + p * OC);
 #pragma unroll
-            for (int g = 0; g < OC / 4; g++) o[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+            for (int g = 0; g < OC / 4; g++) o[g] = make_float4(acc[r][4 * g], acc[r][4 * g + 1], acc[r][4 * g + 2], acc[r][4 * g + 3]);
         }
     }
 }
 
 void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W, const __half * Wt, int OC,
                  const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st) {
-    const int64_t total = (int64_t)N * (H / 2) * (W / 2);
-    int64_t       nb    = (total + 255) / 256;
-    const int64_t cap   = (int64_t)runtime().sm_count * 32;
-    const int     grid  = (int)(nb > cap ? cap : nb);
+    const int tiles_x = (W / 2 + 31) / 32, tiles_y = (H / 2 + 15) / 16;
+    const int grid    = N * tiles_x * tiles_y;
     switch (OC) {
-        case 8: k_stem<8><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
-        case 16: k_stem<16><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
-        case 24: k_stem<24><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
-        case 32: k_stem<32><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32); break;
+        case 8: k_stem<8><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32, tiles_x, tiles_y); break;
+        case 16: k_stem<16><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32, tiles_x, tiles_y); break;
+        case 24: k_stem<24><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32, tiles_x, tiles_y); break;
+        case 32: k_stem<32><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32, tiles_x, tiles_y); break;
         default: B200_ABORT("stem: unsupported OC %d", OC);
     }
 }
@@ -236,39 +254,47 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// 8 lanes per row (4 rows per warp): C/4 float4 per row split over 8 lanes keeps every lane busy for C = 144..256
+// (one full warp per row left 28 of 32 lanes idle on the second pass of a 36-float4 row and made the kernel issue-bound).
+template <int MAXV>  // float4 per lane = ceil(C / 32), compile-time so no predicated-off iterations are issued
 __global__ void __launch_bounds__(256) k_layernorm(const float * __restrict__ x, int64_t rows, int C, const float * __restrict__ gamma,
                                                    const float * __restrict__ beta, float eps, __half * __restrict__ out16,
                                                    float * __restrict__ out32) {
-    const int     lane = threadIdx.x & 31;
-    const int64_t row  = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float * xr = x + row * C;
-    constexpr int MAXV = 4;  // float4 per lane: C <= 512
+    constexpr int LPR  = 8;   // lanes per row
+    const int     sub  = threadIdx.x & (LPR - 1);
+    const int64_t row  = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+    const bool    live = row < rows;
+    const float * xr   = x + (live ? row : 0) * C;
+    const int     nv   = C >> 2;
     float4        v[MAXV];
-    const int     nv = C / 4;  // C % 4 == 0 (channels are multiples of 8)
-    float         s  = 0.f;
+    float         s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; i++) {
-        const int idx = lane + i * 32;
+        const int idx = sub + i * LPR;
         if (idx < nv) {
-            v[i] = reinterpret_cast<const float4 *>(xr)[idx];
+            v[i] = live ? reinterpret_cast<const float4 *>(xr)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
     }
-    const float mean = warp_sum(s) / (float)C;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
     float       s2   = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; i++) {
-        const int idx = lane + i * 32;
+        const int idx = sub + i * LPR;
         if (idx < nv) {
             v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
             s2 += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
         }
     }
-    const float rstd = rsqrtf(warp_sum(s2) / (float)C + eps);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    const float rstd = rsqrtf(s2 / (float)C + eps);
+    if (!live) return;
 #pragma unroll
     for (int i = 0; i < MAXV; i++) {
-        const int idx = lane + i * 32;
+        const int idx = sub + i * LPR;
         if (idx < nv) {
             const float4 g = reinterpret_cast<const float4 *>(gamma)[idx];
             const float4 b = reinterpret_cast<const float4 *>(beta)[idx];
@@ -279,9 +305,11 @@ __global__ void __launch_bounds__(256) k_layernorm(const float * __restrict__ x,
             y.w = fmaf(v[i].w * rstd, g.w, b.w);
             if (out32) reinterpret_cast<float4 *>(out32 + row * C)[idx] = y;
             if (out16) {
-                __half2 * o = reinterpret_cast<__half2 *>(out16 + row * C) + idx * 2;
-                o[0]        = __floats2half2_rn(y.x, y.y);
-                o[1]        = __floats2half2_rn(y.z, y.w);
+                uint2 o;
+                __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+                o.x = *reinterpret_cast<uint32_t *>(&h0);
+                o.y = *reinterpret_cast<uint32_t *>(&h1);
+                reinterpret_cast<uint2 *>(out16 + row * C)[idx] = o;
             }
         }
     }
@@ -290,8 +318,15 @@ __global__ void __launch_bounds__(256) k_layernorm(const float * __restrict__ x,
 void launch_layernorm(const float * x, int64_t rows, int C, const float * gamma, const float * beta, float eps, __half * out16,
                       float * out32, cudaStream_t st) {
     if (C % 4 || C > 512) B200_ABORT("layernorm: unsupported C %d", C);
-    const int grid = (int)((rows + 7) / 8);
-    k_layernorm<<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out16, out32);
+    const int grid = (int)((rows + 31) / 32);  // 256 threads = 32 rows
+    const int nvl  = (C / 4 + 7) / 8;
+#define LN_CASE(V) case V: k_layernorm<V><<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out16, out32); break;
+    switch (nvl) {
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+        LN_CASE(9) LN_CASE(10) LN_CASE(11) LN_CASE(12) LN_CASE(13) LN_CASE(14) LN_CASE(15) LN_CASE(16)
+        default: B200_ABORT("layernorm: unsupported C %d", C);
+    }
+#undef LN_CASE
 }
 
 // ---------------------------------------------------------------------------------------------------------

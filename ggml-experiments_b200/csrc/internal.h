@@ -119,12 +119,13 @@ struct Plan {
     bool                  upload_inputs = true, download_outputs = true;
     cudaGraphExec_t       graph_exec = nullptr;
     bool                  graph_failed = false;
+    cudaStream_t          private_stream = nullptr;  // set by ggml_b200_graph_use_private_stream (pipelined submission)
     ~Plan();
 };
 
 // plan.cpp
 Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf);
-void   run_plan(Plan * plan);
+void   run_plan(Plan * plan, bool wait_for_results = true);
 void   add_launch(Plan * plan, const char * kernel, Launch l, double flops = 0, double bytes = 0, std::string what = "");
 void   destroy_plans_of(ggml_context * ctx);
 void   fix_graph_pointers(ggml_cgraph * gf);

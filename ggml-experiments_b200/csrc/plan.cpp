@@ -135,6 +135,7 @@ static std::multimap<ggml_context *, Plan *>    g_plans;
 static std::unordered_map<const ggml_tensor *, void *> g_external;  // leaf -> caller-owned device memory
 
 Plan::~Plan() {
+    if (private_stream) { cudaStreamSynchronize(private_stream); cudaStreamDestroy(private_stream); }
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (void * p : owned_device) cudaFree(p);
     for (void * p : pinned) cudaHostUnregister(p);
@@ -291,8 +292,8 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
     return plan;
 }
 
-void run_plan(Plan * plan) {
-    cudaStream_t st = current_stream();
+void run_plan(Plan * plan, bool wait_for_results) {
+    cudaStream_t st = plan->private_stream ? plan->private_stream : current_stream();
     if (plan->upload_inputs)
         for (const Transfer & u : plan->uploads) B200_CHECK(cudaMemcpyAsync(u.dptr, u.t->data, u.bytes, cudaMemcpyHostToDevice, st));
     Runtime & rt = runtime();
@@ -326,7 +327,7 @@ void run_plan(Plan * plan) {
     B200_CHECK(cudaGetLastError());
     if (plan->download_outputs) {
         for (const Transfer & d : plan->downloads) B200_CHECK(cudaMemcpyAsync(d.t->data, d.dptr, d.bytes, cudaMemcpyDeviceToHost, st));
-        B200_CHECK(cudaStreamSynchronize(st));  // ggml semantics: results are readable when compute returns
+        if (wait_for_results) B200_CHECK(cudaStreamSynchronize(st));  // ggml semantics: results are readable when compute returns
     }
 }
 
@@ -346,6 +347,24 @@ extern "C" void ggml_graph_release_plan(struct ggml_cgraph * gf) {
     cudaDeviceSynchronize();
     delete p;
     gf->plan = nullptr;
+}
+
+// ---- pipelined submission: several graphs (e.g. two copies of the same forward graph with their own input/output
+// buffers) each on a private stream, so the H2D copy of batch i+1 and the D2H of batch i-1 overlap the kernels of batch i.
+extern "C" void ggml_b200_graph_use_private_stream(struct ggml_cgraph * gf) {
+    if (!gf->plan) B200_ABORT("ggml_b200_graph_use_private_stream: call ggml_b200_graph_prepare first");
+    Plan * p = (Plan *)gf->plan;
+    if (!p->private_stream) B200_CHECK(cudaStreamCreateWithFlags(&p->private_stream, cudaStreamNonBlocking));
+}
+extern "C" void ggml_b200_graph_compute_async(struct ggml_context * ctx, struct ggml_cgraph * gf) {
+    fix_graph_pointers(gf);
+    Plan * plan = get_or_build_plan(ctx, gf);
+    run_plan(plan, /*wait_for_results=*/false);
+}
+extern "C" void ggml_b200_graph_wait(struct ggml_cgraph * gf) {
+    if (!gf->plan) return;
+    Plan * p = (Plan *)gf->plan;
+    B200_CHECK(cudaStreamSynchronize(p->private_stream ? p->private_stream : current_stream()));
 }
 
 extern "C" void ggml_b200_set_mode(enum ggml_b200_mode mode) { runtime().mode = (int)mode; }

@@ -283,8 +283,8 @@ ggml_tensor * model::build_forward(ggml_context * ctx, ggml_tensor * images_hwc,
     return x;
 }
 
-forward_graph & model::graph_for(int n, int h, int w) {
-    auto key = std::make_tuple(n, h, w);
+forward_graph & model::graph_for(int n, int h, int w, int slot) {
+    auto key = std::make_tuple(n, h, w, slot);
     auto it  = graphs.find(key);
     if (it != graphs.end()) return it->second;
     forward_graph g;
@@ -313,11 +313,15 @@ forward_graph & model::graph_for(int n, int h, int w) {
 }
 
 void model::release(int n, int h, int w) {
-    auto it = graphs.find(std::make_tuple(n, h, w));
-    if (it == graphs.end()) return;
-    ggml_graph_release_plan(it->second.gf);
-    ggml_free(it->second.ctx);
-    graphs.erase(it);
+    for (auto it = graphs.begin(); it != graphs.end();) {
+        if (std::get<0>(it->first) == n && std::get<1>(it->first) == h && std::get<2>(it->first) == w) {
+            ggml_graph_release_plan(it->second.gf);
+            ggml_free(it->second.ctx);
+            it = graphs.erase(it);
+        } else {
+            ++it;
+        }
+    }
 }
 
 }  // namespace mvit
@@ -392,6 +396,41 @@ extern "C" int64_t mvit_debug_stage(mvit_model * m, int n, int h, int w, int idx
     if (!t->data || cnt > cap_floats) return -2;
     memcpy(out, t->data, (size_t)cnt * sizeof(float));
     return cnt;
+}
+
+// ---- pipelined slots: slot s has its own input buffer, output shadows, device arena and stream ----
+static mvit::forward_graph * slot_graph(mvit_model * m, int n, int h, int w, int slot) {
+    if (!m || !shape_ok(n, h, w) || slot < 0 || slot > 7) return nullptr;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w, 1 + slot);  // slot graphs are distinct from the synchronous one (0)
+    if (!g.gf->plan) {
+        ggml_b200_graph_prepare(g.ctx, g.gf);
+        ggml_b200_graph_use_private_stream(g.gf);
+    }
+    return &g;
+}
+extern "C" float * mvit_slot_input(mvit_model * m, int n, int h, int w, int slot) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    return g ? (float *)ggml_get_data(g->input_hwc) : nullptr;
+}
+extern "C" int mvit_slot_submit(mvit_model * m, int n, int h, int w, int slot) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    if (!g) return 1;
+    ggml_b200_graph_compute_async(g->ctx, g->gf);
+    return 0;
+}
+extern "C" int mvit_slot_wait(mvit_model * m, int n, int h, int w, int slot) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    if (!g) return 1;
+    ggml_b200_graph_wait(g->gf);
+    return 0;
+}
+extern "C" const float * mvit_slot_features(mvit_model * m, int n, int h, int w, int slot) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    return g ? (const float *)ggml_get_data(g->features) : nullptr;
+}
+extern "C" const float * mvit_slot_pooled(mvit_model * m, int n, int h, int w, int slot) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    return g ? (const float *)ggml_get_data(g->pooled) : nullptr;
 }
 
 extern "C" int mvit_prepare(mvit_model * m, int n, int h, int w) {

@@ -73,10 +73,10 @@ struct model {  // mobilevit_model, main.cpp:202-213
     ggml_context *                       ctx_w = nullptr;
     std::map<std::string, ggml_tensor *> tensors;
     int64_t                              total_weights = 0;
-    std::map<std::tuple<int, int, int>, forward_graph> graphs;
+    std::map<std::tuple<int, int, int, int>, forward_graph> graphs;  // key: (n, h, w, slot)
 
     bool            load(const std::string & path);                  // load_model_v2, main.cpp:314-515
-    forward_graph & graph_for(int n, int h, int w);                  // builds (once) the batched forward graph
+    forward_graph & graph_for(int n, int h, int w, int slot = 0);    // builds (once) the batched forward graph
     ggml_tensor *   build_forward(ggml_context * ctx, ggml_tensor * images_hwc, ggml_tensor ** pooled,
                                   std::vector<ggml_tensor *> * stages = nullptr) const;
     void            release(int n, int h, int w);

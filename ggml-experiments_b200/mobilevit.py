@@ -82,6 +82,11 @@ def lib_mobilevit() -> ctypes.CDLL:
         L.mvit_debug_stage.restype = ctypes.c_int64
         L.mvit_debug_stage.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p,
                                        ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+        for name in ("mvit_slot_input", "mvit_slot_features", "mvit_slot_pooled"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+            getattr(L, name).restype = _f32p
+        for name in ("mvit_slot_submit", "mvit_slot_wait"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.mvit_release.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.mvit_plan_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PlanInfo)]
         _mv = L
@@ -150,6 +155,22 @@ class MobileViT:
         if cnt < 0:
             raise RuntimeError(f"mvit_debug_stage rc={cnt}")
         return buf[:cnt].reshape(ne[3], ne[2], ne[1], ne[0]).copy()
+
+    # ---- pipelined slots (throughput serving) ----
+    def slot_input(self, n, h, w, slot) -> np.ndarray:
+        return np.ctypeslib.as_array(self._L.mvit_slot_input(self._h, n, h, w, slot), shape=(n, h, w, 3))
+
+    def slot_submit(self, n, h, w, slot) -> None:
+        if self._L.mvit_slot_submit(self._h, n, h, w, slot) != 0:
+            raise ValueError("mvit_slot_submit: invalid arguments")
+
+    def slot_wait(self, n, h, w, slot):
+        if self._L.mvit_slot_wait(self._h, n, h, w, slot) != 0:
+            raise ValueError("mvit_slot_wait: invalid arguments")
+        c = self.out_channels
+        f = np.ctypeslib.as_array(self._L.mvit_slot_features(self._h, n, h, w, slot), shape=(n, c, h // 32, w // 32))
+        p = np.ctypeslib.as_array(self._L.mvit_slot_pooled(self._h, n, h, w, slot), shape=(n, c))
+        return f, p
 
     def profile(self, n, h, w, reps: int = 3) -> list:
         import json

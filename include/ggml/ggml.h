@@ -232,6 +232,13 @@ void   ggml_b200_tensor_set_device_data(struct ggml_tensor * leaf, void * device
 void * ggml_b200_tensor_get_device_data(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor);
 void   ggml_b200_graph_set_transfers(struct ggml_cgraph * cgraph, bool upload_inputs, bool download_outputs);
 
+/* Pipelined submission (throughput serving): give a graph a private stream, submit without waiting, wait later.
+ * With two copies of a forward graph (own input leaf and output shadows each) the H2D copy of batch i+1 and the D2H
+ * copy of batch i-1 overlap the kernels of batch i.  ggml_graph_compute_with_ctx itself stays synchronous. */
+void ggml_b200_graph_use_private_stream(struct ggml_cgraph * cgraph);
+void ggml_b200_graph_compute_async(struct ggml_context * ctx, struct ggml_cgraph * cgraph);
+void ggml_b200_graph_wait(struct ggml_cgraph * cgraph);
+
 /* Introspection of the compiled plan (bench.py's gpu_launches, DESIGN.md's memory-planner numbers). */
 struct ggml_b200_plan_stats {
     int     mode;              /* enum ggml_b200_mode actually used */

@@ -46,6 +46,16 @@ int     mvit_compute(mvit_model * m, int n, int h, int w);         /* H2D + forw
 const float * mvit_host_features(mvit_model * m, int n, int h, int w);  /* [N,C,H/32,W/32] after mvit_compute */
 const float * mvit_host_pooled(mvit_model * m, int n, int h, int w);    /* [N,C] after mvit_compute */
 
+/* ---- pipelined host variant (throughput serving): `slot` in 0..7, each with its own pinned input buffer, output buffers,
+ * device arena and stream.  Fill slot s, submit it (returns immediately), fill and submit slot s+1, then wait for s:
+ * the H2D/D2H copies of one slot overlap the kernels of the other.  Every submit still performs its own H2D + forward +
+ * D2H; only the waiting is deferred. ---- */
+float *       mvit_slot_input(mvit_model * m, int n, int h, int w, int slot);
+int           mvit_slot_submit(mvit_model * m, int n, int h, int w, int slot);
+int           mvit_slot_wait(mvit_model * m, int n, int h, int w, int slot);
+const float * mvit_slot_features(mvit_model * m, int n, int h, int w, int slot);
+const float * mvit_slot_pooled(mvit_model * m, int n, int h, int w, int slot);
+
 /* ---- device-resident variant (bench.py `value`): inputs/outputs stay in HBM -------------------------- */
 int    mvit_prepare(mvit_model * m, int n, int h, int w);           /* build graph + device plan; 0 on success */
 void * mvit_device_input(mvit_model * m, int n, int h, int w);      /* device ptr, [N,H,W,3] f32 */
