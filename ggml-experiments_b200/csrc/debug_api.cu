@@ -63,3 +63,31 @@ extern "C" int ggml_b200_debug_conv3x3(const uint16_t * x0, int C0, const uint16
     B200_CHECK(cudaMemcpy(out32, dO.p, px * OC * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
+
+// Timing probe for kernel tuning: device buffers only (uninitialised A/B are fine for timing), returns mean ms per launch.
+extern "C" float ggml_b200_debug_gemm_time(int M, int N, int K, int act, int want16, int want32, int want_res, int reps) {
+    ensure_device();
+    DevBuf dA(nullptr, (size_t)M * K * 2), dB(nullptr, (size_t)N * K * 2), dS(nullptr, (size_t)N * 4), dH(nullptr, (size_t)N * 4);
+    DevBuf dR(nullptr, want_res ? (size_t)M * N * 4 : 0), dO32(nullptr, want32 ? (size_t)M * N * 4 : 0), dO16(nullptr, want16 ? (size_t)M * N * 2 : 0);
+    GemmEpilogue ep;
+    ep.scale = (const float *)dS.p; ep.shift = (const float *)dH.p; ep.act = act;
+    ep.res32 = (const float *)dR.p; ep.ldr32 = N;
+    ep.out32 = (float *)dO32.p; ep.ld32 = N;
+    ep.out16 = (__half *)dO16.p; ep.ld16 = N;
+    GemmLaunch L;
+    if (!gemm_prepare(L, (const __half *)dA.p, K, (const __half *)dB.p, K, M, N, K, ep)) return -1.f;
+    cudaStream_t st = current_stream();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    gemm_launch(L, st);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; i++) gemm_launch(L, st);
+    cudaEventRecord(e1, st);
+    B200_CHECK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    fprintf(stderr, "gemm %dx%dx%d act=%d: block_n=%d n_tiles=%d stages=%d ctas/sm=%d grid=%ux%u smem=%zu  %.1f us\n", M, N, K, act, L.p.block_n,
+            L.p.n_tiles, L.p.stages, L.ctas_per_sm, L.grid.x, L.grid.y, L.smem_bytes, 1e3f * ms / reps);
+    return ms / reps;
+}

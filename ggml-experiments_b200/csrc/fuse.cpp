@@ -67,6 +67,7 @@ struct FNode {
     const ggml_tensor * leaf = nullptr;
     bool  chw  = false;
     bool  dead = false;
+    bool  fused_into_reduce = false;  // depthwise node executed inside the following reduce conv's kernel (K4a)
     int   order = -1;
     // folded constants (offsets into the plan's constant pool)
     int64_t c_w = -1, c_scale = -1, c_shift = -1;
@@ -709,6 +710,14 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
             } break;
             case FK_DW: {
                 FVal * in = n->in[0];
+                // K4a (experimental, GGML_B200_DWREDUCE=1): depthwise whose only consumer is a 1x1 conv (the reduce of an
+                // inverted residual) runs inside that conv's kernel; its output never goes to HBM.  Parity-green, but in
+                // round 1 still slower than the two separate kernels (one CTA of 8 compute warps per SM), so off by default.
+                if (getenv("GGML_B200_DWREDUCE") != nullptr && o->users.size() == 1 && o->users[0]->kind == FK_CONV1 &&
+                    o->users[0]->in[0] == o && !out_set.count(o) && o->users[0]->out->C <= 256) {
+                    n->fused_into_reduce = true;
+                    break;
+                }
                 const __half * x = in->p16;
                 const __half * wt = P.pool.ptr<__half>(n->c_w);
                 const float *scale = P.pool.ptr<float>(n->c_scale), *shift = P.pool.ptr<float>(n->c_shift);
@@ -725,6 +734,27 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
             } break;
             case FK_CONV1: case FK_LINEAR: case FK_QKV: {
                 FVal * in = n->in[0];
+                if (n->kind == FK_CONV1 && in->prod && in->prod->kind == FK_DW && in->prod->fused_into_reduce) {
+                    FNode * dw = in->prod;
+                    FVal *  xe = dw->in[0];  // the expanded activation
+                    auto DL = std::make_shared<DwRedLaunch>();
+                    if (dwreduce_prepare(*DL, xe->p16, xe->N, xe->H, xe->W, xe->C, dw->stride, P.pool.ptr<__half>(dw->c_w), P.pool.ptr<float>(dw->c_scale),
+                                         P.pool.ptr<float>(dw->c_shift), dw->act, P.pool.ptr<__half>(n->c_w), o->C, P.pool.ptr<float>(n->c_scale),
+                                         P.pool.ptr<float>(n->c_shift), n->act, n->res ? n->res->p32 : nullptr, o->p16, o->p32)) {
+                        const double bytes = (double)xe->rows() * xe->C * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0) + (n->res ? 4 : 0));
+                        add_launch(plan, "dwconv3x3_reduce1x1_fused", [DL](cudaStream_t st) { dwreduce_launch(*DL, st); },
+                                   2.0 * in->rows() * in->C * 9 + 2.0 * in->rows() * o->C * in->C, bytes, "dw+reduce " + what);
+                        break;
+                    }
+                    // shape not supported by the fused kernel: run the depthwise on its own after all
+                    const __half * x = xe->p16;
+                    const __half * wt = P.pool.ptr<__half>(dw->c_w);
+                    const float *scale = P.pool.ptr<float>(dw->c_scale), *shift = P.pool.ptr<float>(dw->c_shift);
+                    const int N = xe->N, H = xe->H, W = xe->W, C = xe->C, stride = dw->stride, act = dw->act;
+                    __half * o16 = in->p16;
+                    add_launch(plan, "dwconv3x3_bn_silu", [=](cudaStream_t st) { launch_dwconv(x, N, H, W, C, stride, wt, scale, shift, act, o16, st); },
+                               2.0 * in->rows() * C * 9, ((double)xe->rows() + (double)in->rows()) * C * 2, "dw (unfused fallback)");
+                }
                 GemmEpilogue ep;
                 ep.scale = P.pool.ptr<float>(n->c_scale);
                 ep.shift = P.pool.ptr<float>(n->c_shift);

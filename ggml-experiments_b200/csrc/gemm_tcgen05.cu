@@ -147,13 +147,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float * v) {
 // UMMA shared-memory descriptor for a K-major tile in the canonical 128-byte-swizzle layout:
 // rows of 128 B, 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// row_bytes = 128 / 64 / 32 selects SWIZZLE_128B / 64B / 32B (layout type 2 / 4 / 6); the 8-row group stride follows.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address, 16-byte units
     d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)((8u * row_bytes) >> 4) << 32;   // stride byte offset: 8 rows x row_bytes
     d |= (uint64_t)1 << 46;                         // descriptor version = 1
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    d |= layout << 61;
     return d;
 }
 // Instruction descriptor (cute InstrDescriptor): c=f32, a=b=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     // swizzle-128B atoms need 1 KiB alignment; offset arithmetic (not a uintptr_t round trip) keeps the pointer in the
     // shared address space for the compiler (LDS/STS instead of generic LD/ST)
     uint8_t * smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int       a_bytes     = kBlockM * kBlockK * 2;
-    const int       b_bytes     = p.block_n * kBlockK * 2;
+    const int       a_bytes     = kBlockM * p.kb_elems * 2;
+    const int       b_bytes     = p.block_n * p.kb_elems * 2;
     const int       stage_bytes = a_bytes + b_bytes;
     uint64_t *      bars        = (uint64_t *)(smem + (size_t)p.stages * stage_bytes);
     uint64_t *      full_bar    = bars;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         if (p.ep.out32) tma_prefetch_desc(&map_o32);
         if (p.ep.res32) tma_prefetch_desc(&map_r32);
         for (int s = 0; s < p.stages; s++) {
-            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&full_bar[s]), p.a_cp_async ? 33 : 1);  // TMA thread (+ 32 cp.async lanes)
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         for (int a = 0; a < 2; a++) {
@@ -247,7 +249,38 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
 
     const int cblk_tot = p.cblk0 + p.cblk1;
 
-    if (warp == 0) {
+    if (warp == 0 && p.a_cp_async) {
+        // ===================== producer, small-K mode: A by cp.async (whole warp), B by TMA =====================
+        // With K = 16 / 32 a TMA box row is only 32 / 64 bytes and the TMA's per-row cost dominates (measured: 2.2 TB/s
+        // at K=16).  The A tile is a contiguous 128 x K block, so the warp copies it with 16-byte cp.async into the
+        // 32B / 64B-swizzled K-major layout the UMMA descriptor expects; completion is signalled on the same mbarrier.
+        const int      cpr   = p.kb_elems >> 3;              // 16-byte chunks per row (2 or 4)
+        const int      chunks = kBlockM * cpr;
+        const uint32_t row_bytes = (uint32_t)p.kb_elems * 2;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, it++) {
+            const int      m0 = tile * kBlockM;
+            const int      s  = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1u;
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            if (lane == 0) {
+                mbar_expect_tx(fb, (uint32_t)b_bytes);
+                tma_load_2d(sa + a_bytes, &map_b, 0, n0, fb);
+            }
+            for (int i = lane; i < chunks; i += 32) {
+                const int      row = i / cpr, ch = i - row * cpr;
+                const uint32_t sw  = cpr == 2 ? ((uint32_t)row >> 2) & 1u : ((uint32_t)row >> 1) & 3u;
+                const uint32_t dst = sa + (uint32_t)row * row_bytes + (((uint32_t)ch ^ sw) << 4);
+                const int      m   = m0 + row;
+                const __half * src = p.a_ptr + (size_t)(m < p.M ? m : 0) * p.lda + ch * 8;
+                const uint32_t nbytes = m < p.M ? 16u : 0u;  // rows past M are zero-filled
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fb) : "memory");
+        }
+    } else if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;  // k-block counter across all tiles of this CTA
@@ -268,8 +301,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     const uint32_t sb = sa + a_bytes;
                     mbar_expect_tx(fb, (uint32_t)stage_bytes);
                     if (!p.conv) {
-                        tma_load_2d(sa, &map_a0, kb * kBlockK, m0, fb);
-                        tma_load_2d(sb, &map_b, kb * kBlockK, n0, fb);
+                        tma_load_2d(sa, &map_a0, kb * p.kb_elems, m0, fb);
+                        tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
                     } else {
                         const int tap = kb / cblk_tot, r = kb % cblk_tot;
                         const int src = r >= p.cblk0;
@@ -296,20 +329,22 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     const int      s  = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1u;
                     mbar_wait(smem_u32(&full_bar[s]), ph);
+                    if (p.a_cp_async) fence_proxy_async();  // cp.async wrote through the generic proxy
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
                     int rem;
                     if (!p.conv) {
-                        rem = p.K - kb * kBlockK;
+                        rem = p.K - kb * p.kb_elems;
+                        if (rem > p.kb_elems) rem = p.kb_elems;
                     } else {
                         const int r   = kb % cblk_tot;
                         const int src = r >= p.cblk0;
                         rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
                     }
                     const int      ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
-                    const uint64_t adesc  = make_smem_desc(sa);
-                    const uint64_t bdesc  = make_smem_desc(sb);
+                    const uint64_t adesc  = make_smem_desc(sa, (uint32_t)p.kb_elems * 2);
+                    const uint64_t bdesc  = make_smem_desc(sb, (uint32_t)p.kb_elems * 2);
                     for (int k = 0; k < ksteps; k++) {
                         // advancing 16 f16 (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
                         umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
@@ -511,7 +546,7 @@ static void choose_tiling(GemmLaunch & L, int N) {
     // two accumulator stages in TMEM (tile i+1 accumulates while tile i drains); power-of-two column count >= 32
     const int need         = 2 * p.block_n;
     p.tmem_cols            = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-    const int stage_bytes  = kBlockM * kBlockK * 2 + p.block_n * kBlockK * 2;
+    const int stage_bytes  = kBlockM * p.kb_elems * 2 + p.block_n * p.kb_elems * 2;
     const int staging      = 2 * ((p.ep.out16 ? kBlockM * 128 : 0) + ((p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0));
     // TMEM (512 columns) and shared memory (~220 KiB usable) decide how many persistent CTAs share an SM
     int stages = 0;
@@ -522,6 +557,8 @@ static void choose_tiling(GemmLaunch & L, int N) {
     }
     if (stages > kMaxStage) stages = kMaxStage;
     if (stages < 1) stages = 1;
+    if (const char * e = getenv("GGML_B200_GEMM_STAGES")) stages = atoi(e);      // tuning probes
+    if (const char * e = getenv("GGML_B200_GEMM_CTAS")) L.ctas_per_sm = atoi(e);
     p.stages     = stages;
     L.smem_bytes = 1024 + (size_t)stages * stage_bytes + kCtrlBytes + staging;
 }
@@ -567,21 +604,32 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
     GemmLaunch::Params & p = L.p;
     p.M = M; p.N = N; p.K = K;
     p.conv   = 0;
-    p.num_kb = (K + kBlockK - 1) / kBlockK;
+    // TMA cost is per box row: with K = 16 / 32 the rows are 32 / 64 bytes (or mostly out-of-bounds fill in a 64-wide
+    // box) and the load runs at 2.2 TB/s (tests/gemm_probe.py).  Those shapes use one exact K block in the 32B / 64B
+    // swizzled layout, filled by cp.async from the producer warp.
+    // Larger K keeps 64-wide blocks (a partly out-of-bounds last box costs less than nine 32-byte-row boxes).
+    // (measured, N=128 K=32: 64-wide box with fill 345 us, exact 64B-swizzle box 367 us, cp.async 395 us -> keep TMA;
+    //            N=64  K=16: 310 us / 243 us / 212 us -> cp.async)
+    p.kb_elems   = K == 16 ? 16 : 64;
+    p.a_cp_async = K == 16 && getenv("GGML_B200_GEMM_NO_CPASYNC") == nullptr;
+    p.a_ptr      = A;
+    p.lda        = lda;
+    p.num_kb = (K + p.kb_elems - 1) / p.kb_elems;
     p.ep     = ep;
     choose_tiling(L, N);
+    const CUtensorMapSwizzle swz = p.kb_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kb_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
         const uint64_t str[1]  = {(uint64_t)lda * 2};
-        const uint32_t box[2]  = {(uint32_t)kBlockK, (uint32_t)kBlockM};
-        make_map(&L.map_a0, A, 2, dims, str, box);
+        const uint32_t box[2]  = {(uint32_t)p.kb_elems, (uint32_t)kBlockM};
+        tma_encode(&L.map_a0, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dims, str, box, swz);
         L.map_a1 = L.map_a0;
     }
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         const uint64_t str[1]  = {(uint64_t)ldb * 2};
-        const uint32_t box[2]  = {(uint32_t)kBlockK, (uint32_t)p.block_n};
-        make_map(&L.map_b, B, 2, dims, str, box);
+        const uint32_t box[2]  = {(uint32_t)p.kb_elems, (uint32_t)p.block_n};
+        tma_encode(&L.map_b, B, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dims, str, box, swz);
     }
     make_output_maps(L);
     choose_grid(L);
@@ -612,6 +660,7 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
     p.cblk0  = (C0 + kBlockK - 1) / kBlockK;
     p.cblk1  = C1 > 0 ? (C1 + kBlockK - 1) / kBlockK : 0;
     p.num_kb = 9 * (p.cblk0 + p.cblk1);
+    p.kb_elems = kBlockK;
     p.ep     = ep;
     choose_tiling(L, OC);
     auto act_map = [&](CUtensorMap * map, const __half * x, int C) {

@@ -33,6 +33,10 @@ struct GemmLaunch {
     struct Params {
         int M, N, K;
         int block_n, n_tiles, num_kb, stages, tmem_cols;
+        int kb_elems;               // K elements per smem stage: 64 (128B swizzle), 32 (64B swizzle) or 16 (32B swizzle)
+        int a_cp_async;             // 1: A tile loaded by the producer warp with cp.async (K = 16 / 32: TMA rows would be 32-64 B)
+        const __half * a_ptr;       // cp.async mode: A base pointer and leading dimension
+        int lda;
         int conv;                   // 0: plain GEMM, 1: 3x3 stride-1 pad-1 implicit GEMM over NHWC
         int H, W, rows_per_tile;    // conv: image rows covered by one 128-pixel tile (0 if a tile spans whole images)
         int cblk0, cblk1, C0, C1;   // conv: 64-channel blocks / channels of source 0 and source 1 (concat fusion)
@@ -77,5 +81,30 @@ struct DwLaunch {
 bool dw_prepare(DwLaunch & L, const __half * x, int N, int H, int W, int C, int stride, const __half * Wt, const float * scale,
                 const float * shift, int act, __half * out);
 void dw_launch(const DwLaunch & L, cudaStream_t st);
+
+// K4a: depthwise 3x3 (+BN+SiLU) fused with the following 1x1 reduce convolution (+BN, + f32 residual); see dwreduce.cu
+struct DwRedLaunch {
+    CUtensorMap map_x, map_w;
+    struct Params {
+        int N, H, W, E, OH, OW, stride, Cout, Cout_pad;
+        int TW, TH, tiles_x, tiles_y, cblocks, box_w, box_h, ntiles, tmem_cols;
+        const __half * dwW;       // [3][3][E]
+        const float *  dw_scale;  // [E]
+        const float *  dw_shift;
+        int            dw_act;
+        const float *  r_scale;   // [Cout]
+        const float *  r_shift;
+        int            r_act;
+        const float *  res32;     // [N*OH*OW, Cout] or null
+        __half *       out16;     // [N*OH*OW, Cout] or null
+        float *        out32;
+    } p;
+    size_t smem_bytes;
+    int    grid;
+};
+bool dwreduce_prepare(DwRedLaunch & L, const __half * x, int N, int H, int W, int E, int stride, const __half * dwW,
+                      const float * dw_scale, const float * dw_shift, int dw_act, const __half * Wr, int Cout, const float * r_scale,
+                      const float * r_shift, int r_act, const float * res32, __half * out16, float * out32);
+void dwreduce_launch(const DwRedLaunch & L, cudaStream_t st);
 
 }  // namespace b200

@@ -412,6 +412,12 @@ extern "C" float * mvit_slot_input(mvit_model * m, int n, int h, int w, int slot
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     return g ? (float *)ggml_get_data(g->input_hwc) : nullptr;
 }
+extern "C" int mvit_slot_set_transfers(mvit_model * m, int n, int h, int w, int slot, int upload_inputs, int download_outputs) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    if (!g) return 1;
+    ggml_b200_graph_set_transfers(g->gf, upload_inputs != 0, download_outputs != 0);
+    return 0;
+}
 extern "C" int mvit_slot_submit(mvit_model * m, int n, int h, int w, int slot) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     if (!g) return 1;

@@ -85,6 +85,7 @@ def lib_mobilevit() -> ctypes.CDLL:
         for name in ("mvit_slot_input", "mvit_slot_features", "mvit_slot_pooled"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
             getattr(L, name).restype = _f32p
+        L.mvit_slot_set_transfers.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6
         for name in ("mvit_slot_submit", "mvit_slot_wait"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.mvit_release.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -163,6 +164,9 @@ class MobileViT:
     def slot_submit(self, n, h, w, slot) -> None:
         if self._L.mvit_slot_submit(self._h, n, h, w, slot) != 0:
             raise ValueError("mvit_slot_submit: invalid arguments")
+
+    def slot_set_transfers(self, n, h, w, slot, upload: bool, download: bool) -> None:
+        self._L.mvit_slot_set_transfers(self._h, n, h, w, slot, int(upload), int(download))
 
     def slot_wait(self, n, h, w, slot):
         if self._L.mvit_slot_wait(self._h, n, h, w, slot) != 0:

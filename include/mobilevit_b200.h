@@ -52,6 +52,7 @@ const float * mvit_host_pooled(mvit_model * m, int n, int h, int w);    /* [N,C]
  * D2H; only the waiting is deferred. ---- */
 float *       mvit_slot_input(mvit_model * m, int n, int h, int w, int slot);
 int           mvit_slot_submit(mvit_model * m, int n, int h, int w, int slot);
+int           mvit_slot_set_transfers(mvit_model * m, int n, int h, int w, int slot, int upload_inputs, int download_outputs);
 int           mvit_slot_wait(mvit_model * m, int n, int h, int w, int slot);
 const float * mvit_slot_features(mvit_model * m, int n, int h, int w, int slot);
 const float * mvit_slot_pooled(mvit_model * m, int n, int h, int w, int slot);
