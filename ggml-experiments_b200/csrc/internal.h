@@ -116,6 +116,7 @@ struct Plan {
     int                   n_folded = 0;
     std::vector<Transfer> uploads, downloads;
     std::vector<void *>   pinned;        // host ranges registered with cudaHostRegister
+    void *                host_mirror = nullptr;  // pinned host copies of small intermediates (tiny graphs only, see plan.cpp)
     bool                  upload_inputs = true, download_outputs = true;
     cudaGraphExec_t       graph_exec = nullptr;
     bool                  graph_failed = false;

@@ -139,6 +139,7 @@ Plan::~Plan() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (void * p : owned_device) cudaFree(p);
     for (void * p : pinned) cudaHostUnregister(p);
+    if (host_mirror) cudaFreeHost(host_mirror);
 }
 
 static uint64_t graph_signature(const ggml_cgraph * gf) {
@@ -161,16 +162,6 @@ void destroy_plans_of(ggml_context * ctx) {
     auto range = g_plans.equal_range(ctx);
     for (auto it = range.first; it != range.second; ++it) delete it->second;
     g_plans.erase(range.first, range.second);
-}
-
-static void try_pin(Plan * plan, void * p, size_t bytes) {
-    // Pin the host range of an input leaf / output shadow so the per-compute copies are true async DMA.
-    if (bytes < (64u << 10)) return;
-    uintptr_t lo = (uintptr_t)p & ~uintptr_t(4095);
-    uintptr_t hi = ((uintptr_t)p + bytes + 4095) & ~uintptr_t(4095);
-    cudaError_t e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault);
-    if (e == cudaSuccess) plan->pinned.push_back((void *)lo);
-    else (void)cudaGetLastError();  // already pinned / overlapping: harmless, copy still works
 }
 
 // Assign device memory to leafs; shared by both plan builders.
@@ -215,7 +206,6 @@ static void place_leafs(Plan * plan, ggml_cgraph * gf) {
             ioff += b;
             if (!t->data) B200_ABORT("input leaf '%s' has no host data", t->name);
             plan->uploads.push_back({t, s.dptr, (size_t)raw});
-            try_pin(plan, t->data, (size_t)raw);
         } else {
             s.kind = SLOT_CONST;
             s.dptr = cpool + coff;
@@ -278,7 +268,35 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
         size_t bytes = (size_t)ggml_nelements(t) * ggml_type_size(t->type);
         if (!t->data) t->data = arena_alloc(t->ctx, bytes, 4096);
         plan->downloads.push_back({t, it->second.dptr, bytes});
-        try_pin(plan, t->data, bytes);
+    }
+    // Tiny graphs (rnn_text_generation.cpp: ~60 nodes) keep upstream's "every tensor has host data after compute"
+    // semantics: the program reads an intermediate (`output.states->data`, rnn.cpp:307) that was never declared an
+    // output.  Every intermediate of at most 64 KiB gets a host mirror owned by the plan; big graphs never pay for this.
+    if (plan->mode != GGML_B200_MODE_FAST && gf->n_nodes <= 256) {
+        size_t total = 0;
+        for (int i = 0; i < gf->n_nodes; i++) {
+            ggml_tensor * t = gf->nodes[i];
+            if (is_view_op(t->op) || t->data || !plan->slots.count(t)) continue;
+            const size_t bytes = (size_t)ggml_nelements(t) * ggml_type_size(t->type);
+            if (bytes <= (64u << 10)) total += (bytes + 255) & ~size_t(255);
+        }
+        if (total) {
+            B200_CHECK(cudaMallocHost(&plan->host_mirror, total));
+            size_t off = 0;
+            for (int i = 0; i < gf->n_nodes; i++) {
+                ggml_tensor * t = gf->nodes[i];
+                if (is_view_op(t->op) || t->data || !plan->slots.count(t)) continue;
+                const size_t bytes = (size_t)ggml_nelements(t) * ggml_type_size(t->type);
+                if (bytes > (64u << 10)) continue;
+                t->data = (char *)plan->host_mirror + off;
+                off += (bytes + 255) & ~size_t(255);
+                plan->downloads.push_back({t, plan->slots[t].dptr, bytes});
+            }
+        }
+        for (int i = 0; i < gf->n_nodes; i++) {  // views of mirrored tensors read through their base
+            ggml_tensor * t = gf->nodes[i];
+            if (is_view_op(t->op) && !t->data && t->view_src && t->view_src->data) t->data = (char *)t->view_src->data + t->view_offs;
+        }
     }
     gf->plan = plan;
     {
@@ -365,6 +383,20 @@ extern "C" void ggml_b200_graph_wait(struct ggml_cgraph * gf) {
     if (!gf->plan) return;
     Plan * p = (Plan *)gf->plan;
     B200_CHECK(cudaStreamSynchronize(p->private_stream ? p->private_stream : current_stream()));
+}
+
+// Pinned host memory for a caller-provided arena (ggml_init_params.mem_buffer): with the input leaf and the output shadows
+// in page-locked memory the per-compute copies are true asynchronous DMA.  (Registering ranges of a malloc'ed arena after
+// the fact is not safe: two tensors sharing a page end up half pinned and cudaMemcpyAsync rejects them.)
+extern "C" void * ggml_b200_host_malloc(size_t bytes) {
+    void * p = nullptr;
+    int    n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0 && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p;
+    (void)cudaGetLastError();
+    return nullptr;  // no device / no pinned memory: the caller falls back to an ordinary arena
+}
+extern "C" void ggml_b200_host_free(void * p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" void ggml_b200_set_mode(enum ggml_b200_mode mode) { runtime().mode = (int)mode; }

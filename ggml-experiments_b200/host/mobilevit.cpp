@@ -141,6 +141,7 @@ model::~model() {
     for (auto & kv : graphs) {
         ggml_graph_release_plan(kv.second.gf);
         ggml_free(kv.second.ctx);
+        ggml_b200_host_free(kv.second.pinned_arena);
     }
     if (ctx_w) ggml_free(ctx_w);
 }
@@ -295,7 +296,9 @@ forward_graph & model::graph_for(int n, int h, int w, int slot) {
     if (debug_stages) out_bytes += (size_t)n * h * w * 16 * sizeof(float);  // all stage taps together are < 16 floats per input pixel
     // the compute arena only holds tensor records, the input staging area and the output shadows:
     // intermediates live in the device plan's arena (the reference needs 1 GiB per image, main.cpp:605)
-    ggml_init_params params = {in_bytes + out_bytes + (size_t)(24u << 20), nullptr, false};
+    const size_t arena_bytes = in_bytes + out_bytes + (size_t)(24u << 20);
+    g.pinned_arena          = ggml_b200_host_malloc(arena_bytes);  // NULL without a GPU: ggml_init then mallocs
+    ggml_init_params params = {arena_bytes, g.pinned_arena, false};
     g.ctx                   = ggml_init(params);
     GGML_ASSERT(g.ctx != nullptr);
     g.gf        = ggml_new_graph(g.ctx);
@@ -317,6 +320,7 @@ void model::release(int n, int h, int w) {
         if (std::get<0>(it->first) == n && std::get<1>(it->first) == h && std::get<2>(it->first) == w) {
             ggml_graph_release_plan(it->second.gf);
             ggml_free(it->second.ctx);
+            ggml_b200_host_free(it->second.pinned_arena);
             it = graphs.erase(it);
         } else {
             ++it;

@@ -62,6 +62,7 @@ struct forward_graph {
     ggml_tensor *  input_hwc = nullptr;  // ne = (3, W, H, N): the caller's HWC images, uploaded as they are
     ggml_tensor *  features  = nullptr;  // ne = (W/32, H/32, C, N)
     ggml_tensor *  pooled    = nullptr;  // ne = (1, 1, C, N)
+    void *         pinned_arena = nullptr;  // page-locked backing store of ctx (input staging + output shadows)
     std::vector<ggml_tensor *> stages;   // stem, layer_1..layer_5, conv_1x1_exp outputs (debug taps, MVIT_DEBUG_STAGES=1)
 };
 

@@ -232,6 +232,10 @@ void   ggml_b200_tensor_set_device_data(struct ggml_tensor * leaf, void * device
 void * ggml_b200_tensor_get_device_data(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor);
 void   ggml_b200_graph_set_transfers(struct ggml_cgraph * cgraph, bool upload_inputs, bool download_outputs);
 
+/* Page-locked host memory to be passed as ggml_init_params.mem_buffer (returns NULL without a device). */
+void * ggml_b200_host_malloc(size_t bytes);
+void   ggml_b200_host_free(void * p);
+
 /* Pipelined submission (throughput serving): give a graph a private stream, submit without waiting, wait later.
  * With two copies of a forward graph (own input leaf and output shadows each) the H2D copy of batch i+1 and the D2H
  * copy of batch i-1 overlap the kernels of batch i.  ggml_graph_compute_with_ctx itself stays synchronous. */

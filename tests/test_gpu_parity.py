@@ -196,3 +196,37 @@ def test_unmodified_reference_main_runs_on_libggml_b200(G, oracle, weight_files,
     ref = np.concatenate([ref_f[0, :5, 0, 0], ref_f[0, -5:, 0, 0]])
     print("reference main.cpp printed:", vals, "oracle:", ref.tolist(), r.stderr[-300:])
     assert np.abs(np.array(vals) - ref).max() < 3e-2
+
+
+def test_unmodified_reference_rnn_runs_on_libggml_b200(G, tmp_path):
+    """the reference's GRU text generator (rnn_text_generation.cpp, compiled untouched, linked with
+    libggml_b200.so) runs its 200-step greedy loop on the GPU (EXACT plan); the generated token sequence must equal the
+    numpy restatement of gru_forward wherever the greedy decision is not a numerical coin flip."""
+    import os
+    import subprocess
+    from oracle import gru_oracle as GO
+    exe = os.path.join(os.path.dirname(G.native_paths()["ggml"]), "ref_rnn_b200")
+    if not os.path.exists(exe):
+        pytest.skip("ref_rnn_b200 not built (needs /root/reference at build time)")
+    w = GO.make_synthetic_gru(seed=5)
+    os.makedirs(tmp_path / "rnn_text_gen")
+    GO.write_gru_bin(str(tmp_path / "rnn_text_gen" / "gru.bin"), w)  # rnn.cpp:117 opens this relative path
+    prompt = "ROMEO: what light"
+    r = subprocess.run([exe], cwd=tmp_path, input=prompt + "\n", capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-800:], r.stderr[-800:])
+    # print_text (rnn.cpp:92-96) prints the growing sequence followed by a separator line; take the last sequence
+    blocks = r.stdout.split("\n--------\n")
+    assert len(blocks) > 100, r.stdout[-500:]
+    last = blocks[-2] if blocks[-1].strip() == "" else blocks[-1]
+    ids, margins = GO.generate(w, prompt, steps=200)
+    ref_text = "".join(GO.VOCAB[i] for i in ids)
+    got = last[-len(ref_text):]
+    # compare up to the first step whose greedy margin is within f32 noise
+    n_cmp = len(ref_text)
+    for i, mg in enumerate(margins[:len(ref_text)]):
+        if mg < 1e-3:
+            n_cmp = min(n_cmp, i)
+            break
+    assert n_cmp > len(prompt) + 20, margins[:40]
+    assert got[:n_cmp] == ref_text[:n_cmp], (got[:80], ref_text[:80])
+    print("GRU: %d of %d generated tokens compared equal; min margin %.3g" % (n_cmp, len(ref_text), min(margins)))
