@@ -337,7 +337,9 @@ struct mvit_model {
     mvit::model m;
 };
 
-static bool shape_ok(int n, int h, int w) { return n > 0 && h > 0 && w > 0 && h % 32 == 0 && w % 32 == 0; }
+// H and W must be multiples of 64: the network downsamples by 32 and the last ViT block unfolds 2x2 patches
+// (the reference asserts this at main.cpp:729-730 for its fixed 256x256 input)
+static bool shape_ok(int n, int h, int w) { return n > 0 && h > 0 && w > 0 && h % 64 == 0 && w % 64 == 0; }
 
 extern "C" mvit_model * mvit_load(const char * path) {
     mvit_model * h = new mvit_model();

@@ -9,7 +9,7 @@
  *   mvit_free              <- ggml_free(model.ctx_w)                               (main.cpp:699)
  *
  * extract_features is generalised from the reference's hard-coded (256,256,3,1) input (main.cpp:612) to a
- * batch of N images of H x W (multiples of 32).  The graph is still built from ggml_* calls
+ * batch of N images of H x W (multiples of 64).  The graph is still built from ggml_* calls
  * (include/ggml/ggml.h) and runs through ggml_graph_compute_with_ctx on the GPU; there is no CPU path.
  */
 #ifndef MOBILEVIT_B200_H
@@ -36,7 +36,7 @@ int     mvit_out_channels(const mvit_model * m);  /* 640 / 384 / 320 for S / XS 
  * features  : N*C*(H/32)*(W/32) floats, per image the ggml tensor ne=(W/32,H/32,C,1) the reference returns
  *             (main.cpp:645), i.e. [N][C][H/32][W/32]; may be NULL.
  * pooled    : N*C floats, mean of the feature map over space (the build's "logits"); may be NULL.
- * Returns 0 on success, non-zero for invalid arguments (n <= 0, H or W not a multiple of 32). */
+ * Returns 0 on success, non-zero for invalid arguments (n <= 0, H or W not a multiple of 64). */
 int mvit_extract_features(mvit_model * m, const float * images_hwc, int n, int h, int w, float * features, float * pooled);
 
 /* ---- zero-copy host variant: the reference's own flow (write inp->data, compute, read output->data;

@@ -62,7 +62,7 @@ def test_extract_features_rejects_bad_shapes(weight_files):
     import ggml_experiments_b200 as G
     m = G.MobileViT(weight_files["xxs"])
     with pytest.raises(ValueError):
-        m.extract_features(np.zeros((1, 100, 100, 3), np.float32))  # not a multiple of 32
+        m.extract_features(np.zeros((1, 96, 96, 3), np.float32))  # not a multiple of 64
 
 
 def test_compute_without_gpu_fails_loudly(weight_files):

@@ -230,3 +230,18 @@ def test_unmodified_reference_rnn_runs_on_libggml_b200(G, tmp_path):
     assert n_cmp > len(prompt) + 20, margins[:40]
     assert got[:n_cmp] == ref_text[:n_cmp], (got[:80], ref_text[:80])
     print("GRU: %d of %d generated tokens compared equal; min margin %.3g" % (n_cmp, len(ref_text), min(margins)))
+
+
+def test_non_square_and_odd_batch_fast_equals_exact(G, weight_files):
+    """The reference is square-only (main.cpp:754); the batched builder is not.  For a non-square input and an odd batch the
+    fused plan (tokens kept in NHWC pixel order, unfold/fold elided) must agree with the per-node EXACT plan, which executes
+    the generalised unfold/fold permutations literally."""
+    from ggml_experiments_b200 import mobilevit as MV
+    imgs = W.synthetic_images(3, 128, 256, seed=3)  # widths must tile 128 for the fused 3x3 conv (else the EXACT plan runs)
+    fe, pe, ie = _run_model(G, weight_files["xxs"], imgs, MV.EXACT)
+    ff, pf, i_f = _run_model(G, weight_files["xxs"], imgs, MV.FAST)
+    assert ie["mode"] == MV.EXACT and i_f["mode"] == MV.FAST
+    r = parity_report(ff, fe, rtol=1e-2, atol_rms=1e-2)
+    print(r)
+    assert r["violations"] <= r["n"] * 1e-3 and r["rel_l2"] < 5e-3, r
+    assert (pf.argmax(1) == pe.argmax(1)).all()
