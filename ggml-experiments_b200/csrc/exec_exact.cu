@@ -198,6 +198,26 @@ __global__ void k_soft_max(V4 a, float * __restrict__ dst, int64_t rows) {
     for (int i = lane; i < n; i += 32) dst[row * n + i] *= inv;
 }
 
+// ggml_argmax: one warp per row; ties resolve to the lowest index (std::max_element, rnn.cpp:76)
+__global__ void k_argmax(V4 a, int32_t * __restrict__ dst, int64_t rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const char * src = a.p + row * a.nb[1];
+    float best = -INFINITY;
+    int   bi   = 0x7fffffff;
+    for (int i = lane; i < (int)a.ne[0]; i += 32) {
+        const float v = *(const float *)(src + (int64_t)i * a.nb[0]);
+        if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int   oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) dst[row] = bi;
+}
+
 // ---- generic 64x64 tiled "GEMM with functor loaders" on CUDA cores ----------------------------------------
 // C(m, n, batch) = sum_k A(m, k, batch) * B(k, n, batch), f32 accumulate, k ascending.
 struct MulMatArgs {
@@ -565,6 +585,12 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                 V4 a = src_view(0), b = src_view(1);
                 int g = grid_for(ne);
                 add_launch(plan, "exact_get_rows", [=](cudaStream_t st) { k_get_rows<<<g, 256, 0, st>>>(a, b, (float *)d, ne); });
+            } break;
+            case GGML_OP_ARGMAX: {
+                V4 a = src_view(0);
+                const int64_t rows = t->ne[0];
+                int g = (int)((rows + 7) / 8);
+                add_launch(plan, "exact_argmax", [=](cudaStream_t st) { k_argmax<<<g, 256, 0, st>>>(a, (int32_t *)d, rows); });
             } break;
             case GGML_OP_POOL_MEAN_HW: {
                 V4 a = src_view(0);

@@ -420,6 +420,24 @@ extern "C" struct ggml_tensor * ggml_transpose(struct ggml_context * ctx, struct
     return new_view(ctx, a, GGML_OP_TRANSPOSE, ne, nb);
 }
 
+extern "C" struct ggml_tensor * ggml_view_2d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1, size_t nb1,
+                                             size_t offset) {
+    const int64_t ne[4] = {ne0, ne1, 1, 1};
+    const size_t  nb[4] = {a->nb[0], nb1, nb1 * (size_t)ne1, nb1 * (size_t)ne1};
+    ggml_tensor * base  = a->view_src ? a->view_src : a;
+    ggml_tensor * r     = new_tensor_impl(ctx, a->type, 2, ne, base, a->view_offs + offset, false);
+    for (int i = 0; i < 4; i++) r->nb[i] = nb[i];
+    r->op     = GGML_OP_VIEW;
+    r->src[0] = a;
+    return r;
+}
+
+extern "C" struct ggml_tensor * ggml_argmax(struct ggml_context * ctx, struct ggml_tensor * a) {
+    GGML_ASSERT(a->type == GGML_TYPE_F32 && a->ne[2] == 1 && a->ne[3] == 1);
+    const int64_t ne[4] = {a->ne[1], 1, 1, 1};
+    return new_result(ctx, GGML_TYPE_I32, ne, GGML_OP_ARGMAX, a, nullptr);
+}
+
 static int64_t conv_out(int64_t in, int64_t k, int s, int p, int d) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
 
 static ggml_tensor * conv_impl(ggml_context * ctx, enum ggml_op op, ggml_tensor * a, ggml_tensor * b, int s0, int s1,

@@ -133,6 +133,7 @@ void * device_ptr_of(Plan * plan, const ggml_tensor * t) {
 static std::mutex                               g_plans_mu;
 static std::multimap<ggml_context *, Plan *>    g_plans;
 static std::unordered_map<const ggml_tensor *, void *> g_external;  // leaf -> caller-owned device memory
+static std::unordered_map<const ggml_cgraph *, std::vector<std::pair<ggml_tensor *, ggml_tensor *>>> g_feedback;
 
 Plan::~Plan() {
     if (private_stream) { cudaStreamSynchronize(private_stream); cudaStreamDestroy(private_stream); }
@@ -269,6 +270,20 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
         if (!t->data) t->data = arena_alloc(t->ctx, bytes, 4096);
         plan->downloads.push_back({t, it->second.dptr, bytes});
     }
+    // device-side feedback copies (autoregressive loops): node -> input leaf, after the last kernel of each compute
+    {
+        auto fb = g_feedback.find(gf);
+        if (fb != g_feedback.end())
+            for (auto & pr : fb->second) {
+                void *       src   = device_ptr_of(plan, pr.first);
+                void *       dst   = device_ptr_of(plan, pr.second);
+                const size_t bytes = (size_t)ggml_nelements(pr.second) * ggml_type_size(pr.second->type);
+                if (!ggml_is_contiguous(pr.first) || (size_t)ggml_nelements(pr.first) * ggml_type_size(pr.first->type) != bytes)
+                    B200_ABORT("ggml_b200_graph_add_feedback: '%s' -> '%s' must be contiguous and of equal size", pr.first->name, pr.second->name);
+                add_launch(plan, "feedback_copy", [=](cudaStream_t st) { B200_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st)); },
+                           0.0, 2.0 * bytes, pr.second->name);
+            }
+    }
     // Tiny graphs (rnn_text_generation.cpp: ~60 nodes) keep upstream's "every tensor has host data after compute"
     // semantics: the program reads an intermediate (`output.states->data`, rnn.cpp:307) that was never declared an
     // output.  Every intermediate of at most 64 KiB gets a host mirror owned by the plan; big graphs never pay for this.
@@ -397,6 +412,22 @@ extern "C" void * ggml_b200_host_malloc(size_t bytes) {
 }
 extern "C" void ggml_b200_host_free(void * p) {
     if (p) cudaFreeHost(p);
+}
+
+extern "C" int ggml_b200_tensor_download(struct ggml_cgraph * gf, struct ggml_tensor * t, void * host_dst) {
+    if (!gf->plan) return 1;
+    Plan * p = (Plan *)gf->plan;
+    auto it  = p->slots.find(t);
+    if (it == p->slots.end() || !it->second.dptr || !ggml_is_contiguous(t)) return 1;
+    cudaStream_t st = p->private_stream ? p->private_stream : current_stream();
+    B200_CHECK(cudaStreamSynchronize(st));
+    B200_CHECK(cudaMemcpy(host_dst, it->second.dptr, (size_t)ggml_nelements(t) * ggml_type_size(t->type), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" void ggml_b200_graph_add_feedback(struct ggml_cgraph * gf, struct ggml_tensor * src, struct ggml_tensor * dst) {
+    GGML_ASSERT(dst->op == GGML_OP_NONE);
+    g_feedback[gf].push_back({src, dst});
 }
 
 extern "C" void ggml_b200_set_mode(enum ggml_b200_mode mode) { runtime().mode = (int)mode; }

@@ -63,6 +63,7 @@ enum ggml_op {
     GGML_OP_RESHAPE, GGML_OP_VIEW, GGML_OP_PERMUTE, GGML_OP_TRANSPOSE,
     GGML_OP_CONV_2D, GGML_OP_CONV_DEPTHWISE_2D,
     GGML_OP_POOL_MEAN_HW,   /* build addition: global average pool */
+    GGML_OP_ARGMAX,         /* upstream ggml_argmax: index of the row maximum, I32 (batched greedy decoding, rnn.cpp:74-77,312) */
     GGML_OP_COUNT
 };
 
@@ -180,6 +181,11 @@ struct ggml_tensor * ggml_reshape_3d(struct ggml_context * ctx, struct ggml_tens
 struct ggml_tensor * ggml_reshape_4d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3);
 struct ggml_tensor * ggml_permute(struct ggml_context * ctx, struct ggml_tensor * a, int axis0, int axis1, int axis2, int axis3); /* result.ne[axis_i] = a.ne[i] */
 struct ggml_tensor * ggml_transpose(struct ggml_context * ctx, struct ggml_tensor * a);
+/* upstream ggml_view_2d: ne0 x ne1 window into a, row stride nb1 bytes, starting `offset` bytes into a (the batched GRU
+ * program slices the z / r / h gate blocks with it instead of rnn.cpp's get_rows-on-a-fake-transpose trick, :41-49,212) */
+struct ggml_tensor * ggml_view_2d(struct ggml_context * ctx, struct ggml_tensor * a, int64_t ne0, int64_t ne1, size_t nb1, size_t offset);
+/* upstream ggml_argmax: a [n, rows] F32 -> I32 [rows] (device-side replacement of rnn.cpp:74-77 argmax_1d) */
+struct ggml_tensor * ggml_argmax(struct ggml_context * ctx, struct ggml_tensor * a);
 
 /* ---- convolution (main.cpp:788,798) ----
  * kernel a: [KW, KH, IC, OC] F16 (depthwise: [KW, KH, 1, C]); input b: [W, H, C, N] F32; result F32
@@ -242,6 +248,15 @@ void   ggml_b200_host_free(void * p);
 void ggml_b200_graph_use_private_stream(struct ggml_cgraph * cgraph);
 void ggml_b200_graph_compute_async(struct ggml_context * ctx, struct ggml_cgraph * cgraph);
 void ggml_b200_graph_wait(struct ggml_cgraph * cgraph);
+
+/* Device-side feedback for autoregressive loops: after every compute of `cgraph`, copy node `src` into
+ * the device buffer of leaf `dst` (same byte size).  Replaces rnn.cpp:303-310 (host writes the next token id and memcpy's
+ * the new state back into the input leaf).  Register before the first compute. */
+void ggml_b200_graph_add_feedback(struct ggml_cgraph * cgraph, struct ggml_tensor * src, struct ggml_tensor * dst);
+
+/* Synchronous device->host copy of any (contiguous) tensor of the graph's plan, e.g. an intermediate that is not a
+ * declared output.  Returns 0 on success. */
+int ggml_b200_tensor_download(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor, void * host_dst);
 
 /* Introspection of the compiled plan (bench.py's gpu_launches, DESIGN.md's memory-planner numbers). */
 struct ggml_b200_plan_stats {

@@ -74,3 +74,27 @@ def generate(w, prompt: str, steps: int = 200):
         srt = np.sort(logits)
         margins.append(float(srt[-1] - srt[-2]))
     return ids, margins
+
+
+def generate_batch(w, first_tokens, steps):
+    """B independent streams (BASELINE.json config 5): stream b starts from first_tokens[b] with a zero state and feeds
+    back its own greedy argmax.  Returns tokens [steps, B], margins [steps, B] (top-1 minus top-2 logit) and final state."""
+    ids = np.asarray(first_tokens, dtype=np.int64)
+    B, u = ids.shape[0], w["U"].shape[0]
+    h = np.zeros((B, u), np.float32)
+    toks = np.empty((steps, B), np.int32)
+    margins = np.empty((steps, B), np.float32)
+    for t in range(steps):
+        x = w["emb"][ids]
+        mx = x @ w["W"] + w["b"][0]
+        mh = h @ w["U"] + w["b"][1]
+        z = _sigmoid_like_reference(mx[:, :u] + mh[:, :u])
+        r = _sigmoid_like_reference(mx[:, u:2 * u] + mh[:, u:2 * u])
+        hh = np.tanh(mx[:, 2 * u:] + r * mh[:, 2 * u:])
+        h = (z * h + (np.float32(1) - z) * hh).astype(np.float32)
+        logits = (h @ w["D"] + w["c"]).astype(np.float32)
+        ids = logits.argmax(1)
+        srt = np.sort(logits, axis=1)
+        toks[t] = ids
+        margins[t] = srt[:, -1] - srt[:, -2]
+    return toks, margins, h
