@@ -9,7 +9,9 @@
 //   * ggml_norm / ggml_soft_max accumulate their sums in double, like ggml's ggml_float.
 // Kernels here are deliberately simple (CUDA cores, 64x64 smem tiles); the fast path lives in fuse.cpp.
 #include <cstring>
+#include <memory>
 
+#include "gemm_tcgen05.h"
 #include "internal.h"
 
 namespace b200 {
@@ -196,6 +198,18 @@ __global__ void k_soft_max(V4 a, float * __restrict__ dst, int64_t rows) {
     }
     const float inv = (float)(1.0 / warp_sum_d(s));
     for (int i = lane; i < n; i += 32) dst[row * n + i] *= inv;
+}
+
+// f32 -> f16 (contiguous), operand preparation for tensor-core lowered mul_mat
+__global__ void k_cast_f16(const float4 * __restrict__ src, uint2 * __restrict__ dst, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t *>(&a);
+        o.y = *reinterpret_cast<uint32_t *>(&b);
+        dst[i] = o;
+    }
 }
 
 // ggml_argmax: one warp per row; ties resolve to the lowest index (std::max_element, rnn.cpp:76)
@@ -413,6 +427,19 @@ static int grid_for(int64_t n, int threads = 256) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// mul_mat of a constant 2-d f32 weight leaf with a contiguous 2-d f32 activation, when the caller asked for FAST mode
+static bool tensor_core_mul_mat(Plan * plan, const ggml_tensor * t) {
+    if (t->op != GGML_OP_MUL_MAT || runtime().mode != GGML_B200_MODE_FAST || getenv("GGML_B200_NO_TC_MULMAT")) return false;
+    const ggml_tensor * w = t->src[0];
+    const ggml_tensor * x = t->src[1];
+    if (w->op != GGML_OP_NONE || w->view_src || w->type != GGML_TYPE_F32 || !ggml_is_contiguous(w) || w->ne[2] != 1 || w->ne[3] != 1) return false;
+    auto it = plan->slots.find(w);
+    if (it == plan->slots.end() || it->second.kind != SLOT_CONST) return false;
+    if (x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x) || x->ne[2] != 1 || x->ne[3] != 1) return false;
+    const int64_t K = w->ne[0], M = w->ne[1], N = x->ne[1];
+    return K % 8 == 0 && M % 8 == 0 && N >= 64 && (K * N) % 4 == 0;
+}
+
 void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
     const int n = gf->n_nodes;
     // ---- liveness: last node index that reads each buffer-owning tensor (through any chain of views) ----
@@ -430,6 +457,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
         if (gf->nodes[i]->flags & GGML_TENSOR_FLAG_OUTPUT) last_use[base_of(gf->nodes[i])] = n;  // outputs live forever
     // ---- assign arena offsets in execution order ----
     ArenaPlanner ap;
+    std::unordered_map<const ggml_tensor *, int64_t> scratch_off;
     std::vector<std::vector<const ggml_tensor *>> dies_at(n + 1);
     for (int i = 0; i < n; i++) {
         ggml_tensor * t = gf->nodes[i];
@@ -444,6 +472,12 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
             s.last_use  = lu;
             plan->slots[t] = s;
             if (lu < n) dies_at[lu < i ? i : lu].push_back(t);  // a never-read result is freed right after its node
+            if (tensor_core_mul_mat(plan, t)) {  // scratch for the f16 copy of the activation operand, live for this node only
+                const int64_t sb = (int64_t)ggml_nelements(t->src[1]) * 2;
+                const int64_t so = ap.alloc(sb);
+                scratch_off[t] = so;
+                ap.release(so, sb);
+            }
         }
         // buffers whose last reader is node i are released only after node i's own output was placed,
         // so an op never writes over one of its inputs
@@ -516,6 +550,35 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                 });
             } break;
             case GGML_OP_MUL_MAT: {
+                if (scratch_off.count(t)) {
+                    // FAST-mode lowering of a dense layer in a graph the fused planner does not know (e.g. the GRU cell):
+                    // ggml [K,M] weights x [K,N] activations -> [M,N] is exactly the K-major A/B layout of the tcgen05 GEMM
+                    // (C[N rows, M] = act[N,K] * W[M,K]^T); operands go to f16, accumulation stays f32.
+                    const ggml_tensor * wt = t->src[0];
+                    const ggml_tensor * xt = t->src[1];
+                    const int K = (int)wt->ne[0], M = (int)wt->ne[1], N = (int)xt->ne[1];
+                    std::vector<uint16_t> w16((size_t)K * M);
+                    ggml_fp32_to_fp16_row((const float *)wt->data, w16.data(), K * M);
+                    void * dw = nullptr;
+                    B200_CHECK(cudaMalloc(&dw, w16.size() * 2));
+                    plan->owned_device.push_back(dw);
+                    B200_CHECK(cudaMemcpy(dw, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+                    plan->weight_bytes += (int64_t)w16.size() * 2;
+                    __half *      x16 = (__half *)(plan->arena + scratch_off[t]);
+                    const float * x32 = (const float *)device_ptr_of(plan, xt);
+                    const int64_t n4  = (int64_t)K * N / 4;
+                    const int     cg  = grid_for(n4);
+                    add_launch(plan, "cast_f32_to_f16", [=](cudaStream_t st) { k_cast_f16<<<cg, 256, 0, st>>>((const float4 *)x32, (uint2 *)x16, n4); }, 0.0,
+                               6.0 * K * N, t->name);
+                    GemmEpilogue ep;
+                    ep.out32 = (float *)d;
+                    ep.ld32  = M;
+                    auto L = std::make_shared<GemmLaunch>();
+                    if (!gemm_prepare(*L, x16, K, (const __half *)dw, K, N, M, K, ep)) B200_ABORT("tensor-core mul_mat lowering failed for %dx%dx%d", N, M, K);
+                    add_launch(plan, "gemm_tcgen05_mul_mat", [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * N * M * K,
+                               2.0 * ((double)N * K + (double)M * K) + 4.0 * N * M, t->name);
+                    break;
+                }
                 MulMatArgs g;
                 g.a = src_view(0);
                 g.b = src_view(1);

@@ -11,6 +11,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 w = GO.make_synthetic_gru(seed=5)
 path = os.path.join(tempfile.mkdtemp(), "gru.bin")
 GO.write_gru_bin(path, w)
+from ggml_experiments_b200 import mobilevit as MV
+MV.set_mode(MV.EXACT if os.environ.get("GRU_MODE", "fast") == "exact" else MV.FAST)
 m = GRU(path)
 first = (np.arange(B) * 7 % 66).astype(np.int32)
 m.generate(first, 3)  # warm-up (plan build)

@@ -252,15 +252,18 @@ def test_batched_gru_matches_numpy_oracle(G, tmp_path):
     (argmax + state feedback).  Every greedy token must equal the numpy restatement up to the first decision whose logit
     margin is within f32 accumulation noise; the final state of never-diverged streams must match to 1e-4."""
     from ggml_experiments_b200.gru import GRU
+    from ggml_experiments_b200 import mobilevit as MV
     from oracle import gru_oracle as GO
     w = GO.make_synthetic_gru(seed=5)
     path = str(tmp_path / "gru.bin")
     GO.write_gru_bin(path, w)
     B, steps = 48, 40
     first = (np.arange(B) * 7 % 66).astype(np.int32)
+    MV.set_mode(MV.EXACT)  # f32 matmuls, like the reference's F32 x F32 ggml_mul_mat
     m = GRU(path)
     toks, state, ms = m.generate(first, steps)
     m.close()
+    MV.set_mode(MV.FAST)
     ref, margins, ref_state = GO.generate_batch(w, first, steps)
     n_equal, n_compared, clean = 0, 0, []
     for b in range(B):
@@ -274,3 +277,29 @@ def test_batched_gru_matches_numpy_oracle(G, tmp_path):
     assert n_compared > 0.8 * B * steps and n_equal == n_compared
     assert len(clean) > B // 2
     assert np.abs(state[clean] - ref_state[clean]).max() < 1e-4
+
+
+def test_batched_gru_fast_mode_tensor_cores(G, tmp_path):
+    """FAST mode lowers the three dense layers of the cell to the tcgen05 GEMM (f16 operands, f32 accumulate).  One step from
+    identical inputs must match the f32 oracle to f16-operand accuracy, and greedy tokens agree wherever the margin is clear."""
+    from ggml_experiments_b200.gru import GRU
+    from ggml_experiments_b200 import mobilevit as MV
+    from oracle import gru_oracle as GO
+    w = GO.make_synthetic_gru(seed=5)
+    path = str(tmp_path / "gru.bin")
+    GO.write_gru_bin(path, w)
+    B, steps = 128, 12
+    first = (np.arange(B) * 5 % 66).astype(np.int32)
+    MV.set_mode(MV.FAST)
+    m = GRU(path)
+    toks, state, ms = m.generate(first, steps)
+    m.close()
+    ref, margins, ref_state = GO.generate_batch(w, first, steps)
+    # step 0 starts from identical inputs: compare tokens where the f32 margin is clear of f16-operand noise
+    clear0 = margins[0] > 2e-2
+    assert clear0.sum() > B // 2 and (toks[0][clear0] == ref[0][clear0]).all()
+    same = (toks == ref).all(axis=0)
+    print(f"GRU fast: {same.sum()}/{B} streams identical to the f32 oracle over {steps} steps")
+    assert same.sum() > B // 2
+    err = np.abs(state[same] - ref_state[same]).max()
+    assert err < 2e-2, err
