@@ -212,6 +212,24 @@ __global__ void k_cast_f16(const float4 * __restrict__ src, uint2 * __restrict__
     }
 }
 
+// Fused GRU gates (rnn.cpp:231-250, Keras reset_after=True): from mx = W^T x + b0 and mh = U^T h + b1 (both [3U, B], gate
+// order z | r | h) and the previous state h [U, B]:  z = s(mx_z + mh_z), r = s(mx_r + mh_r), hh = tanh(mx_h + r * mh_h),
+// h' = z * h + (1 - z) * hh, with s(x) = silu(x) / x exactly as the reference writes its sigmoid (rnn.cpp:51-55).
+__global__ void k_gru_gates(const float * __restrict__ mx, const float * __restrict__ mh, const float * __restrict__ h,
+                            float * __restrict__ out, int U, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / U;
+        const int     u = (int)(i - b * U);
+        const float * px = mx + b * 3 * U + u;
+        const float * ph = mh + b * 3 * U + u;
+        const float az = px[0] + ph[0], ar = px[U] + ph[U];
+        const float z  = (az / (1.0f + expf(-az))) / az;
+        const float r  = (ar / (1.0f + expf(-ar))) / ar;
+        const float hh = tanhf(px[2 * U] + r * ph[2 * U]);
+        out[i]         = z * h[i] + (1.0f - z) * hh;
+    }
+}
+
 // ggml_argmax: one warp per row; ties resolve to the lowest index (std::max_element, rnn.cpp:76)
 __global__ void k_argmax(V4 a, int32_t * __restrict__ dst, int64_t rows) {
     const int lane = threadIdx.x & 31;
@@ -440,8 +458,89 @@ static bool tensor_core_mul_mat(Plan * plan, const ggml_tensor * t) {
     return K % 8 == 0 && M % 8 == 0 && N >= 64 && (K * N) % 4 == 0;
 }
 
+// ---- FAST-mode peephole fusions for graphs outside the MobileViT matcher (the batched GRU cell) ----------------------
+struct GruGates { const ggml_tensor *mx, *mh, *h; int U; };
+
+static const ggml_tensor * gate_view(const ggml_tensor * v, int k, int U, const ggml_tensor ** base) {
+    // VIEW(base [3U,B]; ne0 = U, ne1 = B, nb1 = base->nb[1], offset k*U floats)
+    if (!v || v->op != GGML_OP_VIEW || v->ne[0] != U || v->nb[1] != v->src[0]->nb[1]) return nullptr;
+    const ggml_tensor * b = v->src[0];
+    if (b->type != GGML_TYPE_F32 || !ggml_is_contiguous(b) || b->ne[0] != 3 * U || b->ne[1] != v->ne[1]) return nullptr;
+    if (v->view_offs != b->view_offs + (size_t)k * U * sizeof(float)) return nullptr;
+    if (*base && *base != b) return nullptr;
+    *base = b;
+    return b;
+}
+// s(a) = DIV(SILU(a), a) with a = ADD(view(mx,k), view(mh,k))
+static bool match_gate_sigmoid(const ggml_tensor * t, int k, int U, const ggml_tensor ** mx, const ggml_tensor ** mh, std::vector<const ggml_tensor *> & inner) {
+    if (t->op != GGML_OP_DIV || t->src[0]->op != GGML_OP_SILU || t->src[0]->src[0] != t->src[1]) return false;
+    const ggml_tensor * a = t->src[1];
+    if (a->op != GGML_OP_ADD || !gate_view(a->src[0], k, U, mx) || !gate_view(a->src[1], k, U, mh)) return false;
+    inner.push_back(t->src[0]);
+    inner.push_back(a);
+    return true;
+}
+static bool match_gru_gates(const ggml_tensor * t, GruGates & g, std::vector<const ggml_tensor *> & inner) {
+    // t = ADD(MUL(z, h), MUL(SUB(REPEAT(1), z), hh))
+    if (t->op != GGML_OP_ADD || t->type != GGML_TYPE_F32 || t->src[0]->op != GGML_OP_MUL || t->src[1]->op != GGML_OP_MUL) return false;
+    const ggml_tensor * zh = t->src[0], * rest = t->src[1];
+    const ggml_tensor * z = zh->src[0], * h = zh->src[1];
+    const int U = (int)t->ne[0];
+    if (!ggml_is_contiguous(h) || h->type != GGML_TYPE_F32 || h->ne[0] != U || h->ne[1] != t->ne[1]) return false;
+    const ggml_tensor * omz = rest->src[0], * hh = rest->src[1];
+    if (omz->op != GGML_OP_SUB || omz->src[1] != z || omz->src[0]->op != GGML_OP_REPEAT) return false;
+    const ggml_tensor * one = omz->src[0]->src[0];
+    if (one->op != GGML_OP_NONE || ggml_nelements(one) != 1 || !one->data || *(const float *)one->data != 1.0f) return false;
+    const ggml_tensor *mx = nullptr, *mh = nullptr;
+    if (!match_gate_sigmoid(z, 0, U, &mx, &mh, inner)) return false;
+    if (hh->op != GGML_OP_TANH || hh->src[0]->op != GGML_OP_ADD) return false;
+    const ggml_tensor * ah = hh->src[0];
+    const ggml_tensor * rm = ah->src[1];
+    if (!gate_view(ah->src[0], 2, U, &mx) || rm->op != GGML_OP_MUL || !gate_view(rm->src[1], 2, U, &mh)) return false;
+    if (!match_gate_sigmoid(rm->src[0], 1, U, &mx, &mh, inner)) return false;
+    const ggml_tensor * chain[] = {zh, rest, omz, omz->src[0], hh, ah, rm, z, rm->src[0]};
+    for (const ggml_tensor * x : chain) inner.push_back(x);
+    g.mx = mx; g.mh = mh; g.h = h; g.U = U;
+    return true;
+}
+
 void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
     const int n = gf->n_nodes;
+    // FAST-mode peepholes: (1) GRU gate chain -> one kernel, (2) mul_mat + bias add -> GEMM epilogue
+    std::unordered_map<const ggml_tensor *, GruGates> gru_roots;
+    std::unordered_map<const ggml_tensor *, int> skip;                           // nodes computed inside a fused kernel
+    std::unordered_map<const ggml_tensor *, const ggml_tensor *> bias_of;         // mul_mat node -> bias leaf folded into its GEMM
+    std::unordered_map<const ggml_tensor *, const ggml_tensor *> alias_of;        // bias-add node -> the mul_mat whose buffer it shares
+    if (runtime().mode == GGML_B200_MODE_FAST && !getenv("GGML_B200_NO_PEEPHOLE")) {
+        std::unordered_map<const ggml_tensor *, int> uses;
+        for (int i = 0; i < n; i++)
+            for (int s = 0; s < GGML_MAX_SRC; s++)
+                if (gf->nodes[i]->src[s]) uses[gf->nodes[i]->src[s]]++;
+        for (int i = 0; i < n; i++) {
+            const ggml_tensor * t = gf->nodes[i];
+            GruGates g;
+            std::vector<const ggml_tensor *> inner;
+            if (match_gru_gates(t, g, inner)) {
+                bool ok = true;
+                for (const ggml_tensor * x : inner)
+                    if (x->flags & GGML_TENSOR_FLAG_OUTPUT) ok = false;  // an inner value is observable: keep the chain
+                if (ok) {
+                    gru_roots[t] = g;
+                    for (const ggml_tensor * x : inner) skip[x] = 1;
+                }
+            }
+        }
+        for (int i = 0; i < n; i++) {
+            const ggml_tensor * t = gf->nodes[i];  // ADD(MUL_MAT(w, x), bias [M,1]) with the product used only here
+            if (t->op != GGML_OP_ADD || t->src[0]->op != GGML_OP_MUL_MAT || uses[t->src[0]] != 1) continue;
+            const ggml_tensor * mm = t->src[0], * b = t->src[1];
+            if (b->op != GGML_OP_NONE || b->view_src || b->type != GGML_TYPE_F32 || b->ne[0] != mm->ne[0] || ggml_nelements(b) != mm->ne[0]) continue;
+            if (!plan->slots.count(b) || plan->slots[b].kind != SLOT_CONST || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) continue;
+            if (!tensor_core_mul_mat(plan, mm)) continue;
+            bias_of[mm]  = b;
+            alias_of[t]  = mm;
+        }
+    }
     // ---- liveness: last node index that reads each buffer-owning tensor (through any chain of views) ----
     auto base_of = [](const ggml_tensor * t) -> const ggml_tensor * {
         while (t && is_view_op(t->op)) t = t->src[0];
@@ -455,6 +554,20 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
     }
     for (int i = 0; i < n; i++)
         if (gf->nodes[i]->flags & GGML_TENSOR_FLAG_OUTPUT) last_use[base_of(gf->nodes[i])] = n;  // outputs live forever
+    // fused kernels read their operands at the ROOT node and a folded bias-add lives in its mul_mat's buffer
+    for (int i = 0; i < n; i++) {
+        const ggml_tensor * t = gf->nodes[i];
+        auto extend = [&](const ggml_tensor * x, int until) {
+            const ggml_tensor * b = base_of(x);
+            if (!last_use.count(b) || last_use[b] < until) last_use[b] = until;
+        };
+        if (gru_roots.count(t)) {
+            extend(gru_roots[t].mx, i);
+            extend(gru_roots[t].mh, i);
+            extend(gru_roots[t].h, i);
+        }
+        if (alias_of.count(t)) extend(alias_of[t], last_use.count(t) ? last_use[t] : i);
+    }
     // ---- assign arena offsets in execution order ----
     ArenaPlanner ap;
     std::unordered_map<const ggml_tensor *, int64_t> scratch_off;
@@ -503,6 +616,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
         } else {
             plan->slots[t].dptr = plan->arena + plan->slots[t].offset;
         }
+        if (alias_of.count(t)) plan->slots[t].dptr = plan->slots[alias_of[t]].dptr;  // the GEMM epilogue already added the bias in place
     }
     // NOTE: a view created over a *view* records view_src = the root tensor and view_offs from the root, so the
     // alias above is correct for chains (reshape(permute(x)) etc.).
@@ -513,6 +627,16 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
         if (is_view_op(t->op)) continue;
         void *        d  = plan->slots[t].dptr;
         const int64_t ne = ggml_nelements(t);
+        if (skip.count(t) || alias_of.count(t)) { plan->n_folded++; continue; }
+        if (gru_roots.count(t)) {
+            const GruGates & g = gru_roots[t];
+            const float *mx = (const float *)device_ptr_of(plan, g.mx), *mh = (const float *)device_ptr_of(plan, g.mh), *hp = (const float *)device_ptr_of(plan, g.h);
+            const int U = g.U;
+            const int gr = grid_for(ne);
+            add_launch(plan, "gru_gates_fused", [=](cudaStream_t st) { k_gru_gates<<<gr, 256, 0, st>>>(mx, mh, hp, (float *)d, U, ne); }, 12.0 * ne,
+                       4.0 * ne * 8, t->name);
+            continue;
+        }
         auto src_view = [&](int s) { return v4(make_view(t->src[s], device_ptr_of(plan, t->src[s]))); };
         switch (t->op) {
             case GGML_OP_ADD: case GGML_OP_SUB: case GGML_OP_MUL: case GGML_OP_DIV: {
@@ -573,6 +697,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                     GemmEpilogue ep;
                     ep.out32 = (float *)d;
                     ep.ld32  = M;
+                    if (bias_of.count(t)) ep.shift = (const float *)device_ptr_of(plan, bias_of[t]);  // bias add folded into the epilogue
                     auto L = std::make_shared<GemmLaunch>();
                     if (!gemm_prepare(*L, x16, K, (const __half *)dw, K, N, M, K, ep)) B200_ABORT("tensor-core mul_mat lowering failed for %dx%dx%d", N, M, K);
                     add_launch(plan, "gemm_tcgen05_mul_mat", [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * N * M * K,
