@@ -230,6 +230,14 @@ __global__ void k_gru_gates(const float * __restrict__ mx, const float * __restr
     }
 }
 
+// [rows, ldp] padded GEMM result -> contiguous [rows, m]
+__global__ void k_unpad_rows(const float * __restrict__ src, float * __restrict__ dst, int m, int ldp, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / m;
+        dst[i]          = src[r * ldp + (i - r * m)];
+    }
+}
+
 // ggml_argmax: one warp per row; ties resolve to the lowest index (std::max_element, rnn.cpp:76)
 __global__ void k_argmax(V4 a, int32_t * __restrict__ dst, int64_t rows) {
     const int lane = threadIdx.x & 31;
@@ -455,7 +463,8 @@ static bool tensor_core_mul_mat(Plan * plan, const ggml_tensor * t) {
     if (it == plan->slots.end() || it->second.kind != SLOT_CONST) return false;
     if (x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x) || x->ne[2] != 1 || x->ne[3] != 1) return false;
     const int64_t K = w->ne[0], M = w->ne[1], N = x->ne[1];
-    return K % 8 == 0 && M % 8 == 0 && N >= 64 && (K * N) % 4 == 0;
+    (void)M;  // M that is not a multiple of 8 (the GRU's 66-way dense layer) goes through a zero-padded weight and a padded scratch
+    return K % 8 == 0 && N >= 64 && (K * N) % 4 == 0;
 }
 
 // ---- FAST-mode peephole fusions for graphs outside the MobileViT matcher (the batched GRU cell) ----------------------
@@ -586,7 +595,8 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
             plan->slots[t] = s;
             if (lu < n) dies_at[lu < i ? i : lu].push_back(t);  // a never-read result is freed right after its node
             if (tensor_core_mul_mat(plan, t)) {  // scratch for the f16 copy of the activation operand, live for this node only
-                const int64_t sb = (int64_t)ggml_nelements(t->src[1]) * 2;
+                int64_t sb = (int64_t)ggml_nelements(t->src[1]) * 2;
+                if (t->ne[0] % 8) sb = ArenaPlanner::align_up(sb) + ((t->ne[0] + 7) / 8 * 8) * t->ne[1] * 4;  // + padded f32 result
                 const int64_t so = ap.alloc(sb);
                 scratch_off[t] = so;
                 ap.release(so, sb);
@@ -681,7 +691,8 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                     const ggml_tensor * wt = t->src[0];
                     const ggml_tensor * xt = t->src[1];
                     const int K = (int)wt->ne[0], M = (int)wt->ne[1], N = (int)xt->ne[1];
-                    std::vector<uint16_t> w16((size_t)K * M);
+                    const int Mp = (M + 7) / 8 * 8;
+                    std::vector<uint16_t> w16((size_t)K * Mp, 0);
                     ggml_fp32_to_fp16_row((const float *)wt->data, w16.data(), K * M);
                     void * dw = nullptr;
                     B200_CHECK(cudaMalloc(&dw, w16.size() * 2));
@@ -695,13 +706,31 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                     add_launch(plan, "cast_f32_to_f16", [=](cudaStream_t st) { k_cast_f16<<<cg, 256, 0, st>>>((const float4 *)x32, (uint2 *)x16, n4); }, 0.0,
                                6.0 * K * N, t->name);
                     GemmEpilogue ep;
-                    ep.out32 = (float *)d;
-                    ep.ld32  = M;
-                    if (bias_of.count(t)) ep.shift = (const float *)device_ptr_of(plan, bias_of[t]);  // bias add folded into the epilogue
+                    float * padded = Mp == M ? nullptr : (float *)(plan->arena + scratch_off[t] + ArenaPlanner::align_up((int64_t)K * N * 2));
+                    ep.out32 = padded ? padded : (float *)d;
+                    ep.ld32  = Mp;
+                    if (bias_of.count(t)) {  // bias add folded into the epilogue
+                        ep.shift = (const float *)device_ptr_of(plan, bias_of[t]);
+                        if (padded) {
+                            std::vector<float> bp(Mp, 0.f);
+                            memcpy(bp.data(), bias_of[t]->data, (size_t)M * 4);
+                            void * db = nullptr;
+                            B200_CHECK(cudaMalloc(&db, (size_t)Mp * 4));
+                            plan->owned_device.push_back(db);
+                            B200_CHECK(cudaMemcpy(db, bp.data(), (size_t)Mp * 4, cudaMemcpyHostToDevice));
+                            ep.shift = (const float *)db;
+                        }
+                    }
                     auto L = std::make_shared<GemmLaunch>();
-                    if (!gemm_prepare(*L, x16, K, (const __half *)dw, K, N, M, K, ep)) B200_ABORT("tensor-core mul_mat lowering failed for %dx%dx%d", N, M, K);
+                    if (!gemm_prepare(*L, x16, K, (const __half *)dw, K, N, Mp, K, ep)) B200_ABORT("tensor-core mul_mat lowering failed for %dx%dx%d", N, M, K);
                     add_launch(plan, "gemm_tcgen05_mul_mat", [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * N * M * K,
                                2.0 * ((double)N * K + (double)M * K) + 4.0 * N * M, t->name);
+                    if (padded) {
+                        const int64_t tot = (int64_t)N * M;
+                        const int     ug  = grid_for(tot);
+                        float *       dst = (float *)d;
+                        add_launch(plan, "unpad_rows", [=](cudaStream_t st) { k_unpad_rows<<<ug, 256, 0, st>>>(padded, dst, M, Mp, tot); }, 0.0, 8.0 * tot, t->name);
+                    }
                     break;
                 }
                 MulMatArgs g;

@@ -147,6 +147,10 @@ extern "C" float gru_generate(gru_model * m, const int32_t * first_tokens, int B
         memcpy(out_tokens + (size_t)t * B, g.next_ids->data, (size_t)B * 4);
     }
     const int64_t t1 = ggml_time_us();
+    if (getenv("GRU_B200_PROFILE")) {  // per-launch device times of one cell step, to stderr
+        std::vector<char> buf(1 << 16);
+        if (ggml_b200_graph_profile_json(g.gf, 20, buf.data(), buf.size()) == 0) fprintf(stderr, "%s\n", buf.data());
+    }
     if (final_state && ggml_b200_tensor_download(g.gf, g.new_states, final_state) != 0) return -1.f;
     return steps > 1 ? (float)(t1 - t0) / 1000.f * (float)steps / (float)(steps - 1) : 0.f;
 }

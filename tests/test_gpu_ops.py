@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-F32, F16, I32 = 0, 1, 2  # enum ggml_type (include/ggml/ggml.h)
+F32, F16, I32 = 0, 1, 26  # enum ggml_type (include/ggml/ggml.h)
 vp = ctypes.c_void_p
 
 
