@@ -230,6 +230,14 @@ __global__ void k_gru_gates(const float * __restrict__ mx, const float * __restr
     }
 }
 
+// dst[r, :] = table[ids[r], :] in 16-byte pieces (folded embedding projection)
+__global__ void k_gather_rows_f4(const float4 * __restrict__ table, const int32_t * __restrict__ ids, float4 * __restrict__ dst, int m4, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / m4;
+        dst[i]          = table[(int64_t)ids[r] * m4 + (i - r * m4)];
+    }
+}
+
 // [rows, ldp] padded GEMM result -> contiguous [rows, m]
 __global__ void k_unpad_rows(const float * __restrict__ src, float * __restrict__ dst, int m, int ldp, int64_t total) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -255,7 +263,7 @@ __global__ void k_argmax(V4 a, int32_t * __restrict__ dst, int64_t rows) {
         const int   oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (lane == 0) dst[row] = bi;
+    if (lane == 0) dst[row] = bi == 0x7fffffff ? 0 : bi;  // nothing compared greater (all NaN / -inf): index 0, as upstream's vec_argmax
 }
 
 // ---- generic 64x64 tiled "GEMM with functor loaders" on CUDA cores ----------------------------------------
@@ -520,6 +528,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
     std::unordered_map<const ggml_tensor *, int> skip;                           // nodes computed inside a fused kernel
     std::unordered_map<const ggml_tensor *, const ggml_tensor *> bias_of;         // mul_mat node -> bias leaf folded into its GEMM
     std::unordered_map<const ggml_tensor *, const ggml_tensor *> alias_of;        // bias-add node -> the mul_mat whose buffer it shares
+    std::unordered_map<const ggml_tensor *, const ggml_tensor *> table_of;        // mul_mat node -> the get_rows it absorbed (folded embedding projection)
     if (runtime().mode == GGML_B200_MODE_FAST && !getenv("GGML_B200_NO_PEEPHOLE")) {
         std::unordered_map<const ggml_tensor *, int> uses;
         for (int i = 0; i < n; i++)
@@ -548,6 +557,18 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
             if (!tensor_core_mul_mat(plan, mm)) continue;
             bias_of[mm]  = b;
             alias_of[t]  = mm;
+            // W^T E[ids] + b with a constant embedding table E (rnn.cpp:200-209): fold W^T E + b into one [M, V] table at plan
+            // time (f32 on the host) and gather its rows -- the per-step GEMM disappears
+            const ggml_tensor * gr = mm->src[1];
+            if (gr->op == GGML_OP_GET_ROWS && uses[gr] == 1 && !(gr->flags & GGML_TENSOR_FLAG_OUTPUT) && mm->ne[0] % 4 == 0) {
+                const ggml_tensor * E = gr->src[0];
+                if (E->op == GGML_OP_NONE && !E->view_src && E->type == GGML_TYPE_F32 && ggml_is_contiguous(E) && E->data && E->ne[2] == 1 && E->ne[3] == 1 &&
+                    E->ne[1] <= 65536 && plan->slots.count(E) && plan->slots[E].kind == SLOT_CONST && gr->src[1]->type == GGML_TYPE_I32 &&
+                    ggml_is_contiguous(gr->src[1])) {
+                    table_of[mm] = gr;
+                    skip[gr]     = 1;
+                }
+            }
         }
     }
     // ---- liveness: last node index that reads each buffer-owning tensor (through any chain of views) ----
@@ -576,6 +597,7 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
             extend(gru_roots[t].h, i);
         }
         if (alias_of.count(t)) extend(alias_of[t], last_use.count(t) ? last_use[t] : i);
+        if (table_of.count(t)) extend(table_of[t]->src[1], i);
     }
     // ---- assign arena offsets in execution order ----
     ArenaPlanner ap;
@@ -684,6 +706,30 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
                 });
             } break;
             case GGML_OP_MUL_MAT: {
+                if (table_of.count(t)) {
+                    const ggml_tensor * wt = t->src[0], * gr = table_of[t], * E = gr->src[0], * bt = bias_of[t];
+                    const int K = (int)wt->ne[0], M = (int)wt->ne[1], V = (int)E->ne[1];
+                    std::vector<float> table((size_t)V * M);
+                    const float *Wd = (const float *)wt->data, *Ed = (const float *)E->data, *Bd = (const float *)bt->data;
+                    for (int v = 0; v < V; v++)
+                        for (int m = 0; m < M; m++) {
+                            double acc = 0.0;
+                            for (int k = 0; k < K; k++) acc += (double)Wd[(size_t)m * K + k] * (double)Ed[(size_t)v * K + k];
+                            table[(size_t)v * M + m] = (float)acc + Bd[m];
+                        }
+                    void * dt = nullptr;
+                    B200_CHECK(cudaMalloc(&dt, table.size() * 4));
+                    plan->owned_device.push_back(dt);
+                    B200_CHECK(cudaMemcpy(dt, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+                    plan->weight_bytes += (int64_t)table.size() * 4;
+                    const int32_t * ids = (const int32_t *)device_ptr_of(plan, gr->src[1]);
+                    const int       m4  = M / 4;
+                    const int64_t   tot = (int64_t)m4 * t->ne[1];
+                    const int       gg  = grid_for(tot);
+                    add_launch(plan, "gather_folded_projection", [=](cudaStream_t st) { k_gather_rows_f4<<<gg, 256, 0, st>>>((const float4 *)dt, ids, (float4 *)d, m4, tot); },
+                               0.0, 32.0 * tot, t->name);
+                    break;
+                }
                 if (scratch_off.count(t)) {
                     // FAST-mode lowering of a dense layer in a graph the fused planner does not know (e.g. the GRU cell):
                     // ggml [K,M] weights x [K,N] activations -> [M,N] is exactly the K-major A/B layout of the tcgen05 GEMM

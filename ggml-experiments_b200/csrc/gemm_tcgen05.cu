@@ -539,7 +539,10 @@ static void choose_tiling(GemmLaunch & L, int N) {
     // Output-heavy shapes (K small against N) are epilogue-bound: 128-column tiles let two CTAs (16 epilogue warps)
     // share an SM, and re-reading the small A operand from L2 is cheap.  Otherwise one tile spans N (<= 256) so A is
     // read exactly once.  With several N tiles the tile width is a multiple of the 64-column store slab.
-    const int max_bn       = (N > 128 && 2 * p.K <= N) ? 128 : 256;
+    // Compute-heavy shapes (K >= 512, the batched GRU's recurrent matmul) take 256-wide tiles again: with 128-wide tiles the
+    // operand re-reads from L2 (403 MB at 4096 x 3072 x 1024) bound the kernel at ~570 TFLOP/s, 256-wide reaches ~900.
+    int max_bn             = (N > 128 && 2 * p.K <= N && p.K < 512) ? 128 : 256;
+    if (const char * e = getenv("GGML_B200_GEMM_BN")) max_bn = atoi(e);  // tuning probe
     p.n_tiles              = (N + max_bn - 1) / max_bn;
     int per                = (N + p.n_tiles - 1) / p.n_tiles;
     p.block_n              = p.n_tiles > 1 ? (per + 63) / 64 * 64 : (per + 31) / 32 * 32;

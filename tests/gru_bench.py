@@ -17,6 +17,7 @@ m = GRU(path)
 first = (np.arange(B) * 7 % 66).astype(np.int32)
 m.generate(first, 3)  # warm-up (plan build)
 toks, state, ms = m.generate(first, steps)
+print('nan in final state:', int(np.isnan(state).sum()), 'token range', int(toks.min()), int(toks.max()), flush=True)
 ref, margins, _ = GO.generate_batch(w, first[:64], min(steps, 20))
 agree = float((toks[:min(steps, 20), :64] == ref).mean())
 flop = 2.0 * B * (256 * 3072 + 1024 * 3072 + 1024 * 66)
