@@ -52,6 +52,7 @@ struct Runtime {
     int          sm_count        = 148;
     bool         verbose         = false;
     bool         use_cuda_graph  = true;
+    cudaEvent_t  compute_chain   = nullptr;  // end of the most recent private-stream forward (pipelined slots run their kernels FIFO)
 };
 Runtime &    runtime();
 void         ensure_device();  // aborts if no CUDA device is usable (there is no CPU fallback)
@@ -120,6 +121,7 @@ struct Plan {
     bool                  upload_inputs = true, download_outputs = true;
     cudaGraphExec_t       graph_exec = nullptr;
     bool                  graph_failed = false;
+    cudaEvent_t           compute_done   = nullptr;  // recorded after this plan's kernels on its private stream
     cudaStream_t          private_stream = nullptr;  // set by ggml_b200_graph_use_private_stream (pipelined submission)
     ~Plan();
 };

@@ -137,6 +137,10 @@ static std::unordered_map<const ggml_cgraph *, std::vector<std::pair<ggml_tensor
 
 Plan::~Plan() {
     if (private_stream) { cudaStreamSynchronize(private_stream); cudaStreamDestroy(private_stream); }
+    if (compute_done) {
+        if (runtime().compute_chain == compute_done) runtime().compute_chain = nullptr;
+        cudaEventDestroy(compute_done);
+    }
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (void * p : owned_device) cudaFree(p);
     for (void * p : pinned) cudaHostUnregister(p);
@@ -352,12 +356,21 @@ void run_plan(Plan * plan, bool wait_for_results) {
             }
         }
     }
+    // Pipelined slots: the copies of one slot overlap the kernels of another, but the forwards themselves run FIFO --
+    // two forwards sharing the SMs only thrash L2 and fight for CTA slots (bench e2e 9.4 -> see profiles/README.md).
+    static const bool chain = getenv("GGML_B200_SLOT_OVERLAP") == nullptr;
+    if (plan->private_stream && chain && rt.compute_chain) B200_CHECK(cudaStreamWaitEvent(st, rt.compute_chain, 0));
     if (plan->graph_exec) {
         B200_CHECK(cudaGraphLaunch(plan->graph_exec, st));
     } else {
         for (auto & l : plan->launches) l(st);
     }
     B200_CHECK(cudaGetLastError());
+    if (plan->private_stream && chain) {
+        if (!plan->compute_done) B200_CHECK(cudaEventCreateWithFlags(&plan->compute_done, cudaEventDisableTiming));
+        B200_CHECK(cudaEventRecord(plan->compute_done, st));
+        rt.compute_chain = plan->compute_done;
+    }
     if (plan->download_outputs) {
         for (const Transfer & d : plan->downloads) B200_CHECK(cudaMemcpyAsync(d.t->data, d.dptr, d.bytes, cudaMemcpyDeviceToHost, st));
         if (wait_for_results) B200_CHECK(cudaStreamSynchronize(st));  // ggml semantics: results are readable when compute returns
