@@ -685,4 +685,82 @@ void launch_pool_mean(const __half * x16, const float * x32, int N, int HW, int 
     k_pool_mean<<<grid, 128, 0, st>>>(x16, x32, HW, C, out);
 }
 
+// ---- u8 image preprocessing -------------------------------------------------------------------------------
+// One thread per output pixel, all 3 channels.  The arithmetic is the reference's, operation for operation, with explicit
+// round-to-nearest intrinsics so that nvcc cannot contract mul+add into fma: the result is bit-identical to the CPU code.
+__global__ void k_preprocess_u8(const uint8_t * __restrict__ src, int sh, int sw, float * __restrict__ dst, int H, int W, float scale, int nx3, int ny3,
+                                int64_t total) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int     x = (int)(i % W);
+    const int     y = (int)((i / W) % H);
+    const int64_t n = i / ((int64_t)W * H);
+    float * o = dst + i * 3;
+    if (x >= nx3 || y >= ny3) {
+        o[0] = o[1] = o[2] = 0.f;
+        return;
+    }
+    const float sx = __fsub_rn(__fmul_rn((float)x + 0.5f, scale), 0.5f);
+    const float sy = __fsub_rn(__fmul_rn((float)y + 0.5f, scale), 0.5f);
+    int x0 = max(0, (int)floorf(sx)), y0 = max(0, (int)floorf(sy));
+    x0 = min(x0, sw - 1);
+    y0 = min(y0, sh - 1);
+    const int   x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+    const float dx = __fsub_rn(sx, (float)x0), dy = __fsub_rn(sy, (float)y0);
+    const float wx0 = __fsub_rn(1.0f, dx), wy0 = __fsub_rn(1.0f, dy);
+    const uint8_t * img = src + n * (int64_t)sh * sw * 3;
+    const uint8_t *p00 = img + 3 * ((int64_t)y0 * sw + x0), *p01 = img + 3 * ((int64_t)y0 * sw + x1);
+    const uint8_t *p10 = img + 3 * ((int64_t)y1 * sw + x0), *p11 = img + 3 * ((int64_t)y1 * sw + x1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float v0 = __fadd_rn(__fmul_rn((float)p00[c], wx0), __fmul_rn((float)p01[c], dx));
+        const float v1 = __fadd_rn(__fmul_rn((float)p10[c], wx0), __fmul_rn((float)p11[c], dx));
+        const float v  = __fadd_rn(__fmul_rn(v0, wy0), __fmul_rn(v1, dy));
+        const float q  = fminf(fmaxf(roundf(v), 0.0f), 255.0f);
+        o[c]           = __fdiv_rn((float)(uint8_t)q, 255.0f);
+    }
+}
+void launch_preprocess_u8(const uint8_t * src, int n, int sh, int sw, float * dst, int H, int W, cudaStream_t st) {
+    // scale as main.cpp:550 for the square target; the general form keeps the whole image inside an H x W target
+    const float scale = H == W ? (float)(sw > sh ? sw : sh) * 1.0f / (float)W : fmaxf((float)sw / (float)W, (float)sh / (float)H);
+    int nx3 = (int)((float)sw / scale + 0.5f), ny3 = (int)((float)sh / scale + 0.5f);
+    if (nx3 > W) nx3 = W;
+    if (ny3 > H) ny3 = H;
+    const int64_t total = (int64_t)n * H * W;
+    k_preprocess_u8<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, sh, sw, dst, H, W, scale, nx3, ny3, total);
+}
+
+// Classifier head: logits[n][o] = sum_c pooled[n][c] * W[c][o] + bias[o], f32 FFMA.  W is the file's
+// (in, out) kernel as loaded (ggml ne = (out, in): `out` fastest), so consecutive threads read consecutive weights;
+// 8 pooled rows are staged in shared memory and share each weight load.
+static constexpr int kHeadRows = 8;
+__global__ void k_head_linear(const float * __restrict__ pooled, const float * __restrict__ W, const float * __restrict__ bias, float * __restrict__ out,
+                              int N, int C, int OUT) {
+    extern __shared__ float s_rows[];  // [kHeadRows][C]
+    const int n0 = blockIdx.y * kHeadRows;
+    for (int i = threadIdx.x; i < kHeadRows * C; i += blockDim.x) {
+        const int r = i / C;
+        s_rows[i]   = n0 + r < N ? pooled[(int64_t)(n0 + r) * C + (i - r * C)] : 0.f;
+    }
+    __syncthreads();
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= OUT) return;
+    float acc[kHeadRows];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; r++) acc[r] = 0.f;
+    for (int c = 0; c < C; c++) {
+        const float w = W[(int64_t)c * OUT + o];
+#pragma unroll
+        for (int r = 0; r < kHeadRows; r++) acc[r] = fmaf(s_rows[r * C + c], w, acc[r]);
+    }
+    const float b = bias[o];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; r++)
+        if (n0 + r < N) out[(int64_t)(n0 + r) * OUT + o] = acc[r] + b;
+}
+void launch_head_linear(const float * pooled, const float * W, const float * bias, int N, int C, int OUT, float * out, cudaStream_t st) {
+    dim3 grid((OUT + 127) / 128, (N + kHeadRows - 1) / kHeadRows);
+    k_head_linear<<<grid, 128, (size_t)kHeadRows * C * sizeof(float), st>>>(pooled, W, bias, out, N, C, OUT);
+}
+
 }  // namespace b200

@@ -547,8 +547,19 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
         if (gf->nodes[i]->flags & GGML_TENSOR_FLAG_OUTPUT) outs.push_back(gf->nodes[i]);
     if (outs.empty()) return false;
     std::vector<FVal *> out_vals;
+    // classifier head: ADD(MUL_MAT(CONT(TRANSPOSE(kernel)), RESHAPE(pooled)), bias) with `pooled` itself an output
+    struct Head { const ggml_tensor *pooled, *w, *b; };
+    std::map<const ggml_tensor *, Head> heads;
     try {
         for (ggml_tensor * t : outs) {
+            const ggml_tensor *hx, *hw, *hb;
+            if (t->op == GGML_OP_ADD && P.match_dense(t, &hx, &hw, &hb) && hx->op == GGML_OP_RESHAPE && hx->src[0]->op == GGML_OP_POOL_MEAN_HW) {
+                const ggml_tensor * pooled = hx->src[0];
+                if (!(pooled->flags & GGML_TENSOR_FLAG_OUTPUT) || hx->ne[0] != pooled->ne[2] || hx->ne[1] != pooled->ne[3]) throw Fail();
+                heads[t] = Head{pooled, hw, hb};
+                out_vals.push_back(P.lower(pooled));
+                continue;
+            }
             FVal * v = P.lower(t);
             if (t->op == GGML_OP_POOL_MEAN_HW) {
                 if (!(t->ne[2] == v->C && t->ne[3] == v->N)) throw Fail();
@@ -661,6 +672,11 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     // graph outputs in ggml layout
     std::vector<int64_t> out_off(outs.size());
     for (size_t i = 0; i < outs.size(); i++) out_off[i] = ap.alloc((int64_t)ggml_nelements(outs[i]) * 4);
+    std::map<const ggml_tensor *, size_t> head_w, head_b;
+    for (auto & kv : heads) {
+        head_w[kv.first] = P.pool.add(kv.second.w->data, ggml_nbytes(kv.second.w));
+        head_b[kv.first] = P.pool.add(kv.second.b->data, (size_t)kv.first->ne[0] * 4);
+    }
     plan->arena_bytes = ap.extent;
     B200_CHECK(cudaMalloc((void **)&plan->arena, plan->arena_bytes > 0 ? plan->arena_bytes : 256));
     plan->owned_device.push_back(plan->arena);
@@ -826,7 +842,15 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
         s.dptr = dst;
         s.bytes = (int64_t)ggml_nelements(t) * 4;
         plan->slots[t] = s;
-        if (t->op == GGML_OP_POOL_MEAN_HW) {
+        if (heads.count(t)) {
+            const Head & h = heads[t];
+            const float * pooled = (const float *)plan->slots.at(h.pooled).dptr;  // node order: the pooled output was emitted before its consumer
+            const int N = (int)t->ne[1], C = (int)h.pooled->ne[2], OUT = (int)t->ne[0];
+            const float * W  = P.pool.ptr<float>(head_w[t]);
+            const float * bb = P.pool.ptr<float>(head_b[t]);
+            add_launch(plan, "classifier_head_f32", [=](cudaStream_t st) { launch_head_linear(pooled, W, bb, N, C, OUT, dst, st); }, 2.0 * N * C * OUT,
+                       4.0 * ((double)C * OUT + (double)N * (C + OUT)), t->name);
+        } else if (t->op == GGML_OP_POOL_MEAN_HW) {
             FVal * in = v->prod->in[0];
             const __half * x16 = in->p32 ? nullptr : in->p16;
             const float * x32 = in->p32;

@@ -121,6 +121,8 @@ struct Plan {
     bool                  upload_inputs = true, download_outputs = true;
     cudaGraphExec_t       graph_exec = nullptr;
     bool                  graph_failed = false;
+    void *                u8_stage       = nullptr;  // device staging of raw u8 images (ggml_b200_graph_upload_u8_images)
+    size_t                u8_stage_bytes = 0;
     cudaEvent_t           compute_done   = nullptr;  // recorded after this plan's kernels on its private stream
     cudaStream_t          private_stream = nullptr;  // set by ggml_b200_graph_use_private_stream (pipelined submission)
     ~Plan();

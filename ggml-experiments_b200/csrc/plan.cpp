@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 
+#include "fast_kernels.h"
 #include "internal.h"
 
 namespace b200 {
@@ -142,6 +143,7 @@ Plan::~Plan() {
         cudaEventDestroy(compute_done);
     }
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (u8_stage) cudaFree(u8_stage);
     for (void * p : owned_device) cudaFree(p);
     for (void * p : pinned) cudaHostUnregister(p);
     if (host_mirror) cudaFreeHost(host_mirror);
@@ -473,6 +475,29 @@ extern "C" void * ggml_b200_tensor_get_device_data(struct ggml_cgraph * gf, stru
     Plan * p = (Plan *)gf->plan;
     auto it  = p->slots.find(t);
     return it == p->slots.end() ? nullptr : it->second.dptr;
+}
+// Device-side replacement of sam_image_preprocess + the HWC copy (main.cpp:538-601,627-634): enqueue, on the graph's stream,
+// the H2D copy of n raw u8 images and the resize/normalise kernel that writes the device copy of the f32 input leaf.
+extern "C" int ggml_b200_graph_upload_u8_images(struct ggml_cgraph * gf, struct ggml_tensor * input, const uint8_t * host_u8, int n, int src_h,
+                                                int src_w) {
+    if (!gf->plan) B200_ABORT("ggml_b200_graph_upload_u8_images: call ggml_b200_graph_prepare first");
+    Plan * p = (Plan *)gf->plan;
+    auto it  = p->slots.find(input);
+    if (it == p->slots.end() || !it->second.dptr || input->type != GGML_TYPE_F32 || input->ne[0] != 3 || input->ne[3] != n || !host_u8 || src_h <= 0 ||
+        src_w <= 0)
+        return 1;
+    const size_t bytes = (size_t)n * src_h * src_w * 3;
+    cudaStream_t st    = p->private_stream ? p->private_stream : current_stream();
+    if (p->u8_stage_bytes < bytes) {
+        B200_CHECK(cudaStreamSynchronize(st));
+        if (p->u8_stage) B200_CHECK(cudaFree(p->u8_stage));
+        B200_CHECK(cudaMalloc(&p->u8_stage, bytes));
+        p->u8_stage_bytes = bytes;
+    }
+    B200_CHECK(cudaMemcpyAsync(p->u8_stage, host_u8, bytes, cudaMemcpyHostToDevice, st));
+    launch_preprocess_u8((const uint8_t *)p->u8_stage, n, src_h, src_w, (float *)it->second.dptr, (int)input->ne[2], (int)input->ne[1], st);
+    B200_CHECK(cudaGetLastError());
+    return 0;
 }
 extern "C" void ggml_b200_graph_set_transfers(struct ggml_cgraph * gf, bool upload_inputs, bool download_outputs) {
     if (!gf->plan) B200_ABORT("ggml_b200_graph_set_transfers: call ggml_b200_graph_prepare first");

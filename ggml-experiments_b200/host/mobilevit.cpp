@@ -3,6 +3,7 @@
 #include "mobilevit.h"
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -134,6 +135,18 @@ bool model::load(const std::string & path) {
     bind(*this, layer_4, root + "/encoder/layer.3");
     bind(*this, layer_5, root + "/encoder/layer.4");
     bind(*this, conv_1x1_exp, root + "/conv_1x1_exp");
+    // optional classification head (TFMobileViTForImageClassification's `classifier/{kernel,bias}:0`, kernel (in, out) like
+    // every dense kernel of the file); the reference stops at the feature map (main.cpp:645), SURVEY 8f.1
+    for (auto & kv : tensors) {
+        const std::string & nm = kv.first;
+        auto ends_with = [&](const char * suf) { const size_t n = strlen(suf); return nm.size() >= n && nm.compare(nm.size() - n, n, suf) == 0; };
+        if (ends_with("classifier/kernel:0")) classifier_w = kv.second;
+        if (ends_with("classifier/bias:0")) classifier_b = kv.second;
+    }
+    if (classifier_w && (!classifier_b || classifier_w->ne[1] != conv_1x1_exp.out_channels() || classifier_b->ne[0] != classifier_w->ne[0])) {
+        fprintf(stderr, "mobilevit: classifier tensors do not fit the feature width\n");
+        return false;
+    }
     return true;
 }
 
@@ -142,6 +155,7 @@ model::~model() {
         ggml_graph_release_plan(kv.second.gf);
         ggml_free(kv.second.ctx);
         ggml_b200_host_free(kv.second.pinned_arena);
+        ggml_b200_host_free(kv.second.input_u8);
     }
     if (ctx_w) ggml_free(ctx_w);
 }
@@ -291,6 +305,7 @@ forward_graph & model::graph_for(int n, int h, int w, int slot) {
     forward_graph g;
     const size_t in_bytes  = (size_t)n * h * w * 3 * sizeof(float);
     size_t out_bytes = (size_t)n * conv_1x1_exp.out_channels() * ((size_t)(h / 32) * (w / 32) + 1) * sizeof(float);
+    if (classifier_w) out_bytes += (size_t)n * (size_t)classifier_w->ne[0] * sizeof(float);
     const char * dbg = getenv("MVIT_DEBUG_STAGES");
     const bool   debug_stages = dbg && atoi(dbg) > 0;
     if (debug_stages) out_bytes += (size_t)n * h * w * 16 * sizeof(float);  // all stage taps together are < 16 floats per input pixel
@@ -310,6 +325,11 @@ forward_graph & model::graph_for(int n, int h, int w, int slot) {
     ggml_set_name(g.pooled, "pooled");
     ggml_build_forward_expand(g.gf, g.features);
     ggml_build_forward_expand(g.gf, g.pooled);
+    if (classifier_w) {  // logits = pooled . kernel + bias
+        g.logits = dense(g.ctx, ggml_reshape_2d(g.ctx, g.pooled, g.pooled->ne[2], g.pooled->ne[3]), classifier_w, classifier_b);
+        ggml_set_name(g.logits, "logits");
+        ggml_build_forward_expand(g.gf, g.logits);
+    }
     if (debug_stages)
         for (ggml_tensor * t : g.stages) ggml_build_forward_expand(g.gf, t);  // marks them as outputs -> host shadows
     return graphs.emplace(key, g).first->second;
@@ -321,6 +341,7 @@ void model::release(int n, int h, int w) {
             ggml_graph_release_plan(it->second.gf);
             ggml_free(it->second.ctx);
             ggml_b200_host_free(it->second.pinned_arena);
+            ggml_b200_host_free(it->second.input_u8);
             it = graphs.erase(it);
         } else {
             ++it;
@@ -353,6 +374,7 @@ extern "C" void    mvit_free(mvit_model * m) { delete m; }
 extern "C" int     mvit_num_tensors(const mvit_model * m) { return (int)m->m.tensors.size(); }
 extern "C" int64_t mvit_num_weights(const mvit_model * m) { return m->m.total_weights; }
 extern "C" int     mvit_out_channels(const mvit_model * m) { return m->m.conv_1x1_exp.out_channels(); }
+extern "C" int     mvit_num_classes(const mvit_model * m) { return m->m.classifier_w ? (int)m->m.classifier_w->ne[0] : 0; }
 
 extern "C" int mvit_compute(mvit_model * m, int n, int h, int w);
 
@@ -385,6 +407,24 @@ extern "C" const float * mvit_host_features(mvit_model * m, int n, int h, int w)
 extern "C" const float * mvit_host_pooled(mvit_model * m, int n, int h, int w) {
     if (!m || !shape_ok(n, h, w)) return nullptr;
     return (const float *)ggml_get_data(m->m.graph_for(n, h, w).pooled);
+}
+extern "C" const float * mvit_host_logits(mvit_model * m, int n, int h, int w) {
+    if (!m || !shape_ok(n, h, w) || !m->m.classifier_w) return nullptr;
+    return (const float *)ggml_get_data(m->m.graph_for(n, h, w).logits);
+}
+// classify: images -> class logits [n][classes] and/or top-1 class ids; 2 when the weight file has no classifier
+extern "C" int mvit_classify(mvit_model * m, const float * images_hwc, int n, int h, int w, float * logits, int32_t * top1) {
+    if (!m || !images_hwc || !shape_ok(n, h, w)) return 1;
+    if (!m->m.classifier_w) return 2;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    memcpy(ggml_get_data(g.input_hwc), images_hwc, ggml_nbytes(g.input_hwc));
+    mvit_compute(m, n, h, w);
+    const float * lg = (const float *)ggml_get_data(g.logits);
+    const int     nc = (int)g.logits->ne[0];
+    if (logits) memcpy(logits, lg, ggml_nbytes(g.logits));
+    if (top1)
+        for (int i = 0; i < n; i++) top1[i] = (int32_t)(std::max_element(lg + (size_t)i * nc, lg + (size_t)(i + 1) * nc) - (lg + (size_t)i * nc));
+    return 0;
 }
 extern "C" int mvit_profile_json(mvit_model * m, int n, int h, int w, int reps, char * buf, size_t cap) {
     if (mvit_prepare(m, n, h, w)) return -1;
@@ -440,9 +480,60 @@ extern "C" const float * mvit_slot_features(mvit_model * m, int n, int h, int w,
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     return g ? (const float *)ggml_get_data(g->features) : nullptr;
 }
+extern "C" const float * mvit_slot_logits(mvit_model * m, int n, int h, int w, int slot) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    return g && g->logits ? (const float *)ggml_get_data(g->logits) : nullptr;
+}
 extern "C" const float * mvit_slot_pooled(mvit_model * m, int n, int h, int w, int slot) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     return g ? (const float *)ggml_get_data(g->pooled) : nullptr;
+}
+
+// ---- u8 images, preprocessing on the device ----
+static uint8_t * u8_staging(mvit::forward_graph & g, int n, int src_h, int src_w) {
+    const size_t bytes = (size_t)n * src_h * src_w * 3;
+    if (g.input_u8_bytes < bytes) {
+        if (g.gf->plan) ggml_b200_graph_wait(g.gf);  // a submitted copy may still read the old buffer
+        ggml_b200_host_free(g.input_u8);
+        g.input_u8       = (uint8_t *)ggml_b200_host_malloc(bytes);
+        g.input_u8_bytes = g.input_u8 ? bytes : 0;
+    }
+    return g.input_u8;
+}
+static int submit_u8(mvit::forward_graph & g, int n, int src_h, int src_w, bool wait) {
+    if (!g.input_u8 || g.input_u8_bytes < (size_t)n * src_h * src_w * 3) return 1;
+    ggml_b200_graph_prepare(g.ctx, g.gf);
+    if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, g.input_u8, n, src_h, src_w)) return 1;
+    ggml_b200_graph_set_transfers(g.gf, false, true);
+    if (wait) ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
+    else ggml_b200_graph_compute_async(g.ctx, g.gf);
+    return 0;
+}
+extern "C" uint8_t * mvit_host_input_u8(mvit_model * m, int n, int h, int w, int src_h, int src_w) {
+    if (!m || !shape_ok(n, h, w) || src_h <= 0 || src_w <= 0) return nullptr;
+    return u8_staging(m->m.graph_for(n, h, w), n, src_h, src_w);
+}
+extern "C" int mvit_compute_u8(mvit_model * m, int n, int h, int w, int src_h, int src_w) {
+    if (!m || !shape_ok(n, h, w) || src_h <= 0 || src_w <= 0) return 1;
+    return submit_u8(m->m.graph_for(n, h, w), n, src_h, src_w, true);
+}
+extern "C" uint8_t * mvit_slot_input_u8(mvit_model * m, int n, int h, int w, int slot, int src_h, int src_w) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    return g && src_h > 0 && src_w > 0 ? u8_staging(*g, n, src_h, src_w) : nullptr;
+}
+extern "C" int mvit_slot_submit_u8(mvit_model * m, int n, int h, int w, int slot, int src_h, int src_w) {
+    mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
+    return g && src_h > 0 && src_w > 0 ? submit_u8(*g, n, src_h, src_w, false) : 1;
+}
+extern "C" int mvit_preprocess_u8(mvit_model * m, const uint8_t * images, int n, int src_h, int src_w, int h, int w, float * out_hwc) {
+    if (!m || !images || !out_hwc || !shape_ok(n, h, w) || src_h <= 0 || src_w <= 0) return 1;
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    uint8_t * st = u8_staging(g, n, src_h, src_w);
+    if (!st) return 1;
+    memcpy(st, images, (size_t)n * src_h * src_w * 3);
+    ggml_b200_graph_prepare(g.ctx, g.gf);
+    if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, st, n, src_h, src_w)) return 1;
+    return ggml_b200_tensor_download(g.gf, g.input_hwc, out_hwc);
 }
 
 extern "C" int mvit_prepare(mvit_model * m, int n, int h, int w) {

@@ -62,6 +62,9 @@ struct forward_graph {
     ggml_tensor *  input_hwc = nullptr;  // ne = (3, W, H, N): the caller's HWC images, uploaded as they are
     ggml_tensor *  features  = nullptr;  // ne = (W/32, H/32, C, N)
     ggml_tensor *  pooled    = nullptr;  // ne = (1, 1, C, N)
+    ggml_tensor *  logits    = nullptr;  // ne = (classes, N); only when the weight file carries a classifier
+    uint8_t *      input_u8 = nullptr;   // pinned staging of raw u8 images (mvit_*_u8), [N][src_h][src_w][3]
+    size_t         input_u8_bytes = 0;
     void *         pinned_arena = nullptr;  // page-locked backing store of ctx (input staging + output shadows)
     std::vector<ggml_tensor *> stages;   // stem, layer_1..layer_5, conv_1x1_exp outputs (debug taps, MVIT_DEBUG_STAGES=1)
 };
@@ -71,6 +74,7 @@ struct model {  // mobilevit_model, main.cpp:202-213
     conv_layer                           conv_stem, conv_1x1_exp;
     std::vector<inverted_residual>       layer_1, layer_2;  // mobile_net_layer x2 (main.cpp:89-106)
     vit_block                            layer_3, layer_4, layer_5;
+    ggml_tensor *                        classifier_w = nullptr, * classifier_b = nullptr;  // optional head: (640,1000) kernel + bias
     ggml_context *                       ctx_w = nullptr;
     std::map<std::string, ggml_tensor *> tensors;
     int64_t                              total_weights = 0;

@@ -89,6 +89,20 @@ def lib_mobilevit() -> ctypes.CDLL:
         for name in ("mvit_slot_submit", "mvit_slot_wait"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.mvit_release.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        L.mvit_num_classes.argtypes = [ctypes.c_void_p]
+        L.mvit_classify.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, ctypes.POINTER(ctypes.c_int32)]
+        L.mvit_host_logits.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.mvit_host_logits.restype = _f32p
+        L.mvit_slot_logits.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4
+        L.mvit_slot_logits.restype = _f32p
+        L.mvit_host_input_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5
+        L.mvit_host_input_u8.restype = u8p
+        L.mvit_compute_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5
+        L.mvit_slot_input_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6
+        L.mvit_slot_input_u8.restype = u8p
+        L.mvit_slot_submit_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6
+        L.mvit_preprocess_u8.argtypes = [ctypes.c_void_p, u8p] + [ctypes.c_int] * 5 + [_f32p]
         L.mvit_plan_info.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(PlanInfo)]
         _mv = L
     return _mv
@@ -112,6 +126,7 @@ class MobileViT:
         self.out_channels = self._L.mvit_out_channels(self._h)
         self.num_tensors = self._L.mvit_num_tensors(self._h)
         self.num_weights = self._L.mvit_num_weights(self._h)
+        self.num_classes = self._L.mvit_num_classes(self._h)  # 0: the file has no classifier head
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -133,6 +148,51 @@ class MobileViT:
         if rc != 0:
             raise ValueError(f"mvit_extract_features: invalid arguments n={n} h={h} w={w}")
         return feat, pooled
+
+    def classify(self, images_hwc: np.ndarray):
+        """images [N,H,W,3] f32 -> (logits [N,classes], top-1 ids [N]); needs a weight file with a classifier head."""
+        imgs = np.ascontiguousarray(images_hwc, dtype=np.float32)
+        n, h, w, _ = imgs.shape
+        logits = np.empty((n, max(self.num_classes, 1)), dtype=np.float32)
+        top1 = np.empty(n, dtype=np.int32)
+        rc = self._L.mvit_classify(self._h, imgs.ctypes.data_as(_f32p), n, h, w, logits.ctypes.data_as(_f32p),
+                                   top1.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        if rc != 0:
+            raise ValueError("mvit_classify: " + ("weight file has no classifier" if rc == 2 else "invalid arguments"))
+        return logits, top1
+
+    def host_logits(self, n, h, w) -> np.ndarray:
+        return np.ctypeslib.as_array(self._L.mvit_host_logits(self._h, n, h, w), shape=(n, self.num_classes))
+
+    def slot_logits(self, n, h, w, slot) -> np.ndarray:
+        return np.ctypeslib.as_array(self._L.mvit_slot_logits(self._h, n, h, w, slot), shape=(n, self.num_classes))
+
+    # ---- u8 images, preprocessing on the device (sam_image_preprocess, main.cpp:538-601) ----
+    def preprocess_u8(self, images_u8: np.ndarray, h: int, w: int) -> np.ndarray:
+        imgs = np.ascontiguousarray(images_u8, dtype=np.uint8)
+        n, sh, sw, _ = imgs.shape
+        out = np.empty((n, h, w, 3), dtype=np.float32)
+        if self._L.mvit_preprocess_u8(self._h, imgs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), n, sh, sw, h, w, out.ctypes.data_as(_f32p)) != 0:
+            raise ValueError("mvit_preprocess_u8: invalid arguments")
+        return out
+
+    def host_input_u8(self, n, h, w, src_h, src_w) -> np.ndarray:
+        return np.ctypeslib.as_array(self._L.mvit_host_input_u8(self._h, n, h, w, src_h, src_w), shape=(n, src_h, src_w, 3))
+
+    def compute_u8(self, n, h, w, src_h, src_w):
+        if self._L.mvit_compute_u8(self._h, n, h, w, src_h, src_w) != 0:
+            raise ValueError("mvit_compute_u8: invalid arguments")
+        c = self.out_channels
+        f = np.ctypeslib.as_array(self._L.mvit_host_features(self._h, n, h, w), shape=(n, c, h // 32, w // 32))
+        p = np.ctypeslib.as_array(self._L.mvit_host_pooled(self._h, n, h, w), shape=(n, c))
+        return f, p
+
+    def slot_input_u8(self, n, h, w, slot, src_h, src_w) -> np.ndarray:
+        return np.ctypeslib.as_array(self._L.mvit_slot_input_u8(self._h, n, h, w, slot, src_h, src_w), shape=(n, src_h, src_w, 3))
+
+    def slot_submit_u8(self, n, h, w, slot, src_h, src_w) -> None:
+        if self._L.mvit_slot_submit_u8(self._h, n, h, w, slot, src_h, src_w) != 0:
+            raise ValueError("mvit_slot_submit_u8: invalid arguments")
 
     # ---- zero-copy host interface: write the pinned input buffer in place, compute, read the outputs ----
     def host_input(self, n, h, w) -> np.ndarray:

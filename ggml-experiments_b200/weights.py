@@ -65,8 +65,13 @@ def _ln(rng, out, path, c):
     out[f"{path}/beta:0"] = rng.normal(0.0, 0.1, (c,)).astype(np.float32)
 
 
-def make_synthetic_weights(variant: str = "s", seed: int = 1234) -> "OrderedDict[str, np.ndarray]":
-    """Random-init MobileViT weights under the reference's tensor names (313 tensors for every variant)."""
+CLASSIFIER = "tf_mobile_vi_t_for_image_classification/classifier"  # TFMobileViTForImageClassification's head variables
+
+
+def make_synthetic_weights(variant: str = "s", seed: int = 1234, num_classes: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Random-init MobileViT weights under the reference's tensor names (313 tensors for every variant).
+    num_classes > 0 appends the classification head (`classifier/kernel:0` (C, classes), `classifier/bias:0`),
+    drawn after everything else so the 313 backbone tensors do not depend on it."""
     cfg = VARIANTS[variant]
     neck, hidden, expand = cfg["neck"], cfg["hidden"], cfg["expand"]
     rng = np.random.default_rng(seed)
@@ -99,6 +104,8 @@ def make_synthetic_weights(variant: str = "s", seed: int = 1234) -> "OrderedDict
         _conv(rng, out, f"{base}/conv_projection", 1, 1, d, cout)
         _conv(rng, out, f"{base}/fusion", 3, 3, 2 * cout, cout)
     _conv(rng, out, f"{P}/conv_1x1_exp", 1, 1, neck[5], neck[6])
+    if num_classes > 0:
+        _dense(rng, out, CLASSIFIER, neck[6], num_classes)
     return out
 
 
@@ -148,6 +155,9 @@ def to_hf_state_dict(tensors: "OrderedDict[str, np.ndarray]") -> dict:
     """Map file tensors to torch MobileViTModel state-dict entries (numpy arrays)."""
     sd = {}
     for name, arr in tensors.items():
+        if name.startswith(CLASSIFIER + "/"):  # MobileViTForImageClassification.classifier (kept outside the `mobilevit.` prefix)
+            sd["classifier." + ("weight" if name.endswith("kernel:0") else "bias")] = np.ascontiguousarray(arr.T) if arr.ndim == 2 else arr
+            continue
         assert name.startswith(P + "/") and name.endswith(":0")
         parts = name[len(P) + 1:-2].split("/")
         leaf = parts[-1]

@@ -254,6 +254,13 @@ void ggml_b200_graph_wait(struct ggml_cgraph * cgraph);
  * the new state back into the input leaf).  Register before the first compute. */
 void ggml_b200_graph_add_feedback(struct ggml_cgraph * cgraph, struct ggml_tensor * src, struct ggml_tensor * dst);
 
+/* Image preprocessing on the device (sam_image_preprocess + the HWC copy, main.cpp:538-601,627-634): enqueue on
+ * the graph's stream the H2D copy of `n` raw u8 images [src_h][src_w][3] and the bilinear resize / u8 rounding / 1/255 kernel
+ * that fills the device copy of the f32 input leaf `input` (ne = (3, W, H, n)).  Call ggml_b200_graph_prepare first and run
+ * the compute with uploads disabled (ggml_b200_graph_set_transfers(g, false, ...)).  Returns 0 on success. */
+int ggml_b200_graph_upload_u8_images(struct ggml_cgraph * cgraph, struct ggml_tensor * input, const uint8_t * host_u8, int n, int src_h,
+                                     int src_w);
+
 /* Synchronous device->host copy of any (contiguous) tensor of the graph's plan, e.g. an intermediate that is not a
  * declared output.  Returns 0 on success. */
 int ggml_b200_tensor_download(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor, void * host_dst);

@@ -57,6 +57,27 @@ int           mvit_slot_wait(mvit_model * m, int n, int h, int w, int slot);
 const float * mvit_slot_features(mvit_model * m, int n, int h, int w, int slot);
 const float * mvit_slot_pooled(mvit_model * m, int n, int h, int w, int slot);
 
+/* ---- classification head.  The reference stops at the feature map (main.cpp:645); when the weight file also
+ * carries `.../classifier/kernel:0` (C, classes) and `.../classifier/bias:0` (TFMobileViTForImageClassification naming, kernel
+ * stored (in, out) like every dense kernel of the file) the graph ends in logits = pooled . kernel + bias. ---- */
+int           mvit_num_classes(const mvit_model * m);                  /* 0: the file has no classifier */
+/* logits: N*classes floats (may be NULL); top1: N class ids (may be NULL).  Returns 0, 1 (bad arguments) or 2 (no classifier). */
+int           mvit_classify(mvit_model * m, const float * images_hwc, int n, int h, int w, float * logits, int32_t * top1);
+const float * mvit_host_logits(mvit_model * m, int n, int h, int w);  /* [N,classes] after mvit_compute; NULL without a classifier */
+const float * mvit_slot_logits(mvit_model * m, int n, int h, int w, int slot);
+
+/* ---- uint8 images with the preprocessing on the device.  Replaces sam_image_preprocess (main.cpp:538-601) + the
+ * HWC copy (main.cpp:627-634): every source image [src_h][src_w][3] u8 is resized so that its longer side fills the H x W
+ * input (bilinear, the reference's arithmetic and rounding to u8), divided by 255 and written top-left into the zeroed f32
+ * input; rows use stride W (the reference writes stride nx3, which shears non-square images: SURVEY App. C #3).
+ * 4x fewer bytes cross PCIe than with f32 images. ---- */
+uint8_t * mvit_host_input_u8(mvit_model * m, int n, int h, int w, int src_h, int src_w);   /* pinned [N,src_h,src_w,3], fill in place */
+int       mvit_compute_u8(mvit_model * m, int n, int h, int w, int src_h, int src_w);      /* H2D(u8) + preprocess + forward + D2H */
+uint8_t * mvit_slot_input_u8(mvit_model * m, int n, int h, int w, int slot, int src_h, int src_w);
+int       mvit_slot_submit_u8(mvit_model * m, int n, int h, int w, int slot, int src_h, int src_w);
+/* preprocessing alone (parity tests): images -> out_hwc [N,H,W,3] f32 on the host.  Returns 0 on success. */
+int       mvit_preprocess_u8(mvit_model * m, const uint8_t * images, int n, int src_h, int src_w, int h, int w, float * out_hwc);
+
 /* ---- device-resident variant (bench.py `value`): inputs/outputs stay in HBM -------------------------- */
 int    mvit_prepare(mvit_model * m, int n, int h, int w);           /* build graph + device plan; 0 on success */
 void * mvit_device_input(mvit_model * m, int n, int h, int w);      /* device ptr, [N,H,W,3] f32 */

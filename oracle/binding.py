@@ -54,6 +54,9 @@ def lib():
         L.mvo_layernorm.argtypes = [_f32p, ctypes.c_int, ctypes.c_size_t, _f32p, _f32p, ctypes.c_float, _f32p]
         L.mvo_softmax_rows.argtypes = [_f32p, ctypes.c_int, ctypes.c_size_t]
         L.mvo_max_threads.restype = ctypes.c_int
+        L.mvo_num_classes.argtypes = [ctypes.c_void_p]
+        L.mvo_classify.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, _f32p]
+        L.mvo_preprocess_u8.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
         _lib = L
     return _lib
 
@@ -92,6 +95,19 @@ class OracleModel:
             return feat, pooled, secs
         return feat, pooled
 
+    @property
+    def num_classes(self) -> int:
+        return lib().mvo_num_classes(self._h)
+
+    def classify(self, pooled: np.ndarray) -> np.ndarray:
+        """Classifier head on pooled features [N,C] -> logits [N,classes]."""
+        pooled = np.ascontiguousarray(pooled, dtype=np.float32)
+        logits = np.empty((pooled.shape[0], self.num_classes), dtype=np.float32)
+        rc = lib().mvo_classify(self._h, _p(pooled), pooled.shape[0], _p(logits))
+        if rc:
+            raise ValueError("weight file has no classifier")
+        return logits
+
     def forward_stages(self, img_hwc: np.ndarray, stage_shapes, flags: int = 0):
         """One image; returns the 7 stage outputs (stem, layer1..5, exp) as CHW arrays."""
         img = np.ascontiguousarray(img_hwc, dtype=np.float32)
@@ -100,3 +116,13 @@ class OracleModel:
         arr = (_f32p * 7)(*[_p(b) for b in bufs])
         lib().mvo_forward(self._h, _p(img), h, w, None, None, flags, arr)
         return bufs
+
+
+def preprocess_u8(images: np.ndarray, h: int, w: int) -> np.ndarray:
+    """sam_image_preprocess (main.cpp:538-601) per image: [N,src_h,src_w,3] u8 -> [N,h,w,3] f32 (stride-W fix, App. C #3)."""
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    n, sh, sw, _ = images.shape
+    out = np.empty((n, h, w, 3), dtype=np.float32)
+    for i in range(n):
+        lib().mvo_preprocess_u8(images[i].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), sh, sw, h, w, _p(out[i]))
+    return out

@@ -496,6 +496,60 @@ static void linear(const float *x, size_t T, int Cin, const mvo_tensor *kernel, 
         for (int o = 0; o < Cout; o++) y[t * Cout + o] = y[t * Cout + o] + bias->data[o];
 }
 
+/* ---- classifier head (not in main.cpp, which stops at the feature map :645): TFMobileViTForImageClassification's
+ * `classifier/{kernel,bias}:0`, kernel (in, out) like every dense kernel of the file; logits = pooled . kernel + bias. ---- */
+static const mvo_tensor *find_suffix(const mvo_model *m, const char *suffix) {
+    const size_t ls = strlen(suffix);
+    for (int i = 0; i < m->n_tensors; i++) {
+        const size_t ln = strlen(m->t[i].name);
+        if (ln >= ls && strcmp(m->t[i].name + ln - ls, suffix) == 0) return &m->t[i];
+    }
+    return NULL;
+}
+int mvo_num_classes(void *model) {
+    const mvo_tensor *k = find_suffix((mvo_model *)model, "classifier/kernel:0");
+    return k ? k->dims[1] : 0;
+}
+int mvo_classify(void *model, const float *pooled, int N, float *logits) {
+    const mvo_model *m = (mvo_model *)model;
+    const mvo_tensor *k = find_suffix(m, "classifier/kernel:0"), *b = find_suffix(m, "classifier/bias:0");
+    if (!k || !b) return 2;
+    linear(pooled, (size_t)N, k->dims[0], k, b, logits);
+    return 0;
+}
+
+/* ---- sam_image_preprocess (main.cpp:538-601) for an H x W target: longer side fills the target, bilinear on the u8 source,
+ * rounded back to u8, then (v - 0) / 255.  Deliberate deviation: rows are written with stride W, not nx3,
+ * and the area outside the resized image is zero.  fp-contract is off so that no mul+add pair becomes an fma: the reference
+ * Makefile builds without -mfma, and the CUDA kernel uses explicit _rn intrinsics -> bit-identical results. ---- */
+__attribute__((optimize("fp-contract=off")))
+void mvo_preprocess_u8(const uint8_t *img, int ny, int nx, int H, int W, float *out) {
+    const float scale = H == W ? (float)(nx > ny ? nx : ny) * 1.0f / (float)W                      /* main.cpp:550 */
+                               : fmaxf((float)nx / (float)W, (float)ny / (float)H);
+    int nx3 = (int)(nx / scale + 0.5f), ny3 = (int)(ny / scale + 0.5f);                              /* :554-555 */
+    if (nx3 > W) nx3 = W;
+    if (ny3 > H) ny3 = H;
+    memset(out, 0, (size_t)H * W * 3 * sizeof(float));
+    for (int y = 0; y < ny3; y++)
+        for (int x = 0; x < nx3; x++)
+            for (int c = 0; c < 3; c++) {
+                const float sx = (x + 0.5f) * scale - 0.5f, sy = (y + 0.5f) * scale - 0.5f;          /* :566-567 */
+                int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+                if (x0 < 0) x0 = 0;
+                if (y0 < 0) y0 = 0;
+                if (x0 > nx - 1) x0 = nx - 1;
+                if (y0 > ny - 1) y0 = ny - 1;
+                const int x1 = x0 + 1 < nx - 1 ? x0 + 1 : nx - 1, y1 = y0 + 1 < ny - 1 ? y0 + 1 : ny - 1; /* :572-573 */
+                const float dx = sx - x0, dy = sy - y0;
+                const float v00 = img[3 * (y0 * nx + x0) + c], v01 = img[3 * (y0 * nx + x1) + c];
+                const float v10 = img[3 * (y1 * nx + x0) + c], v11 = img[3 * (y1 * nx + x1) + c];
+                const float v0 = v00 * (1.0f - dx) + v01 * dx, v1 = v10 * (1.0f - dx) + v11 * dx;    /* :588-589 */
+                const float v  = v0 * (1.0f - dy) + v1 * dy;
+                const uint8_t v2 = (uint8_t)fminf(fmaxf(roundf(v), 0.0f), 255.0f);                   /* :593 */
+                out[3 * ((size_t)y * W + x) + c] = ((float)v2 - 0.0f) / 255.0f;                       /* :596, stride W */
+            }
+}
+
 /* softmax over ne0: [ggml] ggml_compute_forward_soft_max_f32 -- max, expf, sum in double, scale 1/sum */
 void mvo_softmax_rows(float *x, int n, size_t rows) {
     for (size_t r = 0; r < rows; r++) {

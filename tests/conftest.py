@@ -22,6 +22,10 @@ def weight_files(tmp_path_factory):
         p = str(d / f"weight_{v}.ggml")
         W.write_weight_file(p, W.make_synthetic_weights(v, seed=1234))
         out[v] = p
+    # XXS with the optional 1000-class head; the 313 backbone tensors are identical to out["xxs"]
+    p = str(d / "weight_xxs_cls.ggml")
+    W.write_weight_file(p, W.make_synthetic_weights("xxs", seed=1234, num_classes=1000))
+    out["xxs_cls"] = p
     return out
 
 

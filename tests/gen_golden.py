@@ -35,6 +35,22 @@ def hf_forward(variant, tensors, imgs_hwc):
     return feat, pooled, hidden
 
 
+def hf_classify(variant, tensors, imgs_hwc, num_classes):
+    """HF MobileViTForImageClassification: backbone + global pool + Linear head."""
+    from transformers import MobileViTConfig, MobileViTForImageClassification
+    cfg = MobileViTConfig(image_size=imgs_hwc.shape[1], num_labels=num_classes, **W.hf_config_kwargs(variant))
+    model = MobileViTForImageClassification(cfg).eval()
+    sd = {}
+    for k, v in W.to_hf_state_dict(tensors).items():
+        sd[k if k.startswith("classifier.") else "mobilevit." + k] = torch.from_numpy(v)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    missing = [m for m in missing if "num_batches_tracked" not in m]
+    assert not missing and not unexpected, (missing, unexpected)
+    x = torch.from_numpy(imgs_hwc).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        return model(x).logits.numpy()
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     torch.manual_seed(0)
@@ -55,6 +71,13 @@ def main():
             stage_shapes=np.array([list(h.shape) for h in hidden]),
         )
         print(name, feat.shape, "pooled range", pooled.min(), pooled.max(), "n_hidden", len(hidden))
+    # classification head: XXS + 1000 classes
+    tensors = W.make_synthetic_weights("xxs", seed=1234, num_classes=1000)
+    imgs = W.synthetic_images(2, 256, 256, seed=7)
+    logits = hf_classify("xxs", tensors, imgs, 1000)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hf_cls_xxs_256.npz"), variant="xxs", seed=1234, img_seed=7, n_img=2, hw=256,
+                        num_classes=1000, logits=logits.astype(np.float32))
+    print("hf_cls_xxs_256.npz", logits.shape, "logit range", logits.min(), logits.max(), "top1", logits.argmax(-1))
 
 
 if __name__ == "__main__":

@@ -58,6 +58,19 @@ def test_loader_reads_reference_layout(weight_files):
         G.MobileViT("/nonexistent/weight.ggml")
 
 
+def test_loader_reads_optional_classifier(weight_files):
+    """a file with `classifier/{kernel,bias}:0` gets a head; the reference's 313-tensor file does not."""
+    import ggml_experiments_b200 as G
+    m = G.MobileViT(weight_files["xxs_cls"])
+    assert (m.num_tensors, m.num_classes, m.out_channels) == (315, 1000, 320)
+    m.close()
+    m = G.MobileViT(weight_files["xxs"])
+    assert m.num_classes == 0
+    with pytest.raises(ValueError, match="no classifier"):
+        m.classify(np.zeros((1, 64, 64, 3), np.float32))
+    m.close()
+
+
 def test_extract_features_rejects_bad_shapes(weight_files):
     import ggml_experiments_b200 as G
     m = G.MobileViT(weight_files["xxs"])

@@ -303,3 +303,66 @@ def test_batched_gru_fast_mode_tensor_cores(G, tmp_path):
     assert same.sum() > B // 2
     err = np.abs(state[same] - ref_state[same]).max()
     assert err < 2e-2, err
+
+
+# ---- classifier head --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode_name", ["fast", "exact"])
+def test_classifier_head_matches_oracle_and_hf(G, oracle, weight_files, mode_name):
+    import os
+    from ggml_experiments_b200 import mobilevit as MV
+    mode = MV.FAST if mode_name == "fast" else MV.EXACT
+    imgs = W.synthetic_images(2, 256, 256, seed=7)
+    om = oracle.OracleModel(weight_files["xxs_cls"])
+    _, ref_p = om.forward(imgs)
+    ref_logits = om.classify(ref_p)
+    MV.set_mode(mode)
+    m = G.MobileViT(weight_files["xxs_cls"])
+    try:
+        logits, top1 = m.classify(imgs)
+        info = m.plan_info(2, 256, 256)
+        feat, pooled = m.extract_features(imgs)
+        # the head itself is f32-exact: applied by the oracle to OUR pooled features it must reproduce our logits
+        own = om.classify(pooled)
+        assert np.abs(own - logits).max() < 1e-4 * np.abs(own).max()
+    finally:
+        m.close()
+        MV.set_mode(MV.FAST)
+    assert info["mode"] == mode, info  # the fused planner must cover the graph with the head attached
+    assert np.abs(logits - ref_logits).max() < 1e-2 * np.abs(ref_logits).max()
+    assert (top1 == ref_logits.argmax(1)).all()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hf_cls_xxs_256.npz"))
+    assert (top1 == g["logits"].argmax(1)).all()
+
+
+# ---- u8 images, preprocessing on the device ---------------------------------------------------------------
+@pytest.mark.parametrize("sh,sw,hw", [(256, 256, 256), (300, 400, 256), (480, 270, 256), (100, 80, 256), (720, 1280, 256), (333, 333, 128)])
+def test_device_preprocess_u8_is_bit_identical_to_the_oracle(G, oracle, weight_files, sh, sw, hw):
+    img = np.random.default_rng(sh + 3 * sw).integers(0, 256, (3, sh, sw, 3), dtype=np.uint8)
+    m = G.MobileViT(weight_files["xxs"])
+    try:
+        got = m.preprocess_u8(img, hw, hw)
+    finally:
+        m.close()
+    np.testing.assert_array_equal(got, oracle.preprocess_u8(img, hw, hw))
+
+
+def test_compute_u8_equals_f32_path_on_preprocessed_images(G, oracle, weight_files):
+    """H2D(u8) + device preprocess + forward == forward on the oracle-preprocessed f32 images, bit for bit; also pipelined."""
+    n, hw, sh, sw = 4, 256, 360, 480
+    img = np.random.default_rng(11).integers(0, 256, (n, sh, sw, 3), dtype=np.uint8)
+    pre = oracle.preprocess_u8(img, hw, hw)
+    m = G.MobileViT(weight_files["xs"])
+    try:
+        f_ref, p_ref = m.extract_features(pre)
+        m.host_input_u8(n, hw, hw, sh, sw)[:] = img
+        f, p = m.compute_u8(n, hw, hw, sh, sw)
+        np.testing.assert_array_equal(p, p_ref)
+        np.testing.assert_array_equal(f, f_ref)
+        for s in range(2):
+            m.slot_input_u8(n, hw, hw, s, sh, sw)[:] = img
+            m.slot_submit_u8(n, hw, hw, s, sh, sw)
+        for s in range(2):
+            fs, ps = m.slot_wait(n, hw, hw, s)
+            np.testing.assert_array_equal(ps, p_ref)
+    finally:
+        m.close()

@@ -120,3 +120,56 @@ def test_oracle_layernorm_softmax(oracle):
     L.mvo_softmax_rows(s.ctypes.data_as(f32p), 24, 7)
     e = np.exp(xd - xd.max(1, keepdims=True))
     assert np.abs(s - e / e.sum(1, keepdims=True)).max() < 1e-6
+
+
+# ---- classifier head ---------------------------------------------------------------------------------------
+def test_oracle_classifier_matches_hf_golden(oracle, weight_files):
+    """HF MobileViTForImageClassification (backbone + pool + Linear) pins the head: kernel (in,out) layout and bias."""
+    g = np.load(os.path.join(GOLD, "hf_cls_xxs_256.npz"))
+    m = oracle.OracleModel(weight_files["xxs_cls"])
+    assert (m.num_tensors, m.num_classes) == (315, 1000)
+    imgs = W.synthetic_images(2, 256, 256, seed=7)
+    _, pooled = m.forward(imgs, oracle.PURE_F32)
+    logits = m.classify(pooled)
+    assert np.abs(logits - g["logits"]).max() < 2e-4 * np.abs(g["logits"]).max()
+    assert (logits.argmax(1) == g["logits"].argmax(1)).all()
+    # a file without the head has no classes
+    assert oracle.OracleModel(weight_files["xxs"]).num_classes == 0
+
+
+# ---- SURVEY 8f.2: sam_image_preprocess ----------------------------------------------------------------------------------
+def preprocess_numpy(img, H, W_):
+    """Independent numpy-f32 restatement of main.cpp:538-601 (stride-W variant): every op is a separate f32 operation."""
+    f = np.float32
+    ny, nx, _ = img.shape
+    scale = f(max(nx, ny)) * f(1.0) / f(W_) if H == W_ else max(f(nx) / f(W_), f(ny) / f(H))
+    nx3, ny3 = min(int(f(nx) / scale + f(0.5)), W_), min(int(f(ny) / scale + f(0.5)), H)
+    sx = (np.arange(nx3, dtype=f) + f(0.5)) * scale - f(0.5)
+    sy = (np.arange(ny3, dtype=f) + f(0.5)) * scale - f(0.5)
+    x0 = np.clip(np.floor(sx).astype(np.int64), 0, nx - 1)
+    y0 = np.clip(np.floor(sy).astype(np.int64), 0, ny - 1)
+    x1, y1 = np.minimum(x0 + 1, nx - 1), np.minimum(y0 + 1, ny - 1)
+    dx = (sx - x0.astype(f))[None, :, None]
+    dy = (sy - y0.astype(f))[:, None, None]
+    src = img.astype(f)
+    v0 = src[y0][:, x0] * (f(1.0) - dx) + src[y0][:, x1] * dx
+    v1 = src[y1][:, x0] * (f(1.0) - dx) + src[y1][:, x1] * dx
+    v = v0 * (f(1.0) - dy) + v1 * dy
+    q = np.clip(np.sign(v) * np.floor(np.abs(v) + f(0.5)), 0, 255).astype(np.uint8)  # std::round: half away from zero
+    out = np.zeros((H, W_, 3), f)
+    out[:ny3, :nx3] = q.astype(f) / f(255.0)
+    return out
+
+
+@pytest.mark.parametrize("sh,sw,H,W_", [(256, 256, 256, 256), (300, 400, 256, 256), (400, 300, 256, 256), (100, 80, 256, 256),
+                                        (1080, 1920, 256, 256), (7, 5, 64, 64), (512, 512, 256, 256), (300, 500, 128, 256)])
+def test_oracle_preprocess_u8_is_the_reference_arithmetic(oracle, sh, sw, H, W_):
+    img = np.random.default_rng(sh * 7 + sw).integers(0, 256, (2, sh, sw, 3), dtype=np.uint8)
+    got = oracle.preprocess_u8(img, H, W_)
+    for i in range(2):
+        np.testing.assert_array_equal(got[i], preprocess_numpy(img[i], H, W_))
+    if (sh, sw) == (H, W_):  # scale 1: the identity resize, exactly u8 / 255
+        np.testing.assert_array_equal(got, img.astype(np.float32) / np.float32(255))
+    if sh > sw and H == W_:  # portrait: the right part of the target stays zero, rows keep stride W (App. C #3)
+        nx3 = int(np.float32(sw) / (np.float32(sh) / np.float32(W_)) + np.float32(0.5))
+        assert (got[:, :, nx3:] == 0).all() and got[:, :, :nx3].max() > 0
