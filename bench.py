@@ -256,6 +256,35 @@ def main():
     h2d = n * h * w * 3 * 4
     d2h = int(f.nbytes + p.nbytes)
 
+    # Same pipeline fed with uint8 images: the resize / 1/255 of sam_image_preprocess (main.cpp:538-601) runs on
+    # the device, 4x fewer bytes cross PCIe.  Reported next to the f32 headline, not instead of it.
+    img_u8 = np.random.default_rng(3).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    for s in range(2):
+        model.slot_input_u8(n, h, w, s, h, w)[:] = img_u8
+        model.slot_submit_u8(n, h, w, s, h, w)
+    for s in range(2):
+        model.slot_wait(n, h, w, s)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        s = i & 1
+        if i >= 2:
+            model.slot_wait(n, h, w, s)
+        model.slot_submit_u8(n, h, w, s, h, w)
+    for s in range(2):
+        model.slot_wait(n, h, w, s)
+    u8_s = max_over_ranks(time.perf_counter() - t0)
+    model.host_input_u8(n, h, w, h, w)[:] = img_u8
+    model.compute_u8(n, h, w, h, w)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.compute_u8(n, h, w, h, w)
+    u8_sync_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_u8 = {"value": args.batch * world * args.steps / u8_s, "unit": "images/s", "h2d_bytes_per_step": int(img_u8.nbytes),
+              "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * u8_s / args.steps, "synchronous_call_ms": 1e3 * u8_sync_s / args.steps,
+              "api": "mvit_slot_submit_u8 (device-side sam_image_preprocess), 2 slots in flight"}
+
     # ---- per-kernel roofline (rank 0) -----------------------------------------------------------------------
     peaks = load_peaks()
     roofline, kernels = None, []
@@ -313,7 +342,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mvit_slot_submit/mvit_slot_wait, 2 slots in flight",
                     "synchronous_call_ms": 1e3 * sync_s / args.steps,
-                    "synchronous_call_images_per_s": args.batch * world * args.steps / sync_s},
+                    "synchronous_call_images_per_s": args.batch * world * args.steps / sync_s,
+                    "u8_input": e2e_u8},
             "gpu_launches": info["launches"] * args.steps,
             "clocks": clocks,
             "roofline": roofline,
