@@ -214,7 +214,9 @@ __global__ void k_cast_f16(const float4 * __restrict__ src, uint2 * __restrict__
 
 // Fused GRU gates (rnn.cpp:231-250, Keras reset_after=True): from mx = W^T x + b0 and mh = U^T h + b1 (both [3U, B], gate
 // order z | r | h) and the previous state h [U, B]:  z = s(mx_z + mh_z), r = s(mx_r + mh_r), hh = tanh(mx_h + r * mh_h),
-// h' = z * h + (1 - z) * hh, with s(x) = silu(x) / x exactly as the reference writes its sigmoid (rnn.cpp:51-55).
+// h' = z * h + (1 - z) * hh.  s(x) is a true sigmoid here: the reference writes silu(x) / x (rnn.cpp:51-55), which is the same
+// value to ~1 ulp but NaN at x == 0 -- with 4096 streams x 200 steps that 0/0 does occur.  The per-node
+// EXACT plan keeps the literal silu/div nodes.
 __global__ void k_gru_gates(const float * __restrict__ mx, const float * __restrict__ mh, const float * __restrict__ h,
                             float * __restrict__ out, int U, int64_t total) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -223,8 +225,8 @@ __global__ void k_gru_gates(const float * __restrict__ mx, const float * __restr
         const float * px = mx + b * 3 * U + u;
         const float * ph = mh + b * 3 * U + u;
         const float az = px[0] + ph[0], ar = px[U] + ph[U];
-        const float z  = (az / (1.0f + expf(-az))) / az;
-        const float r  = (ar / (1.0f + expf(-ar))) / ar;
+        const float z  = 1.0f / (1.0f + expf(-az));
+        const float r  = 1.0f / (1.0f + expf(-ar));
         const float hh = tanhf(px[2 * U] + r * ph[2 * U]);
         out[i]         = z * h[i] + (1.0f - z) * hh;
     }

@@ -685,6 +685,17 @@ void launch_pool_mean(const __half * x16, const float * x32, int N, int HW, int 
     k_pool_mean<<<grid, 128, 0, st>>>(x16, x32, HW, C, out);
 }
 
+// small device-to-device copy as a kernel: between two CUDA-graph launches a copy-engine memcpy costs two engine hand-overs
+// (~30 us per GRU step), a kernel does not
+__global__ void k_copy_words(const uint32_t * __restrict__ src, uint32_t * __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void launch_copy_words(const void * src, void * dst, int64_t n_words, cudaStream_t st) {
+    int64_t blocks = (n_words + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    k_copy_words<<<(unsigned)blocks, 256, 0, st>>>((const uint32_t *)src, (uint32_t *)dst, n_words);
+}
+
 // ---- u8 image preprocessing -------------------------------------------------------------------------------
 // One thread per output pixel, all 3 channels.  The arithmetic is the reference's, operation for operation, with explicit
 // round-to-nearest intrinsics so that nvcc cannot contract mul+add into fma: the result is bit-identical to the CPU code.

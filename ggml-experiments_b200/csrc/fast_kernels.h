@@ -37,6 +37,7 @@ void launch_nhwc_to_nchw(const __half * x16, const float * x32, int N, int H, in
 
 // global average pool over H*W of NHWC f32/f16 -> [N][C] f32
 void launch_pool_mean(const __half * x16, const float * x32, int N, int HW, int C, float * out, cudaStream_t st);
+void launch_copy_words(const void * src, void * dst, int64_t n_words, cudaStream_t st);  // n_words 4-byte words
 // sam_image_preprocess on the device (main.cpp:538-601): n u8 images [sh][sw][3] -> f32 [n][H][W][3], longer side fills the target,
 // bilinear with the reference's arithmetic, rounded to u8, /255, zero padding, row stride W.
 void launch_preprocess_u8(const uint8_t * src, int n, int sh, int sw, float * dst, int H, int W, cudaStream_t st);

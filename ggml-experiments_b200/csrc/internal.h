@@ -121,6 +121,8 @@ struct Plan {
     bool                  upload_inputs = true, download_outputs = true;
     cudaGraphExec_t       graph_exec = nullptr;
     bool                  graph_failed = false;
+    void *                history        = nullptr;  // per-step record of ggml_b200_graph_compute_steps (grow-only)
+    size_t                history_bytes  = 0;
     void *                u8_stage       = nullptr;  // device staging of raw u8 images (ggml_b200_graph_upload_u8_images)
     size_t                u8_stage_bytes = 0;
     cudaEvent_t           compute_done   = nullptr;  // recorded after this plan's kernels on its private stream

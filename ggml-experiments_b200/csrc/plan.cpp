@@ -2,6 +2,7 @@
 //
 // Replaces upstream ggml's ggml_graph_compute (CPU thread pool + work buffer) for the reference's
 // ggml_graph_compute_with_ctx calls (main.cpp:640, rnn.cpp:158,311).
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -144,6 +145,7 @@ Plan::~Plan() {
     }
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (u8_stage) cudaFree(u8_stage);
+    if (history) cudaFree(history);
     for (void * p : owned_device) cudaFree(p);
     for (void * p : pinned) cudaHostUnregister(p);
     if (host_mirror) cudaFreeHost(host_mirror);
@@ -408,6 +410,68 @@ extern "C" void ggml_b200_graph_compute_async(struct ggml_context * ctx, struct 
     fix_graph_pointers(gf);
     Plan * plan = get_or_build_plan(ctx, gf);
     run_plan(plan, /*wait_for_results=*/false);
+}
+// Device-resident autoregressive loop: run the plan `steps` times back to back on its stream without any host
+// round trip -- the feedback copies registered with ggml_b200_graph_add_feedback carry the state from step to step -- and keep
+// `record` (e.g. the token ids chosen at each step) in a device history that is copied to the host once, at the end.
+// Inputs are uploaded for step 0 only.  host_dst receives steps * nbytes(record).  Replaces the host loop of rnn.cpp:293-313.
+extern "C" int ggml_b200_graph_compute_steps(struct ggml_context * ctx, struct ggml_cgraph * gf, int steps, struct ggml_tensor * record, void * host_dst) {
+    if (steps <= 0 || !record || !host_dst) return 1;
+    fix_graph_pointers(gf);
+    Plan * plan = get_or_build_plan(ctx, gf);
+    auto it     = plan->slots.find(record);
+    if (it == plan->slots.end() || !it->second.dptr || !ggml_is_contiguous(record)) return 1;
+    const size_t bytes = (size_t)ggml_nelements(record) * ggml_type_size(record->type);
+    cudaStream_t st    = plan->private_stream ? plan->private_stream : current_stream();
+    if (plan->history_bytes < bytes * (size_t)steps) {  // grow-only and plan-owned: cudaMalloc/cudaFree per call cost up to 100 ms
+        B200_CHECK(cudaStreamSynchronize(st));
+        if (plan->history) B200_CHECK(cudaFree(plan->history));
+        const size_t cap = bytes * (size_t)((steps + 255) / 256 * 256);  // in units of 256 steps: a short warm-up call sizes it for the real one
+        B200_CHECK(cudaMalloc(&plan->history, cap));
+        plan->history_bytes = cap;
+    }
+    char * hist = (char *)plan->history;
+    const bool up = plan->upload_inputs, down = plan->download_outputs;
+    plan->download_outputs = false;
+    // the host runs at most kAhead steps ahead of the device (keeps the launch queue short; the device never waits: a step
+    // is ~10x longer than its submission)
+    constexpr int kAhead = 8;
+    cudaEvent_t   ring[kAhead];
+    for (auto & e : ring) B200_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const bool trace = getenv("GGML_B200_STEP_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize((size_t)steps + 1);
+        for (auto & e : tev) B200_CHECK(cudaEventCreate(&e));
+        B200_CHECK(cudaEventRecord(tev[0], st));
+    }
+    for (int t = 0; t < steps; t++) {
+        if (t >= kAhead) B200_CHECK(cudaEventSynchronize(ring[t % kAhead]));
+        plan->upload_inputs = up && t == 0;
+        run_plan(plan, /*wait_for_results=*/false);
+        if (bytes % 4 == 0) launch_copy_words(it->second.dptr, hist + (size_t)t * bytes, (int64_t)(bytes / 4), st);
+        else B200_CHECK(cudaMemcpyAsync(hist + (size_t)t * bytes, it->second.dptr, bytes, cudaMemcpyDeviceToDevice, st));
+        B200_CHECK(cudaEventRecord(ring[t % kAhead], st));
+        if (trace) B200_CHECK(cudaEventRecord(tev[(size_t)t + 1], st));
+    }
+    for (auto & e : ring) cudaEventDestroy(e);
+    if (trace) {
+        B200_CHECK(cudaStreamSynchronize(st));
+        std::vector<float> ms((size_t)steps);
+        for (int t = 0; t < steps; t++) B200_CHECK(cudaEventElapsedTime(&ms[(size_t)t], tev[(size_t)t], tev[(size_t)t + 1]));
+        std::vector<float> sorted = ms;
+        std::sort(sorted.begin(), sorted.end());
+        fprintf(stderr, "step trace: median %.1f us, max %.1f us, slow steps:", sorted[(size_t)steps / 2] * 1e3, sorted.back() * 1e3);
+        for (int t = 0; t < steps; t++)
+            if (ms[(size_t)t] > 3 * sorted[(size_t)steps / 2]) fprintf(stderr, " %d:%.0f", t, ms[(size_t)t] * 1e3);
+        fprintf(stderr, "\n");
+        for (auto & e : tev) cudaEventDestroy(e);
+    }
+    B200_CHECK(cudaMemcpyAsync(host_dst, hist, bytes * (size_t)steps, cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    plan->upload_inputs    = up;
+    plan->download_outputs = down;
+    return 0;
 }
 extern "C" void ggml_b200_graph_wait(struct ggml_cgraph * gf) {
     if (!gf->plan) return;

@@ -19,6 +19,7 @@ struct cell_graph {
     ggml_context * ctx = nullptr;
     ggml_cgraph *  gf  = nullptr;
     ggml_tensor *  ids = nullptr, * states = nullptr, * next_ids = nullptr, * new_states = nullptr, * logits = nullptr;
+    void *         pinned = nullptr;  // page-locked backing store of ctx: the step-0 upload of ids + state is a plain DMA
 };
 
 }  // namespace
@@ -85,6 +86,7 @@ extern "C" void gru_free(gru_model * m) {
     for (auto & kv : m->graphs) {
         ggml_graph_release_plan(kv.second.gf);
         ggml_free(kv.second.ctx);
+        ggml_b200_host_free(kv.second.pinned);
     }
     ggml_free(m->ctx_w);
     delete m;
@@ -100,7 +102,9 @@ static cell_graph & graph_for(gru_model * m, int B) {
     if (it != m->graphs.end()) return it->second;
     cell_graph g;
     const int U = m->U;
-    ggml_init_params p = {(size_t)B * (U + m->V + 8) * 4 * 2 + (8u << 20), nullptr, false};
+    const size_t arena = (size_t)B * (U + m->V + 8) * 4 * 2 + (8u << 20);
+    g.pinned           = ggml_b200_host_malloc(arena);  // NULL without a device: ggml_init then mallocs
+    ggml_init_params p = {arena, g.pinned, false};
     g.ctx = ggml_init(p);
     ggml_context * c = g.ctx;
     g.gf     = ggml_new_graph(c);
@@ -135,16 +139,20 @@ extern "C" float gru_generate(gru_model * m, const int32_t * first_tokens, int B
     cell_graph & g = graph_for(m, B);
     memcpy(g.ids->data, first_tokens, (size_t)B * 4);
     memset(g.states->data, 0, (size_t)B * m->U * 4);
-    // step 0 uploads ids/state from the host; later steps take them from the feedback copies
+    // step 0 uploads ids/state from the host; later steps take them from the feedback copies.  The whole loop is enqueued
+    // at once (no host round trip per token); the chosen ids of every step come back in one copy at the end.
     ggml_b200_graph_prepare(g.ctx, g.gf);
-    ggml_b200_graph_set_transfers(g.gf, true, true);
-    ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
-    memcpy(out_tokens, g.next_ids->data, (size_t)B * 4);
-    ggml_b200_graph_set_transfers(g.gf, false, true);
+    ggml_b200_graph_set_transfers(g.gf, true, false);
     const int64_t t0 = ggml_time_us();
-    for (int t = 1; t < steps; t++) {
-        ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
-        memcpy(out_tokens + (size_t)t * B, g.next_ids->data, (size_t)B * 4);
+    if (getenv("GRU_B200_HOST_LOOP")) {  // the old per-step loop (one D2H + sync per token), kept for comparison
+        ggml_b200_graph_set_transfers(g.gf, true, true);
+        for (int t = 0; t < steps; t++) {
+            ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
+            memcpy(out_tokens + (size_t)t * B, g.next_ids->data, (size_t)B * 4);
+            ggml_b200_graph_set_transfers(g.gf, false, true);
+        }
+    } else if (ggml_b200_graph_compute_steps(g.ctx, g.gf, steps, g.next_ids, out_tokens) != 0) {
+        return -1.f;
     }
     const int64_t t1 = ggml_time_us();
     if (getenv("GRU_B200_PROFILE")) {  // per-launch device times of one cell step, to stderr
@@ -152,5 +160,5 @@ extern "C" float gru_generate(gru_model * m, const int32_t * first_tokens, int B
         if (ggml_b200_graph_profile_json(g.gf, 20, buf.data(), buf.size()) == 0) fprintf(stderr, "%s\n", buf.data());
     }
     if (final_state && ggml_b200_tensor_download(g.gf, g.new_states, final_state) != 0) return -1.f;
-    return steps > 1 ? (float)(t1 - t0) / 1000.f * (float)steps / (float)(steps - 1) : 0.f;
+    return (float)(t1 - t0) / 1000.f;
 }

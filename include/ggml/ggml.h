@@ -254,6 +254,12 @@ void ggml_b200_graph_wait(struct ggml_cgraph * cgraph);
  * the new state back into the input leaf).  Register before the first compute. */
 void ggml_b200_graph_add_feedback(struct ggml_cgraph * cgraph, struct ggml_tensor * src, struct ggml_tensor * dst);
 
+/* Device-resident autoregressive loop (the host loop of rnn.cpp:293-313): run the graph `steps` times back to back
+ * without a host round trip (the registered feedback copies carry ids/state between steps; inputs are uploaded for step 0
+ * only), keep `record` of every step in a device history and copy it to host_dst (steps * nbytes(record)) once at the end.
+ * Returns 0 on success. */
+int ggml_b200_graph_compute_steps(struct ggml_context * ctx, struct ggml_cgraph * cgraph, int steps, struct ggml_tensor * record, void * host_dst);
+
 /* Image preprocessing on the device (sam_image_preprocess + the HWC copy, main.cpp:538-601,627-634): enqueue on
  * the graph's stream the H2D copy of `n` raw u8 images [src_h][src_w][3] and the bilinear resize / u8 rounding / 1/255 kernel
  * that fills the device copy of the f32 input leaf `input` (ne = (3, W, H, n)).  Call ggml_b200_graph_prepare first and run
