@@ -180,6 +180,60 @@ def to_hf_state_dict(tensors: "OrderedDict[str, np.ndarray]") -> dict:
     return sd
 
 
+def from_hf_state_dict(sd: dict) -> "OrderedDict[str, np.ndarray]":
+    """torch-HF MobileViT state dict -> file tensors: the exporter that replaces the TensorFlow-only
+    convert-tf-to-ggml.py (convert.py:7-33 needs TF and a hub download).  Accepts MobileViTModel keys and
+    MobileViTForImageClassification keys (`mobilevit.` prefix + `classifier.*`); values are numpy arrays or torch tensors.
+    Inverse of to_hf_state_dict: conv (OC,IC,KH,KW) -> (KH,KW,IC,OC); Linear (out,in) -> (in,out); BN / LN names as App. B."""
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    bn = {"weight": "gamma", "bias": "beta", "running_mean": "moving_mean", "running_var": "moving_variance"}
+    for key, val in sd.items():
+        arr = np.asarray(val.detach().cpu().numpy() if hasattr(val, "detach") else val, dtype=np.float32)
+        if key.endswith("num_batches_tracked"):
+            continue
+        if key.startswith("mobilevit."):
+            key = key[len("mobilevit."):]
+        parts = key.split(".")
+        leaf = parts[-1]
+        if parts[0] == "classifier":
+            out[f"{CLASSIFIER}/{'kernel' if leaf == 'weight' else 'bias'}:0"] = np.ascontiguousarray(arr.T) if arr.ndim == 2 else arr
+            continue
+        # HF module path "encoder.layer.2.transformer.layer.0" -> file path "encoder/layer.2/transformer/layer.0"
+        path, i = [], 0
+        mods = parts[:-1]
+        while i < len(mods):
+            if mods[i] == "layer" and i + 1 < len(mods) and mods[i + 1].isdigit():
+                path.append(f"layer.{mods[i + 1]}")
+                i += 2
+            else:
+                path.append(mods[i])
+                i += 1
+        base = P + "/" + "/".join(path)
+        if path[-1] == "convolution":
+            out[f"{base}/kernel:0"] = np.ascontiguousarray(arr.transpose(2, 3, 1, 0))
+        elif path[-1] == "normalization":
+            out[f"{base}/{bn[leaf]}:0"] = arr
+        elif path[-1].startswith("layernorm"):
+            out[f"{base}/{'gamma' if leaf == 'weight' else 'beta'}:0"] = arr
+        elif leaf == "weight":
+            out[f"{base}/kernel:0"] = np.ascontiguousarray(arr.T)
+        elif leaf == "bias":
+            out[f"{base}/bias:0"] = arr
+        else:
+            raise KeyError(key)
+    return out
+
+
+def export_hf_checkpoint(model_dir: str, out_path: str) -> int:
+    """Write `weight.ggml` from a local Hugging Face MobileViT checkpoint directory (no network).  Returns the float count."""
+    from transformers import AutoModelForImageClassification, MobileViTModel  # imported lazily: tooling, not the product path
+    try:
+        model = AutoModelForImageClassification.from_pretrained(model_dir, local_files_only=True)
+    except Exception:
+        model = MobileViTModel.from_pretrained(model_dir, local_files_only=True)
+    return write_weight_file(out_path, from_hf_state_dict(model.state_dict()))
+
+
 def synthetic_images(n: int, h: int = 256, w: int = 256, seed: int = 7) -> np.ndarray:
     """image 0 = the reference's own test pattern (main.cpp:680-688); the rest are
     structured (per-channel offset + sinusoid + 0.15 U(0,1) noise, clamped to [0,1]).  Returns [n,h,w,3] f32."""
@@ -197,3 +251,20 @@ def synthetic_images(n: int, h: int = 256, w: int = 256, seed: int = 7) -> np.nd
             img = off + amp * np.sin(fx * xx + fy * yy + ph) + 0.15 * rng.uniform(0, 1, (h, w))
             imgs[i, :, :, c] = np.clip(img, 0.0, 1.0)
     return imgs
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="weight.ggml tooling (layout of mobilevit/convert-tf-to-ggml.py:16-33)")
+    ap.add_argument("--hf", help="local Hugging Face MobileViT checkpoint directory to export")
+    ap.add_argument("--synthetic", choices=sorted(VARIANTS), help="write random-init weights of this variant instead")
+    ap.add_argument("--classes", type=int, default=0, help="with --synthetic: add a classifier head with this many classes")
+    ap.add_argument("--out", default="weight.ggml")
+    a = ap.parse_args()
+    if a.hf:
+        n = export_hf_checkpoint(a.hf, a.out)
+    elif a.synthetic:
+        n = write_weight_file(a.out, make_synthetic_weights(a.synthetic, num_classes=a.classes))
+    else:
+        ap.error("give --hf DIR or --synthetic VARIANT")
+    print(f"{a.out}: {n} floats")
