@@ -171,6 +171,12 @@ void destroy_plans_of(ggml_context * ctx) {
     auto range = g_plans.equal_range(ctx);
     for (auto it = range.first; it != range.second; ++it) delete it->second;
     g_plans.erase(range.first, range.second);
+    // registrations keyed by objects of this arena die with it: a later context may get the same addresses (a pinned
+    // mem_buffer usually does), and a stale feedback pair would then point at unrelated tensors
+    const char * lo = ctx->mem_buffer, * hi = ctx->mem_buffer + ctx->mem_size;
+    auto inside = [&](const void * p) { return (const char *)p >= lo && (const char *)p < hi; };
+    for (auto it = g_feedback.begin(); it != g_feedback.end();) it = inside(it->first) ? g_feedback.erase(it) : std::next(it);
+    for (auto it = g_external.begin(); it != g_external.end();) it = inside(it->first) ? g_external.erase(it) : std::next(it);
 }
 
 // Assign device memory to leafs; shared by both plan builders.
