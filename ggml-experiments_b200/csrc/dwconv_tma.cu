@@ -53,12 +53,26 @@ __device__ __forceinline__ float dw_silu(float x) {
     return fmaf(h, t, h);
 }
 
+// acc[0..7] += x[0..7] * w[0..7] for 8 packed halves each: 8 FHFMA, operands taken from the packed registers (.H0 / .H1)
+__device__ __forceinline__ void dw_fhfma8(float (&acc)[8], const uint4 & x, const uint4 & w) {
+#define DW_FHFMA2(A0, A1, X, W)                                                                                                         \
+    asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\tfma.rn.f32.f16 %0, xl, wl, %0;\n\t"     \
+        "fma.rn.f32.f16 %1, xh, wh, %1;\n\t}"                                                                                       \
+        : "+f"(A0), "+f"(A1)                                                                                                          \
+        : "r"(X), "r"(W))
+    DW_FHFMA2(acc[0], acc[1], x.x, w.x);
+    DW_FHFMA2(acc[2], acc[3], x.y, w.y);
+    DW_FHFMA2(acc[4], acc[5], x.z, w.z);
+    DW_FHFMA2(acc[6], acc[7], x.w, w.w);
+#undef DW_FHFMA2
+}
+
 struct alignas(16) H8 {
     __half2 h[4];
 };
 
 template <int STRIDE>
-__global__ void __launch_bounds__(256) k_dwconv_tma(const __grid_constant__ CUtensorMap map_x, const DwLaunch::Params p) {
+__global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ CUtensorMap map_x, const DwLaunch::Params p) {
     extern __shared__ __align__(128) unsigned char dw_smem[];
     __shared__ __align__(8) uint64_t full_bar[2];
     const uint32_t box_bytes = (uint32_t)p.box_w * p.box_h * 128u;
@@ -102,17 +116,14 @@ __global__ void __launch_bounds__(256) k_dwconv_tma(const __grid_constant__ CUte
         const int ox = tx * p.TW + xl;
         const bool lane_ok = c0 < p.C && ox < p.OW;
 
-        float w[9][8], sc[8], sh[8];
+        // Weights stay packed f16 (36 registers instead of 72 f32) and every tap is one FHFMA (fma.rn.f32.f16: f16 x f16
+        // product, exact in f32, added to the f32 accumulator with one rounding) -- bit-identical to converting both
+        // operands and using FFMA, at half the instructions.
+        uint4 w[9];
+        float sc[8], sh[8];
         if (lane_ok) {
 #pragma unroll
-            for (int k = 0; k < 9; k++) {
-                const H8 v = *reinterpret_cast<const H8 *>(p.Wt + (size_t)k * p.C + c0);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float2 f = __half22float2(v.h[j]);
-                    w[k][2 * j] = f.x; w[k][2 * j + 1] = f.y;
-                }
-            }
+            for (int k = 0; k < 9; k++) w[k] = *reinterpret_cast<const uint4 *>(p.Wt + (size_t)k * p.C + c0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 sc[j] = p.scale ? p.scale[c0 + j] : 1.f;
@@ -122,25 +133,22 @@ __global__ void __launch_bounds__(256) k_dwconv_tma(const __grid_constant__ CUte
         dw_mbar_wait(dw_smem_u32(&full_bar[buf]), (it >> 1) & 1u);
         if (lane_ok) {
             const unsigned char * tile_smem = dw_smem + (size_t)buf * box_bytes + cg * 16;
-            for (int r = 0; r < rows_per; r++) {
-                const int oyl = rs * rows_per + r;
-                const int oy  = ty * p.TH + oyl;
-                if (oy >= p.OH) break;
+            const int             oyl0      = rs * rows_per;
+            auto load_row = [&](uint4 (&dst)[3], int in_row) {
+#pragma unroll
+                for (int kw = 0; kw < 3; kw++)
+                    dst[kw] = *reinterpret_cast<const uint4 *>(tile_smem + ((size_t)in_row * p.box_w + (xl * STRIDE + kw)) * 128);
+            };
+            auto emit = [&](const uint4 (&r0)[3], const uint4 (&r1)[3], const uint4 (&r2)[3], int oyl) {
                 float acc[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc[j] = 0.f;
 #pragma unroll
-                for (int kh = 0; kh < 3; kh++)
+                for (int kw = 0; kw < 3; kw++) dw_fhfma8(acc, r0[kw], w[kw]);
 #pragma unroll
-                    for (int kw = 0; kw < 3; kw++) {
-                        const H8 v = *reinterpret_cast<const H8 *>(tile_smem + ((size_t)(oyl * STRIDE + kh) * p.box_w + (xl * STRIDE + kw)) * 128);
+                for (int kw = 0; kw < 3; kw++) dw_fhfma8(acc, r1[kw], w[3 + kw]);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float2 f = __half22float2(v.h[j]);
-                            acc[2 * j]     = fmaf(f.x, w[kh * 3 + kw][2 * j], acc[2 * j]);
-                            acc[2 * j + 1] = fmaf(f.y, w[kh * 3 + kw][2 * j + 1], acc[2 * j + 1]);
-                        }
-                    }
+                for (int kw = 0; kw < 3; kw++) dw_fhfma8(acc, r2[kw], w[6 + kw]);
                 H8 o;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -149,7 +157,47 @@ __global__ void __launch_bounds__(256) k_dwconv_tma(const __grid_constant__ CUte
                     if (p.act) { y0 = dw_silu(y0); y1 = dw_silu(y1); }
                     o.h[j] = __floats2half2_rn(y0, y1);
                 }
+                const int oy = ty * p.TH + oyl;
                 *reinterpret_cast<H8 *>(p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.C + c0) = o;
+            };
+            int rows = p.OH - (ty * p.TH + oyl0);  // output rows of this thread that exist
+            if (rows > rows_per) rows = rows_per;
+            if (STRIDE == 1) {
+                // sliding 3-row window in registers: each output row loads only its new bottom row (3 LDS.128 instead of 9)
+                uint4 ra[3], rb[3], rc[3];
+                if (rows > 0) {
+                    load_row(ra, oyl0);
+                    load_row(rb, oyl0 + 1);
+                }
+                for (int r = 0; r < rows; r += 3) {
+                    load_row(rc, oyl0 + r + 2);
+                    emit(ra, rb, rc, oyl0 + r);
+                    if (r + 1 < rows) {
+                        load_row(ra, oyl0 + r + 3);
+                        emit(rb, rc, ra, oyl0 + r + 1);
+                    }
+                    if (r + 2 < rows) {
+                        load_row(rb, oyl0 + r + 4);
+                        emit(rc, ra, rb, oyl0 + r + 2);
+                    }
+                }
+            } else {
+                // stride 2: consecutive outputs share one input row (2r+2 is the next output's top row)
+                uint4 ra[3], rb[3], rc[3];
+                if (rows > 0) load_row(ra, oyl0 * 2);
+                for (int r = 0; r < rows; r += 2) {
+                    load_row(rb, (oyl0 + r) * 2 + 1);
+                    load_row(rc, (oyl0 + r) * 2 + 2);
+                    emit(ra, rb, rc, oyl0 + r);
+                    if (r + 1 < rows) {
+                        load_row(ra, (oyl0 + r) * 2 + 3);
+                        load_row(rb, (oyl0 + r) * 2 + 4);
+                        emit(rc, ra, rb, oyl0 + r + 1);
+                        // the window for the next pair starts at rb
+#pragma unroll
+                        for (int kw = 0; kw < 3; kw++) ra[kw] = rb[kw];
+                    }
+                }
             }
         }
         __syncthreads();  // every thread is done with buffer `buf`: it may be refilled by the issue of the next iteration
