@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     uint64_t *      tmem_empty  = bars + 2 * kMaxStage + 2;  // [2]
     uint64_t *      res_full    = bars + 2 * kMaxStage + 4;  // [2] residual slab landed (per epilogue group)
     uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 6);
-    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 7);
+    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 8);  // 16-byte aligned: read back with LDS.128
     float *         s_shift     = s_scale + 256;
     // epilogue staging (per epilogue warp group): 128 rows x 128 B tiles in the TMA 128B-swizzle layout
     uint8_t *       stage_base  = smem + (size_t)p.stages * stage_bytes + kCtrlBytes;
@@ -403,10 +403,16 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     for (int g = 0; g < 4; g++) {
                         const int n = n0 + c0 + g * 8;
                         float y[8];
+                        {   // per-column scale/shift: 4 broadcast LDS.128 per 8 columns (scalar loads were 2 LDS per element)
+                            const uint32_t sa = smem_u32(s_scale + c0 + g * 8), sb = smem_u32(s_shift + c0 + g * 8);
+                            const float4 s0 = ld_shared_f4(sa), s1 = ld_shared_f4(sa + 16), h0 = ld_shared_f4(sb), h1 = ld_shared_f4(sb + 16);
+                            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float tt = fmaf(v[g * 8 + j], s_scale[c0 + g * 8 + j], s_shift[c0 + g * 8 + j]);
-                            y[j]     = ep.act ? silu_f(tt) : tt;
+                            for (int j = 0; j < 8; j++) {
+                                float tt = fmaf(v[g * 8 + j], sc[j], sh[j]);
+                                y[j]     = ep.act ? silu_f(tt) : tt;
+                            }
                         }
                         if (ep.res32) {
                             if (!res_ready) {
