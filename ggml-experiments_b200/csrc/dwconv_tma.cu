@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
     };
 
     uint32_t it = 0;
+    uint4    w[9];
+    float    sc[8], sh[8];
+    int      cb_loaded = -1;
     if (threadIdx.x == 0 && (int)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
         const int buf  = it & 1;
@@ -119,9 +122,9 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
         // Weights stay packed f16 (36 registers instead of 72 f32) and every tap is one FHFMA (fma.rn.f32.f16: f16 x f16
         // product, exact in f32, added to the f32 accumulator with one rounding) -- bit-identical to converting both
         // operands and using FFMA, at half the instructions.
-        uint4 w[9];
-        float sc[8], sh[8];
-        if (lane_ok) {
+        // (declared outside the tile loop: they only change with the channel block, i.e. every tiles_x * tiles_y tiles)
+        if (lane_ok && cb != cb_loaded) {
+            cb_loaded = cb;
 #pragma unroll
             for (int k = 0; k < 9; k++) w[k] = *reinterpret_cast<const uint4 *>(p.Wt + (size_t)k * p.C + c0);
 #pragma unroll

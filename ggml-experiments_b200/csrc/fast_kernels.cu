@@ -120,10 +120,124 @@ __global__ void __launch_bounds__(256) k_stem(const float * __restrict__ x, int6
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K2 on tensor cores.  The stem is a GEMM [pixels x 27] . [27 x OC]; on CUDA cores it needs 27*OC FMAs per pixel and ran at
+// 1.06 TB/s (issue-bound).  Here K is laid out as k' = kh*10 + (kw*3+ic) (9 taps + 1 zero-weight pad per input row, 30 -> 32),
+// so every even/odd K pair is one aligned 32-bit word of the f16-staged input patch: an A fragment of mma.m16n8k16 is 8 LDS.32,
+// no im2col buffer, no shuffles.  Block = 16 x 32 output pixels, warp = 4 m-tiles of 16 consecutive pixels.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int OC>
+__global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W,
+                                                  const __half * __restrict__ Wt, const float * __restrict__ scale, const float * __restrict__ shift,
+                                                  int act, __half * __restrict__ out16, int tiles_x, int tiles_y) {
+    constexpr int TH = 16, TW = 32, IH = 2 * TH + 1, IW = 2 * TW + 1, RS = 200, NT = OC / 8;  // RS: halves per staged row (195 used)
+    __shared__ __align__(16) __half s_in[(IH + 1) * RS + 8];  // +1 row: the zero-weight K pad (k' = 30, 31) reads input row 2*py + 3
+    __shared__ __align__(16) __half s_out[8][16 * OC];
+    __shared__ float ss[OC], sh[OC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < OC; i += blockDim.x) {
+        ss[i] = scale ? scale[i] : 1.f;
+        sh[i] = shift ? shift[i] : 0.f;
+    }
+    // B fragments (weights), constant per thread: bfrag[j][s][h] holds W[oc = 8j+g][k' = 16s + 2t + 8h, +1]
+    uint32_t bfrag[NT][2][2];
+    int      koff[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int kp = 2 * t + 8 * q;
+        koff[q]      = (kp / 10) * RS + (kp % 10);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            __half2 w2;
+            __half  wv[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int kp = 2 * t + 8 * q + e, kh = kp / 10, jj = kp % 10;
+                wv[e]        = (kh < 3 && jj < 9) ? Wt[(8 * j + g) * 27 + kh * 9 + jj] : __float2half_rn(0.f);  // Wt is [oc][kh][kw][ic]
+            }
+            w2                     = __halves2half2(wv[0], wv[1]);
+            bfrag[j][q >> 1][q & 1] = *reinterpret_cast<uint32_t *>(&w2);
+        }
+    const int OH = H / 2, OW = W / 2;
+    int       b  = blockIdx.x;
+    const int tx0 = (b % tiles_x) * TW; b /= tiles_x;
+    const int ty0 = (b % tiles_y) * TH;
+    const int n   = b / tiles_y;
+    const int iy0 = 2 * ty0 - 1, ix0 = 2 * tx0 - 1;
+    const float * xn = x + n * sn;
+    // stage the (2*TH+2) x (2*TW+1) x 3 patch as f16 (ggml's im2col rounding point); warp = row, lanes = (x, c) pairs
+    for (int yy = warp; yy < IH + 1; yy += 8) {
+        const int  iy     = iy0 + yy;
+        const bool row_ok = iy >= 0 && iy < H && yy < IH;
+        for (int i = lane; i < RS; i += 32) {
+            const int xx = i / 3, c = i - 3 * xx, ix = ix0 + xx;
+            float     v  = 0.f;
+            if (row_ok && xx < IW && ix >= 0 && ix < W) v = xn[iy * sy + ix * sx + c * sc];
+            s_in[yy * RS + i] = __float2half_rn(v);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+        const int py = 2 * warp + (mt >> 1), x0 = (mt & 1) * 16;
+        const __half * base = s_in + (2 * py) * RS + 6 * (x0 + g);
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; s2++) {
+            uint32_t a[4];
+            a[0] = *reinterpret_cast<const uint32_t *>(base + koff[2 * s2]);
+            a[1] = *reinterpret_cast<const uint32_t *>(base + 48 + koff[2 * s2]);
+            a[2] = *reinterpret_cast<const uint32_t *>(base + koff[2 * s2 + 1]);
+            a[3] = *reinterpret_cast<const uint32_t *>(base + 48 + koff[2 * s2 + 1]);
+#pragma unroll
+            for (int j = 0; j < NT; j++) mma_16816(acc[j], a, bfrag[j][s2]);
+        }
+        // BN + SiLU, pack, stage the warp's 16 x OC tile so that it leaves as 16-byte coalesced stores
+        __half * so = s_out[warp];
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            const int   oc = 8 * j + 2 * t;
+            const float s0 = ss[oc], s1 = ss[oc + 1], h0 = sh[oc], h1 = sh[oc + 1];
+            float y0 = fmaf(acc[j][0], s0, h0), y1 = fmaf(acc[j][1], s1, h1), y2 = fmaf(acc[j][2], s0, h0), y3 = fmaf(acc[j][3], s1, h1);
+            if (act) { y0 = silu_fast(y0); y1 = silu_fast(y1); y2 = silu_fast(y2); y3 = silu_fast(y3); }
+            *reinterpret_cast<__half2 *>(so + g * OC + oc)       = __floats2half2_rn(y0, y1);
+            *reinterpret_cast<__half2 *>(so + (g + 8) * OC + oc) = __floats2half2_rn(y2, y3);
+        }
+        __syncwarp();
+        const int oy = ty0 + py;
+        for (int ch = lane; ch < 2 * OC; ch += 32) {  // 16 * OC halves = 2 * OC chunks of 8
+            const int pix = (ch * 8) / OC, ox = tx0 + x0 + pix;
+            if (oy < OH && ox < OW)
+                *reinterpret_cast<uint4 *>(out16 + (((int64_t)n * OH + oy) * OW + ox) * OC + (ch * 8) % OC) = *reinterpret_cast<const uint4 *>(so + ch * 8);
+        }
+        __syncwarp();
+    }
+}
+
 void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W, const __half * Wt, int OC,
                  const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st) {
     const int tiles_x = (W / 2 + 31) / 32, tiles_y = (H / 2 + 15) / 16;
     const int grid    = N * tiles_x * tiles_y;
+    static const bool v1 = getenv("GGML_B200_STEM_V1") != nullptr;
+    if (!out32 && out16 && !v1) {
+        switch (OC) {
+            case 8: k_stem_mma<8><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 16: k_stem_mma<16><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 24: k_stem_mma<24><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 32: k_stem_mma<32><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            default: break;
+        }
+    }
     switch (OC) {
         case 8: k_stem<8><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32, tiles_x, tiles_y); break;
         case 16: k_stem<16><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, out32, tiles_x, tiles_y); break;

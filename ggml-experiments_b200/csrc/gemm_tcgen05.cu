@@ -380,9 +380,15 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
             for (int cc = 0; cc < p.block_n; cc += 64) {
                 if (n0 + cc >= p.N) break;  // group-uniform
-                // the previous slab of this group must have been read out by the TMA before it is overwritten
-                if (leader) tma_store_wait_read();
-                named_bar_sync(1 + group, 128);
+                // the previous slab must have been read out by the TMA before it is overwritten.  Without a residual slab
+                // every warp owns its 32 rows end to end (stage, fence, store): no group barrier, four independent store streams
+                if (p.ep_warp) {
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                } else {
+                    if (leader) tma_store_wait_read();
+                    named_bar_sync(1 + group, 128);
+                }
                 if (ep.res32) {
                     // the f32 residual slab(s) of this chunk land in the staging buffer and are updated in place
                     if (leader) {
@@ -457,6 +463,19 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 }
                 ri += ep.res32 ? 1u : 0u;
                 fence_proxy_async();             // generic-proxy smem writes -> visible to the TMA (async proxy)
+                if (p.ep_warp) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t woff = (uint32_t)q * 32u * 128u;
+                        if (ep.out16) tma_store_2d(&map_o16, stg16 + woff, n0 + cc, m0 + q * 32);
+                        if (ep.out32) {
+                            tma_store_2d(&map_o32, stg32 + woff, n0 + cc, m0 + q * 32);
+                            if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_2d(&map_o32, stg32 + kBlockM * 128 + woff, n0 + cc + 32, m0 + q * 32);
+                        }
+                        tma_store_commit();
+                    }
+                    continue;
+                }
                 named_bar_sync(1 + group, 128);
                 if (leader) {
                     if (ep.out16) tma_store_2d(&map_o16, stg16, n0 + cc, m0);
@@ -472,7 +491,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
         }
-        if (leader) tma_store_wait_all();  // all bulk stores of this group have been written before the CTA exits
+        if (p.ep_warp ? lane == 0 : leader) tma_store_wait_all();  // all bulk stores have been written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -584,16 +603,18 @@ static void make_output_maps(GemmLaunch & L) {
         const uint32_t box[2]  = {32, (uint32_t)kBlockM};
         make_map(&L.map_r32, ep.res32, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     }
+    L.p.ep_warp = (!ep.res32 && getenv("GGML_B200_GEMM_GROUP_EPILOGUE") == nullptr) ? 1 : 0;
+    const uint32_t box_rows = L.p.ep_warp ? 32u : (uint32_t)kBlockM;
     if (ep.out16) {
         const uint64_t dims[2] = {(uint64_t)L.p.N, (uint64_t)L.p.M};
         const uint64_t str[1]  = {(uint64_t)ep.ld16 * 2};
-        const uint32_t box[2]  = {64, (uint32_t)kBlockM};
+        const uint32_t box[2]  = {64, box_rows};
         make_map(&L.map_o16, ep.out16, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     }
     if (ep.out32) {
         const uint64_t dims[2] = {(uint64_t)L.p.N, (uint64_t)L.p.M};
         const uint64_t str[1]  = {(uint64_t)ep.ld32 * 4};
-        const uint32_t box[2]  = {32, (uint32_t)kBlockM};
+        const uint32_t box[2]  = {32, box_rows};
         make_map(&L.map_o32, ep.out32, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     }
 }

@@ -37,6 +37,7 @@ struct GemmLaunch {
         int a_cp_async;             // 1: A tile loaded by the producer warp with cp.async (K = 16 / 32: TMA rows would be 32-64 B)
         const __half * a_ptr;       // cp.async mode: A base pointer and leading dimension
         int lda;
+        int ep_warp;                // 1: every epilogue warp stages and TMA-stores its own 32 rows (no residual slab to share)
         int conv;                   // 0: plain GEMM, 1: 3x3 stride-1 pad-1 implicit GEMM over NHWC
         int H, W, rows_per_tile;    // conv: image rows covered by one 128-pixel tile (0 if a tile spans whole images)
         int cblk0, cblk1, C0, C1;   // conv: 64-channel blocks / channels of source 0 and source 1 (concat fusion)

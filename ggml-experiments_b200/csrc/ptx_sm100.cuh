@@ -34,24 +34,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok;
 }
 // Bounded wait: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU.
-// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires) instead
-// of returning at once -- a spinning producer / MMA warp otherwise steals issue slots from the epilogue warps of its
-// sub-partition (ISETP + BRA + CS2R of the old spin loop were 30 % of all instructions executed by the GEMM).
-__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(ns)
-        : "memory");
-    return ok;
-}
+// Bounded wait with back-off.  A bare try_wait loop returns every ~40 ns (a suspend-time hint does not lengthen that on this
+// part): the spinning producer / MMA-issuer warps executed 28 % of all instructions of the GEMM and took issue slots from
+// the epilogue warps of their sub-partitions.  nanosleep between polls parks the warp instead; GGML_B200_WAIT_NS is compiled in.
+#ifndef GGML_B200_WAIT_NS
+#define GGML_B200_WAIT_NS 64
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(GGML_B200_WAIT_NS);
         if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must surface as a CUDA error, never as a hung GPU
     }
 }
