@@ -91,3 +91,50 @@ extern "C" float ggml_b200_debug_gemm_time(int M, int N, int K, int act, int wan
             L.p.n_tiles, L.p.stages, L.ctas_per_sm, L.grid.x, L.grid.y, L.smem_bytes, 1e3f * ms / reps);
     return ms / reps;
 }
+
+// ---- instruction-rate probe (tests/bw_probe.py): FFMA vs FHFMA (fma.rn.f32.f16) vs HFMA2 issue rate, 8 independent chains ----
+template <int MODE>
+__global__ void k_fma_rate(float * out, int iters, uint32_t xa, uint32_t xb) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = (float)(threadIdx.x + j);
+    float    fa = __uint_as_float(xa), fb = __uint_as_float(xb);
+    uint32_t ha = xa, hb = xb;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (MODE == 0) acc[j] = fmaf(acc[j], fa, fb);
+            if (MODE == 1) asm volatile("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tfma.rn.f32.f16 %0, l, h, %0;\n\t}" : "+f"(acc[j]) : "r"(ha + (uint32_t)j));
+            if (MODE == 2) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(reinterpret_cast<uint32_t &>(acc[j])) : "r"(ha), "r"(hb));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += acc[j];
+    if (s == 12345.678f) out[0] = s;
+}
+extern "C" float ggml_b200_debug_fma_rate(int mode, int iters) {
+    b200::ensure_device();
+    float * d = nullptr;
+    cudaMalloc(&d, 4);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = 148 * 8, block = 256;
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0);
+        if (mode == 0) k_fma_rate<0><<<grid, block>>>(d, iters, 0x3f7fff00u, 0x3a000000u);
+        if (mode == 1) k_fma_rate<1><<<grid, block>>>(d, iters, 0x3c003c00u, 0u);
+        if (mode == 2) k_fma_rate<2><<<grid, block>>>(d, iters, 0x3bff3bffu, 0x10001000u);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaFree(d);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // warp-instructions per clock per SM at 1.965 GHz
+    const double instr = (double)grid * (block / 32) * (double)iters * 8.0;
+    return (float)(instr / (ms * 1e-3) / 148.0 / 1.965e9);
+}

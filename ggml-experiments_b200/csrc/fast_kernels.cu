@@ -177,11 +177,16 @@ __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, 
     for (int yy = warp; yy < IH + 1; yy += 8) {
         const int  iy     = iy0 + yy;
         const bool row_ok = iy >= 0 && iy < H && yy < IH;
-        for (int i = lane; i < RS; i += 32) {
-            const int xx = i / 3, c = i - 3 * xx, ix = ix0 + xx;
-            float     v  = 0.f;
-            if (row_ok && xx < IW && ix >= 0 && ix < W) v = xn[iy * sy + ix * sx + c * sc];
-            s_in[yy * RS + i] = __float2half_rn(v);
+        float      v[7];  // all loads of a row are in flight before the first convert/store (the rolled loop exposed one global latency per element)
+#pragma unroll
+        for (int u = 0; u < 7; u++) {
+            const int i = lane + 32 * u, xx = i / 3, c = i - 3 * xx, ix = ix0 + xx;
+            v[u]        = (row_ok && xx < IW && ix >= 0 && ix < W) ? __ldg(xn + iy * sy + ix * sx + c * sc) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 7; u++) {
+            const int i = lane + 32 * u;
+            if (i < RS) s_in[yy * RS + i] = __float2half_rn(v[u]);
         }
     }
     __syncthreads();
