@@ -484,6 +484,94 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // one MUFU; exp2f() adds a range check and two fix-up multiplies per call
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One block of up to 64 keys for a warp's 16 queries: S = Q K^T, online softmax, O += P V.  NTC = 8 compiles the full
+// block without predicates (every sequence length of the model except L = 16); NTC = 0 takes the tile count at run time.
+template <int DP, int NTC>
+__device__ __forceinline__ void attn_block(const uint32_t (&qf)[DP / 16][4], float (&o)[DP / 8][4], float (&m)[2], float (&l)[2], uint32_t kaddr,
+                                           uint32_t vaddr, float sl2, int ntile_rt) {
+    constexpr int LDS = DP + 8, KS = DP / 16, DT = DP / 8;
+    const int ntile = NTC ? NTC : ntile_rt;
+    float     s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+        for (int np = 0; np < 4; np++) {
+            if (np * 2 < ntile) {
+                uint32_t b[4];
+                ldsm_x4(b, kaddr + (uint32_t)((np * 16 * LDS + ks * 16) * 2));
+                mma_16816(s[np * 2], qf[ks], b[0], b[1]);
+                mma_16816(s[np * 2 + 1], qf[ks], b[2], b[3]);
+            }
+        }
+    }
+    // ---- online softmax (rows g and g+8 of this warp's 16 queries) ----
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < ntile) {
+            mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
+        }
+    float mb[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float mn   = fmaxf(m[r], mx[r]);
+        const float corr = ex2_approx((m[r] - mn) * sl2);
+        m[r]             = mn;
+        mb[r]            = mn * sl2;
+        l[r] *= corr;
+#pragma unroll
+        for (int i = 0; i < DT; i++) {
+            o[i][2 * r] *= corr;
+            o[i][2 * r + 1] *= corr;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i < ntile) {
+            s[i][0] = ex2_approx(fmaf(s[i][0], sl2, -mb[0]));
+            s[i][1] = ex2_approx(fmaf(s[i][1], sl2, -mb[0]));
+            s[i][2] = ex2_approx(fmaf(s[i][2], sl2, -mb[1]));
+            s[i][3] = ex2_approx(fmaf(s[i][3], sl2, -mb[1]));
+            l[0] += s[i][0] + s[i][1];
+            l[1] += s[i][2] + s[i][3];
+        }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        if (kk * 2 < ntile) {
+            uint32_t a[4];
+            a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+            a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+            a[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            a[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int dp = 0; dp < DT / 2; dp++) {
+                uint32_t b[4];
+                ldsm_x4_trans(b, vaddr + (uint32_t)((kk * 16 * LDS + dp * 16) * 2));
+                mma_16816(o[dp * 2], a, b[0], b[1]);
+                mma_16816(o[dp * 2 + 1], a, b[2], b[3]);
+            }
+        }
+    }
+}
+
 constexpr int kAttnQB = 128;  // queries per CTA (8 warps x 16)
 constexpr int kAttnLK = 256;  // keys staged in shared memory at a time
 
@@ -541,78 +629,13 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) ldmatrix_x4(qf[ks], sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
         }
+        // per-lane ldmatrix base addresses in the shared window (one cvta per chunk instead of one per ldmatrix)
+        const uint32_t kaddr0 = (uint32_t)__cvta_generic_to_shared(sK + (((lane >> 4) * 8 + (lane & 7)) * LDS + ((lane >> 3) & 1) * 8));
+        const uint32_t vaddr0 = (uint32_t)__cvta_generic_to_shared(sV + ((((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + (lane >> 4) * 8));
         for (int kb = 0; kb < nk; kb += 64) {
-            const int ntile = min(64, nk - kb) >> 3;  // 8-key tiles in this block (multiple of 2)
-            float     s[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; i++) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < KS; ks++) {
-#pragma unroll
-                for (int np = 0; np < 4; np++) {
-                    if (np * 2 < ntile) {
-                        uint32_t b[4];
-                        ldmatrix_x4(b, sK + (kb + (np * 2 + (lane >> 4)) * 8 + (lane & 7)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
-                        mma_16816(s[np * 2], qf[ks], b[0], b[1]);
-                        mma_16816(s[np * 2 + 1], qf[ks], b[2], b[3]);
-                    }
-                }
-            }
-            // ---- online softmax (rows g and g+8 of this warp's 16 queries) ----
-            float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i < ntile) {
-                    mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
-                    mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
-                }
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            }
-            float corr[2], mb[2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const float mn = fmaxf(m[r], mx[r]);
-                corr[r]        = exp2f((m[r] - mn) * sl2);
-                m[r]           = mn;
-                mb[r]          = mn * sl2;
-                l[r] *= corr[r];
-            }
-#pragma unroll
-            for (int i = 0; i < DT; i++) {
-                o[i][0] *= corr[0]; o[i][1] *= corr[0];
-                o[i][2] *= corr[1]; o[i][3] *= corr[1];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i < ntile) {
-                    s[i][0] = exp2f(fmaf(s[i][0], sl2, -mb[0]));
-                    s[i][1] = exp2f(fmaf(s[i][1], sl2, -mb[0]));
-                    s[i][2] = exp2f(fmaf(s[i][2], sl2, -mb[1]));
-                    s[i][3] = exp2f(fmaf(s[i][3], sl2, -mb[1]));
-                    l[0] += s[i][0] + s[i][1];
-                    l[1] += s[i][2] + s[i][3];
-                }
-            // ---- O += P V ----
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                if (kk * 2 < ntile) {
-                    uint32_t a[4];
-                    a[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
-                    a[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
-                    a[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-                    a[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-                    for (int dp = 0; dp < DT / 2; dp++) {
-                        uint32_t b[4];
-                        ldmatrix_x4_trans(b, sV + (kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + (dp * 2 + (lane >> 4)) * 8);
-                        mma_16816(o[dp * 2], a, b[0], b[1]);
-                        mma_16816(o[dp * 2 + 1], a, b[2], b[3]);
-                    }
-                }
-            }
+            const uint32_t kaddr = kaddr0 + (uint32_t)(kb * LDS * 2), vaddr = vaddr0 + (uint32_t)(kb * LDS * 2);
+            if (nk - kb >= 64) attn_block<DP, 8>(qf, o, m, l, kaddr, vaddr, sl2, 8);
+            else attn_block<DP, 0>(qf, o, m, l, kaddr, vaddr, sl2, (nk - kb) >> 3);
         }
     }
     if (!warp_active) return;
