@@ -35,6 +35,9 @@ struct FVal {  // an activation in pixel-major NHWC order: [N*H*W, C]
     int     N = 0, H = 0, W = 0, C = 0;
     FNode * prod = nullptr;
     bool    need16 = false, need32 = false;
+    bool    need_stats = false;  // producer GEMM also writes per-row (sum, sum of squares): a LayerNorm of this value was folded into its consumers
+    float * pstats = nullptr;
+    int64_t off_stats = -1;
     __half * p16 = nullptr;
     float *  p32 = nullptr;
     int64_t  off16 = -1, off32 = -1;
@@ -70,7 +73,10 @@ struct FNode {
     bool  fused_into_reduce = false;  // depthwise node executed inside the following reduce conv's kernel (K4a)
     int   order = -1;
     // folded constants (offsets into the plan's constant pool)
-    int64_t c_w = -1, c_scale = -1, c_shift = -1;
+    int64_t c_w = -1, c_scale = -1, c_shift = -1, c_c1 = -1;
+    // LayerNorm folded into this GEMM (consumer side): gamma / beta of the LN that preceded it
+    const ggml_tensor *ln_g = nullptr, *ln_b = nullptr;
+    float ln_eps = 0.f;
     std::string name;
 };
 
@@ -447,8 +453,12 @@ struct Planner {
     }
 
     // ---- constant folding (host) ---------------------------------------------------------------------------
-    void fold_bn(FNode * n, int OC) {
+    void fold_bn(FNode * n, int OC, const std::vector<float> * pre = nullptr) {
         std::vector<float> scale(OC, 1.f), shift(OC, 0.f);
+        if (!n->has_bn && pre) {  // folded LayerNorm without BN: shift = sum_k beta_k W[n][k]
+            n->c_shift = pool.add(pre->data(), OC * 4);
+            return;
+        }
         if (n->has_bn) {
             const float *mean = (const float *)n->bn.mean->data, *var = (const float *)n->bn.var->data;
             const float *gamma = (const float *)n->bn.gamma->data, *beta = (const float *)n->bn.beta->data;
@@ -458,6 +468,7 @@ struct Planner {
                 const double sc = (double)gamma[i] / sd;
                 scale[i]        = (float)sc;
                 shift[i]        = (float)((double)beta[i] - (double)mean[i] * sc);
+                if (pre) shift[i] = (float)((double)shift[i] + sc * (double)(*pre)[i]);  // BN applied after the folded LayerNorm's beta term
             }
             n->c_scale = pool.add(scale.data(), OC * 4);
             n->c_shift = pool.add(shift.data(), OC * 4);
@@ -484,18 +495,56 @@ struct Planner {
                                     for (int oc = 0; oc < OC; oc++)
                                         wt[(((size_t)oc * KH + kh) * KW + kw) * IC + ic] = src[(((size_t)kh * KW + kw) * IC + ic) * OC + oc];
                     }
+                    std::vector<float> pre;
+                    if (n->ln_g) {  // 1x1 conv over LN(x): W' = f16(W * gamma), c1 = row sums of W', pre = sum_k beta_k W
+                        const float *gm = (const float *)n->ln_g->data, *bt = (const float *)n->ln_b->data;
+                        std::vector<float> c1(OC, 0.f);
+                        pre.assign(OC, 0.f);
+                        for (int oc = 0; oc < OC; oc++) {
+                            double a1 = 0.0, a2 = 0.0;
+                            for (int ic = 0; ic < IC; ic++) {
+                                const float    w  = ggml_fp16_to_fp32(wt[(size_t)oc * IC + ic]);
+                                const uint16_t wg = ggml_fp32_to_fp16(w * gm[ic]);
+                                wt[(size_t)oc * IC + ic] = wg;
+                                a1 += (double)ggml_fp16_to_fp32(wg);
+                                a2 += (double)bt[ic] * (double)w;
+                            }
+                            c1[oc]  = (float)a1;
+                            pre[oc] = (float)a2;
+                        }
+                        n->c_c1 = pool.add(c1.data(), OC * 4);
+                    }
                     n->c_w = pool.add(wt.data(), wt.size() * 2);
                     plan->n_folded += 2;
-                    fold_bn(n, OC);
+                    fold_bn(n, OC, n->ln_g ? &pre : nullptr);
                 } break;
                 case FK_LINEAR: {
                     const int OUT = (int)n->w->ne[0], IN = (int)n->w->ne[1];
                     const float * src = (const float *)n->w->data;  // file (in,out): index in*OUT + out
                     std::vector<uint16_t> wt((size_t)OUT * IN);
-                    for (int o = 0; o < OUT; o++)
-                        for (int i = 0; i < IN; i++) wt[(size_t)o * IN + i] = ggml_fp32_to_fp16(src[(size_t)i * OUT + o]);
+                    std::vector<float> shift((const float *)n->bias->data, (const float *)n->bias->data + OUT);
+                    if (n->ln_g) {
+                        const float *gm = (const float *)n->ln_g->data, *bt = (const float *)n->ln_b->data;
+                        std::vector<float> c1(OUT, 0.f);
+                        for (int o = 0; o < OUT; o++) {
+                            double a1 = 0.0, a2 = 0.0;
+                            for (int i = 0; i < IN; i++) {
+                                const float    w  = src[(size_t)i * OUT + o];
+                                const uint16_t wg = ggml_fp32_to_fp16(w * gm[i]);
+                                wt[(size_t)o * IN + i] = wg;
+                                a1 += (double)ggml_fp16_to_fp32(wg);
+                                a2 += (double)bt[i] * (double)w;
+                            }
+                            c1[o] = (float)a1;
+                            shift[o] += (float)a2;
+                        }
+                        n->c_c1 = pool.add(c1.data(), OUT * 4);
+                    } else {
+                        for (int o = 0; o < OUT; o++)
+                            for (int i = 0; i < IN; i++) wt[(size_t)o * IN + i] = ggml_fp32_to_fp16(src[(size_t)i * OUT + o]);
+                    }
                     n->c_w     = pool.add(wt.data(), wt.size() * 2);
-                    n->c_shift = pool.add(n->bias->data, OUT * 4);
+                    n->c_shift = pool.add(shift.data(), OUT * 4);
                     plan->n_folded += 4;
                 } break;
                 case FK_QKV: {
@@ -504,17 +553,32 @@ struct Planner {
                     const int C = (int)n->wq->ne[0], IN = (int)n->wq->ne[1], heads = n->heads;
                     const int d = C / heads, dp = attention_padded_head_dim(d);
                     std::vector<uint16_t> wt((size_t)3 * heads * dp * IN, 0);
-                    std::vector<float>    bias((size_t)3 * heads * dp, 0.f);
+                    std::vector<float>    bias((size_t)3 * heads * dp, 0.f), c1q((size_t)3 * heads * dp, 0.f);
                     const ggml_tensor * ws[3] = {n->wq, n->wk, n->wv};
                     const ggml_tensor * bs[3] = {n->bq, n->bk, n->bv};
                     for (int s = 0; s < 3; s++) {
                         const float * src = (const float *)ws[s]->data;
                         for (int o = 0; o < C; o++) {
                             const size_t row = ((size_t)s * heads + o / d) * dp + o % d;
-                            for (int i = 0; i < IN; i++) wt[row * IN + i] = ggml_fp32_to_fp16(src[(size_t)i * C + o]);
                             bias[row] = ((const float *)bs[s]->data)[o];
+                            if (n->ln_g) {
+                                const float *gm = (const float *)n->ln_g->data, *bt = (const float *)n->ln_b->data;
+                                double a1 = 0.0, a2 = 0.0;
+                                for (int i = 0; i < IN; i++) {
+                                    const float    w  = src[(size_t)i * C + o];
+                                    const uint16_t wg = ggml_fp32_to_fp16(w * gm[i]);
+                                    wt[row * IN + i]  = wg;
+                                    a1 += (double)ggml_fp16_to_fp32(wg);
+                                    a2 += (double)bt[i] * (double)w;
+                                }
+                                c1q[row] = (float)a1;
+                                bias[row] += (float)a2;
+                            } else {
+                                for (int i = 0; i < IN; i++) wt[row * IN + i] = ggml_fp32_to_fp16(src[(size_t)i * C + o]);
+                            }
                         }
                     }
+                    if (n->ln_g) n->c_c1 = pool.add(c1q.data(), c1q.size() * 4);
                     n->c_w     = pool.add(wt.data(), wt.size() * 2);
                     n->c_shift = pool.add(bias.data(), bias.size() * 4);
                     plan->n_folded += 12;
@@ -603,6 +667,34 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     }
     rebuild_users();
 
+    // ---- LayerNorm folding: LN(x) feeding only GEMMs disappears.  The GEMM that produces x (tile spans the row) also writes
+    // per-row (sum, sum of squares) and an f16 copy of x; each consumer multiplies raw x with gamma-scaled weights and applies
+    // r * (acc - mu * c1[n]) in its epilogue (beta folded into the shift).  Saves the LN kernels' 4+2 bytes per element. ----
+    if (!getenv("GGML_B200_NO_LN_FOLD")) {
+        for (auto & up : P.nodes) {
+            FNode * ln = up.get();
+            if (ln->kind != FK_LN || ln->dead) continue;
+            FVal *x = ln->in[0], *y = ln->out;
+            FNode * pr = x->prod;
+            if (!pr || pr->dead || !(pr->kind == FK_CONV1 || pr->kind == FK_LINEAR) || x->C > 256 || x->C % 8) continue;
+            if (out_set.count(y) || y->users.empty()) continue;
+            bool ok = true;
+            for (FNode * u : y->users)
+                if (!(u->kind == FK_QKV || u->kind == FK_LINEAR || u->kind == FK_CONV1) || u->in.size() != 1 || u->in[0] != y || u->res == y || u->ln_g) ok = false;
+            if (!ok) continue;
+            for (FNode * u : y->users) {
+                u->in[0]  = x;
+                u->ln_g   = ln->g;
+                u->ln_b   = ln->b;
+                u->ln_eps = ln->eps;
+            }
+            x->need_stats = true;
+            ln->dead      = true;
+            plan->n_folded += 6;
+        }
+        rebuild_users();
+    }
+
     // ---- topological order ----
     std::set<FNode *> seen;
     for (FVal * v : out_vals) P.topo(v->prod, seen);
@@ -661,12 +753,14 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
         if (n->kind != FK_INPUT) {
             if (o->need16) { o->off16 = ap.alloc(o->rows() * o->C * 2); plan->naive_bytes += ArenaPlanner::align_up(o->rows() * o->C * 2); }
             if (o->need32) { o->off32 = ap.alloc(o->rows() * o->C * 4); plan->naive_bytes += ArenaPlanner::align_up(o->rows() * o->C * 4); }
+            if (o->need_stats) o->off_stats = ap.alloc(o->rows() * 8);
             int last = std::max(o->last, n->order);
             if (last < n_steps) dies[last].push_back(o);
         }
         for (FVal * d : dies[n->order]) {
             if (d->off16 >= 0) ap.release(d->off16, d->rows() * d->C * 2);
             if (d->off32 >= 0) ap.release(d->off32, d->rows() * d->C * 4);
+            if (d->off_stats >= 0) ap.release(d->off_stats, d->rows() * 8);
         }
     }
     // graph outputs in ggml layout
@@ -683,6 +777,7 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     for (auto & v : P.vals) {
         if (v->off16 >= 0) v->p16 = (__half *)(plan->arena + v->off16);
         if (v->off32 >= 0) v->p32 = (float *)(plan->arena + v->off32);
+        if (v->off_stats >= 0) v->pstats = (float *)(plan->arena + v->off_stats);
     }
 
     // ---- constants ----
@@ -778,6 +873,16 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 if (n->res) { ep.res32 = n->res->p32; ep.ldr32 = n->res->C; }
                 ep.out16 = o->p16; ep.ld16 = o->C;
                 ep.out32 = o->p32; ep.ld32 = o->C;
+                if (o->need_stats) ep.stats_out = o->pstats;
+                if (n->ln_g) {
+                    if (!in->pstats) return false;
+                    ep.ln_stats = in->pstats;
+                    ep.ln_c1    = P.pool.ptr<float>(n->c_c1);
+                    ep.ln_inv_c = 1.0f / (float)in->C;
+                    ep.ln_eps   = n->ln_eps;
+                    what += " ln-folded";
+                }
+                if (o->need_stats) what += " +rowstats";
                 auto L = std::make_shared<GemmLaunch>();
                 if (!gemm_prepare(*L, in->p16, in->C, P.pool.ptr<__half>(n->c_w), in->C, (int)in->rows(), o->C, in->C, ep)) return false;
                 const char * kname = n->kind == FK_CONV1 ? "gemm_tcgen05_conv1x1" : (n->kind == FK_QKV ? "gemm_tcgen05_qkv" : "gemm_tcgen05_linear");

@@ -30,7 +30,8 @@ static constexpr int kBlockM   = 128;
 static constexpr int kBlockK   = 64;   // 64 f16 = 128 bytes = one swizzle-128B row
 static constexpr int kThreads  = 320;  // 10 warps: TMA, MMA, 2 x 4 epilogue
 static constexpr int kMaxStage = 4;
-static constexpr int kCtrlBytes = 3072;  // barriers + TMEM slot + per-column scale/shift, padded to keep 1 KiB alignment
+static constexpr int kCtrlBytes = 4096;
+enum { kEpiAct = 1, kEpiRes32 = 2, kEpiOut16 = 4, kEpiOut32 = 8, kEpiLn = 16, kEpiStats = 32, kEpiRes16 = 64 };  // barriers + TMEM slot + per-column scale/shift, padded to keep 1 KiB alignment
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -181,6 +182,9 @@ __device__ __forceinline__ float silu_f(float x) {
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
+// EPI: compile-time epilogue variant (bit mask, kEpi* below) so the per-element loops carry no run-time feature tests;
+// EPI = -1 is the generic kernel that reads the flags from the parameters.
+template <int EPI>
 __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a0,
                                                            const __grid_constant__ CUtensorMap map_a1,
                                                            const __grid_constant__ CUtensorMap map_b,
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 6);
     float *         s_scale     = (float *)(bars + 2 * kMaxStage + 8);  // 16-byte aligned: read back with LDS.128
     float *         s_shift     = s_scale + 256;
+    float *         s_c1        = s_shift + 256;  // LayerNorm folding: per-column sum of the gamma-scaled weights
     // epilogue staging (per epilogue warp group): 128 rows x 128 B tiles in the TMA 128B-swizzle layout
     uint8_t *       stage_base  = smem + (size_t)p.stages * stage_bytes + kCtrlBytes;
     const int       stg16_bytes = p.ep.out16 ? kBlockM * 128 : 0;      // 64 f16 columns per row
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const int n = n0 + i;
         s_scale[i]  = (p.ep.scale && n < p.N) ? p.ep.scale[n] : 1.0f;
         s_shift[i]  = (p.ep.shift && n < p.N) ? p.ep.shift[n] : 0.0f;
+        s_c1[i]     = (p.ep.ln_c1 && n < p.N) ? p.ep.ln_c1[n] : 0.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -365,6 +371,15 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const int      row    = q * 32 + lane;
         const bool     leader = (warp - 2) % 4 == 0 && lane == 0;
         const GemmEpilogue & ep = p.ep;
+        constexpr bool GEN  = EPI < 0;
+        const bool f_act    = GEN ? ep.act != 0 : (EPI & kEpiAct) != 0;
+        const bool f_res32  = GEN ? ep.res32 != nullptr : (EPI & kEpiRes32) != 0;
+        const bool f_res16  = GEN ? ep.res16 != nullptr : (EPI & kEpiRes16) != 0;
+        const bool f_out16  = GEN ? ep.out16 != nullptr : (EPI & kEpiOut16) != 0;
+        const bool f_out32  = GEN ? ep.out32 != nullptr : (EPI & kEpiOut32) != 0;
+        const bool f_ln     = GEN ? ep.ln_stats != nullptr : (EPI & kEpiLn) != 0;
+        const bool f_stats  = GEN ? ep.stats_out != nullptr : (EPI & kEpiStats) != 0;
+        const bool f_warp   = GEN ? p.ep_warp != 0 : !(EPI & kEpiRes32);
         const uint32_t stg16 = smem_u32(stage_base + (size_t)group * (stg16_bytes + stg32_bytes));
         const uint32_t stg32 = stg16 + (uint32_t)stg16_bytes;
         const uint32_t swz   = (uint32_t)(row & 7);
@@ -375,6 +390,15 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const int      m0  = tile * kBlockM;
             const int      m   = m0 + row;
             const uint32_t acc = group, aph = (t >> 1) & 1u;
+            // folded LayerNorm: this row's mean and 1/std from the producer's (sum, sum of squares)
+            float ln_r = 1.f, ln_mr = 0.f, st_sum = 0.f, st_sq = 0.f;
+            if (f_ln && m < p.M) {
+                const float2 st  = *reinterpret_cast<const float2 *>(ep.ln_stats + 2 * (size_t)m);
+                const float  mu  = st.x * ep.ln_inv_c;
+                const float  var = fmaxf(fmaf(st.y, ep.ln_inv_c, -mu * mu), 0.f);
+                ln_r             = rsqrtf(var + ep.ln_eps);
+                ln_mr            = -mu * ln_r;
+            }
             mbar_wait(smem_u32(&tmem_full[acc]), aph);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
@@ -382,14 +406,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 if (n0 + cc >= p.N) break;  // group-uniform
                 // the previous slab must have been read out by the TMA before it is overwritten.  Without a residual slab
                 // every warp owns its 32 rows end to end (stage, fence, store): no group barrier, four independent store streams
-                if (p.ep_warp) {
+                if (f_warp) {
                     if (lane == 0) tma_store_wait_read();
                     __syncwarp();
                 } else {
                     if (leader) tma_store_wait_read();
                     named_bar_sync(1 + group, 128);
                 }
-                if (ep.res32) {
+                if (f_res32) {
                     // the f32 residual slab(s) of this chunk land in the staging buffer and are updated in place
                     if (leader) {
                         const bool two = cc + 32 < p.block_n && n0 + cc + 32 < p.N;
@@ -398,7 +422,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         if (two) tma_load_2d(stg32 + kBlockM * 128, &map_r32, n0 + cc + 32, m0, rbar);
                     }
                 }
-                bool res_ready = !ep.res32;
+                bool res_ready = !f_res32;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
                     const int c0 = cc + half * 32;
@@ -414,13 +438,20 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                             const float4 s0 = ld_shared_f4(sa), s1 = ld_shared_f4(sa + 16), h0 = ld_shared_f4(sb), h1 = ld_shared_f4(sb + 16);
                             const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                             const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                            if (f_ln) {  // y = r * (acc - mu * c1[n]), then the usual scale / shift
+                                const uint32_t ca = smem_u32(s_c1 + c0 + g * 8);
+                                const float4   c0v = ld_shared_f4(ca), c1v = ld_shared_f4(ca + 16);
+                                const float    c1[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                                for (int j = 0; j < 8; j++) v[g * 8 + j] = fmaf(c1[j], ln_mr, v[g * 8 + j] * ln_r);
+                            }
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
                                 float tt = fmaf(v[g * 8 + j], sc[j], sh[j]);
-                                y[j]     = ep.act ? silu_f(tt) : tt;
+                                y[j]     = f_act ? silu_f(tt) : tt;
                             }
                         }
-                        if (ep.res32) {
+                        if (f_res32) {
                             if (!res_ready) {
                                 mbar_wait(rbar, ri & 1u);
                                 res_ready = true;
@@ -432,7 +463,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                             y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
                         }
                         if (m < p.M && n + 8 <= p.N) {
-                            if (ep.res16) {
+                            if (f_res16) {
                                 const uint4    rr = *reinterpret_cast<const uint4 *>(ep.res16 + (size_t)m * ep.ldr16 + n);
                                 const __half2 * h = reinterpret_cast<const __half2 *>(&rr);
 #pragma unroll
@@ -443,14 +474,21 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                                 }
                             }
                         }
-                        if (ep.out32) {  // slab `half`: row-major 32 floats = 8 x 16 B chunks, chunk index XOR (row % 8)
+                        if (f_stats) {  // row statistics of the FINAL values (columns >= N contribute exact zeros)
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                st_sum += y[j];
+                                st_sq = fmaf(y[j], y[j], st_sq);
+                            }
+                        }
+                        if (f_out32) {  // slab `half`: row-major 32 floats = 8 x 16 B chunks, chunk index XOR (row % 8)
                             const uint32_t base = stg32 + (uint32_t)half * (kBlockM * 128) + (uint32_t)row * 128;
                             st_shared_v4(base + (((uint32_t)(2 * g) ^ swz) << 4), __float_as_uint(y[0]), __float_as_uint(y[1]),
                                          __float_as_uint(y[2]), __float_as_uint(y[3]));
                             st_shared_v4(base + (((uint32_t)(2 * g + 1) ^ swz) << 4), __float_as_uint(y[4]), __float_as_uint(y[5]),
                                          __float_as_uint(y[6]), __float_as_uint(y[7]));
                         }
-                        if (ep.out16) {  // 64 halves per row = 8 chunks; this 8-column group is chunk half*4+g
+                        if (f_out16) {  // 64 halves per row = 8 chunks; this 8-column group is chunk half*4+g
                             uint32_t h[4];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
@@ -461,14 +499,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         }
                     }
                 }
-                ri += ep.res32 ? 1u : 0u;
+                ri += f_res32 ? 1u : 0u;
                 fence_proxy_async();             // generic-proxy smem writes -> visible to the TMA (async proxy)
-                if (p.ep_warp) {
+                if (f_warp) {
                     __syncwarp();
                     if (lane == 0) {
                         const uint32_t woff = (uint32_t)q * 32u * 128u;
-                        if (ep.out16) tma_store_2d(&map_o16, stg16 + woff, n0 + cc, m0 + q * 32);
-                        if (ep.out32) {
+                        if (f_out16) tma_store_2d(&map_o16, stg16 + woff, n0 + cc, m0 + q * 32);
+                        if (f_out32) {
                             tma_store_2d(&map_o32, stg32 + woff, n0 + cc, m0 + q * 32);
                             if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_2d(&map_o32, stg32 + kBlockM * 128 + woff, n0 + cc + 32, m0 + q * 32);
                         }
@@ -478,20 +516,21 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 }
                 named_bar_sync(1 + group, 128);
                 if (leader) {
-                    if (ep.out16) tma_store_2d(&map_o16, stg16, n0 + cc, m0);
-                    if (ep.out32) {
+                    if (f_out16) tma_store_2d(&map_o16, stg16, n0 + cc, m0);
+                    if (f_out32) {
                         tma_store_2d(&map_o32, stg32, n0 + cc, m0);
                         if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_2d(&map_o32, stg32 + kBlockM * 128, n0 + cc + 32, m0);
                     }
                     tma_store_commit();
                 }
             }
+            if (f_stats && m < p.M) *reinterpret_cast<float2 *>(ep.stats_out + 2 * (size_t)m) = make_float2(st_sum, st_sq);
             // this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld_32x32): hand the accumulator back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
         }
-        if (p.ep_warp ? lane == 0 : leader) tma_store_wait_all();  // all bulk stores have been written before the CTA exits
+        if (f_warp ? lane == 0 : leader) tma_store_wait_all();  // all bulk stores have been written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -567,6 +606,7 @@ static void choose_tiling(GemmLaunch & L, int N) {
     // Compute-heavy shapes (K >= 512, the batched GRU's recurrent matmul) take 256-wide tiles again: with 128-wide tiles the
     // operand re-reads from L2 (403 MB at 4096 x 3072 x 1024) bound the kernel at ~570 TFLOP/s, 256-wide reaches ~900.
     int max_bn             = (N > 128 && 2 * p.K <= N && p.K < 512) ? 128 : 256;
+    if (p.ep.stats_out) max_bn = 256;  // row statistics need the whole row in one tile (N <= 256 is checked by the caller)
     if (const char * e = getenv("GGML_B200_GEMM_BN")) max_bn = atoi(e);  // tuning probe
     p.n_tiles              = (N + max_bn - 1) / max_bn;
     int per                = (N + p.n_tiles - 1) / p.n_tiles;
@@ -630,6 +670,7 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
                   const GemmEpilogue & ep) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (lda % 8) || (ldb % 8) || (K % 8)) return false;
     if (((uintptr_t)A | (uintptr_t)B) & 15) return false;
+    if (ep.stats_out && N > 256) return false;  // row statistics need one tile per row
     L = GemmLaunch();
     GemmLaunch::Params & p = L.p;
     p.M = M; p.N = N; p.K = K;
@@ -713,13 +754,42 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
     return true;
 }
 
-void gemm_launch(const GemmLaunch & L, cudaStream_t st) {
+template <int EPI>
+static void gemm_launch_variant(const GemmLaunch & L, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_gemm_tcgen05<<<L.grid, kThreads, L.smem_bytes, st>>>(L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
+    k_gemm_tcgen05<EPI><<<L.grid, kThreads, L.smem_bytes, st>>>(L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
+}
+
+void gemm_launch(const GemmLaunch & L, cudaStream_t st) {
+    const GemmEpilogue & ep = L.p.ep;
+    const int mask = (ep.act ? kEpiAct : 0) | (ep.res32 ? kEpiRes32 : 0) | (ep.out16 ? kEpiOut16 : 0) | (ep.out32 ? kEpiOut32 : 0) |
+                     (ep.ln_stats ? kEpiLn : 0) | (ep.stats_out ? kEpiStats : 0) | (ep.res16 ? kEpiRes16 : 0);
+    static const bool generic_only = getenv("GGML_B200_GEMM_GENERIC") != nullptr;
+    const bool warp_ok = (L.p.ep_warp != 0) == (ep.res32 == nullptr);  // the specialised kernels derive the store mode from the mask
+    if (!generic_only && warp_ok) {
+        switch (mask) {
+#define EPI_CASE(M) case (M): gemm_launch_variant<(M)>(L, st); return;
+            EPI_CASE(kEpiAct | kEpiOut16)                                  // expand 1x1 / 3x3 conv + SiLU, ffn up-projection
+            EPI_CASE(kEpiOut16)                                            // reduce 1x1, qkv
+            EPI_CASE(kEpiOut16 | kEpiOut32)                                // reduce 1x1 feeding a residual
+            EPI_CASE(kEpiOut32)                                            // 1x1 into the transformer (f32 stream)
+            EPI_CASE(kEpiRes32 | kEpiOut16)                                // reduce 1x1 + residual
+            EPI_CASE(kEpiRes32 | kEpiOut16 | kEpiOut32)
+            EPI_CASE(kEpiRes32 | kEpiOut32)                                // attention output / ffn down-projection
+            EPI_CASE(kEpiAct | kEpiOut32)                                  // last 1x1 expansion (features)
+            EPI_CASE(kEpiLn | kEpiOut16)                                   // qkv over a folded LayerNorm
+            EPI_CASE(kEpiLn | kEpiAct | kEpiOut16)                         // ffn up-projection / conv_projection over a folded LayerNorm
+            EPI_CASE(kEpiStats | kEpiOut16 | kEpiOut32)                    // producers of a folded LayerNorm's input
+            EPI_CASE(kEpiStats | kEpiRes32 | kEpiOut16 | kEpiOut32)
+#undef EPI_CASE
+            default: break;
+        }
+    }
+    gemm_launch_variant<-1>(L, st);
 }
 
 }  // namespace b200

@@ -25,6 +25,15 @@ struct GemmEpilogue {
     int            ld16  = 0;
     float *        out32 = nullptr;
     int            ld32  = 0;
+    // LayerNorm folded around the GEMM (no separate LN kernel): a producer whose tile spans the whole row also writes
+    // (sum, sum of squares) of its final values per row; a consumer multiplies RAW activations with gamma-scaled weights and
+    // applies  y = r * (acc - mu * c1[n])  before scale/shift, with mu, r from the producer's row statistics and
+    // c1[n] = sum_k W'[n][k] (beta and the bias are folded into `shift` on the host).
+    float *        stats_out = nullptr;  // [M][2], requires N <= 256 (one tile per row)
+    const float *  ln_stats  = nullptr;  // [M][2]
+    const float *  ln_c1     = nullptr;  // [N]
+    float          ln_inv_c  = 0.f;      // 1 / (channels of the normalised row)
+    float          ln_eps    = 0.f;
 };
 
 // A prepared launch: tensor maps are encoded once at plan time, the launch is then replayable / capturable.
