@@ -135,14 +135,19 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
         }
         dw_mbar_wait(dw_smem_u32(&full_bar[buf]), (it >> 1) & 1u);
         if (lane_ok) {
-            const unsigned char * tile_smem = dw_smem + (size_t)buf * box_bytes + cg * 16;
-            const int             oyl0      = rs * rows_per;
-            auto load_row = [&](uint4 (&dst)[3], int in_row) {
+            // running 32-bit shared addresses and one running output pointer: the row loops carry no index arithmetic
+            const uint32_t pitch = (uint32_t)p.box_w * 128u;
+            const int      oyl0  = rs * rows_per;
+            uint32_t       rp    = sbase + (uint32_t)buf * box_bytes + (uint32_t)cg * 16u + (uint32_t)(xl * STRIDE) * 128u + (uint32_t)(oyl0 * STRIDE) * pitch;
+            __half *       op    = p.out + (((size_t)n * p.OH + (ty * p.TH + oyl0)) * p.OW + ox) * p.C + c0;
+            const size_t   opitch = (size_t)p.OW * p.C;
+            auto load_row = [&](uint4 (&dst)[3]) {  // the 3 taps of the row at rp, then advance one input row
 #pragma unroll
                 for (int kw = 0; kw < 3; kw++)
-                    dst[kw] = *reinterpret_cast<const uint4 *>(tile_smem + ((size_t)in_row * p.box_w + (xl * STRIDE + kw)) * 128);
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dst[kw].x), "=r"(dst[kw].y), "=r"(dst[kw].z), "=r"(dst[kw].w) : "r"(rp + (uint32_t)kw * 128u));
+                rp += pitch;
             };
-            auto emit = [&](const uint4 (&r0)[3], const uint4 (&r1)[3], const uint4 (&r2)[3], int oyl) {
+            auto emit = [&](const uint4 (&r0)[3], const uint4 (&r1)[3], const uint4 (&r2)[3]) {
                 float acc[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc[j] = 0.f;
@@ -160,8 +165,8 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
                     if (p.act) { y0 = dw_silu(y0); y1 = dw_silu(y1); }
                     o.h[j] = __floats2half2_rn(y0, y1);
                 }
-                const int oy = ty * p.TH + oyl;
-                *reinterpret_cast<H8 *>(p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.C + c0) = o;
+                *reinterpret_cast<H8 *>(op) = o;
+                op += opitch;
             };
             int rows = p.OH - (ty * p.TH + oyl0);  // output rows of this thread that exist
             if (rows > rows_per) rows = rows_per;
@@ -169,37 +174,36 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
                 // sliding 3-row window in registers: each output row loads only its new bottom row (3 LDS.128 instead of 9)
                 uint4 ra[3], rb[3], rc[3];
                 if (rows > 0) {
-                    load_row(ra, oyl0);
-                    load_row(rb, oyl0 + 1);
+                    load_row(ra);
+                    load_row(rb);
                 }
                 for (int r = 0; r < rows; r += 3) {
-                    load_row(rc, oyl0 + r + 2);
-                    emit(ra, rb, rc, oyl0 + r);
+                    load_row(rc);
+                    emit(ra, rb, rc);
                     if (r + 1 < rows) {
-                        load_row(ra, oyl0 + r + 3);
-                        emit(rb, rc, ra, oyl0 + r + 1);
+                        load_row(ra);
+                        emit(rb, rc, ra);
                     }
                     if (r + 2 < rows) {
-                        load_row(rb, oyl0 + r + 4);
-                        emit(rc, ra, rb, oyl0 + r + 2);
+                        load_row(rb);
+                        emit(rc, ra, rb);
                     }
                 }
             } else {
                 // stride 2: consecutive outputs share one input row (2r+2 is the next output's top row)
                 uint4 ra[3], rb[3], rc[3];
-                if (rows > 0) load_row(ra, oyl0 * 2);
+                if (rows > 0) load_row(ra);
                 for (int r = 0; r < rows; r += 2) {
-                    load_row(rb, (oyl0 + r) * 2 + 1);
-                    load_row(rc, (oyl0 + r) * 2 + 2);
-                    emit(ra, rb, rc, oyl0 + r);
+                    load_row(rb);
+                    load_row(rc);
+                    emit(ra, rb, rc);
                     if (r + 1 < rows) {
-                        load_row(ra, (oyl0 + r) * 2 + 3);
-                        load_row(rb, (oyl0 + r) * 2 + 4);
-                        emit(rc, ra, rb, oyl0 + r + 1);
-                        // the window for the next pair starts at rb
+                        load_row(ra);
+                        load_row(rb);
+                        emit(rc, ra, rb);
 #pragma unroll
                         for (int kw = 0; kw < 3; kw++) ra[kw] = rb[kw];
-                    }
+                    } 
                 }
             }
         }

@@ -207,11 +207,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     uint64_t *      bars        = (uint64_t *)(smem + (size_t)p.stages * stage_bytes);
     uint64_t *      full_bar    = bars;
     uint64_t *      empty_bar   = bars + kMaxStage;
-    uint64_t *      tmem_full   = bars + 2 * kMaxStage;      // [2]
-    uint64_t *      tmem_empty  = bars + 2 * kMaxStage + 2;  // [2]
-    uint64_t *      res_full    = bars + 2 * kMaxStage + 4;  // [2] residual slab landed (per epilogue group)
-    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 6);
-    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 8);  // 16-byte aligned: read back with LDS.128
+    uint64_t *      tmem_full   = bars + 2 * kMaxStage;      // [4]
+    uint64_t *      tmem_empty  = bars + 2 * kMaxStage + 4;  // [4]
+    uint64_t *      res_full    = bars + 2 * kMaxStage + 8;  // [2] residual slab landed (per epilogue group)
+    uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 10);
+    float *         s_scale     = (float *)(bars + 2 * kMaxStage + 16);  // 16-byte aligned: read back with LDS.128
     float *         s_shift     = s_scale + 256;
     float *         s_c1        = s_shift + 256;  // LayerNorm folding: per-column sum of the gamma-scaled weights
     // epilogue staging (per epilogue warp group): 128 rows x 128 B tiles in the TMA 128B-swizzle layout
@@ -234,11 +234,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             mbar_init(smem_u32(&full_bar[s]), p.a_cp_async ? 33 : 1);  // TMA thread (+ 32 cp.async lanes)
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        for (int a = 0; a < 2; a++) {
+        for (int a = 0; a < 4; a++) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
             mbar_init(smem_u32(&tmem_empty[a]), 4);  // one arrive per epilogue warp
-            mbar_init(smem_u32(&res_full[a]), 1);
         }
+        for (int a = 0; a < 2; a++) mbar_init(smem_u32(&res_full[a]), 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const uint32_t idesc = make_idesc(p.block_n);
             uint32_t it = 0, t = 0;
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
-                const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+                const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;
                 mbar_wait(smem_u32(&tmem_empty[acc]), aph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             if ((t & 1u) != group) continue;
             const int      m0  = tile * kBlockM;
             const int      m   = m0 + row;
-            const uint32_t acc = group, aph = (t >> 1) & 1u;
+            const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;  // (t & 1) == group
             // folded LayerNorm: this row's mean and 1/std from the producer's (sum, sum of squares)
             float ln_r = 1.f, ln_mr = 0.f, st_sum = 0.f, st_sq = 0.f;
             if (f_ln && m < p.M) {
@@ -611,8 +611,10 @@ static void choose_tiling(GemmLaunch & L, int N) {
     p.n_tiles              = (N + max_bn - 1) / max_bn;
     int per                = (N + p.n_tiles - 1) / p.n_tiles;
     p.block_n              = p.n_tiles > 1 ? (per + 63) / 64 * 64 : (per + 31) / 32 * 32;
-    // two accumulator stages in TMEM (tile i+1 accumulates while tile i drains); power-of-two column count >= 32
-    const int need         = 2 * p.block_n;
+    // accumulator stages in TMEM (tile i+1.. accumulate while tile i drains); power-of-two column count >= 32.  Narrow tiles
+    // take 4 stages: with one 64-column chunk per tile the MMA turnaround after a release would otherwise be exposed
+    p.acc_stages           = (p.block_n <= 64 && getenv("GGML_B200_GEMM_ACC2") == nullptr) ? 4 : 2;
+    const int need         = p.acc_stages * p.block_n;
     p.tmem_cols            = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const int stage_bytes  = kBlockM * p.kb_elems * 2 + p.block_n * p.kb_elems * 2;
     const int staging      = 2 * ((p.ep.out16 ? kBlockM * 128 : 0) + ((p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0));

@@ -38,13 +38,13 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // part): the spinning producer / MMA-issuer warps executed 28 % of all instructions of the GEMM and took issue slots from
 // the epilogue warps of their sub-partitions.  nanosleep between polls parks the warp instead; GGML_B200_WAIT_NS is compiled in.
 #ifndef GGML_B200_WAIT_NS
-#define GGML_B200_WAIT_NS 64
+#define GGML_B200_WAIT_NS 32
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(GGML_B200_WAIT_NS);
+        if (GGML_B200_WAIT_NS > 0) __nanosleep(GGML_B200_WAIT_NS);
         if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must surface as a CUDA error, never as a hung GPU
     }
 }
