@@ -601,9 +601,21 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    for (int i = threadIdx.x; i < nq * (DP / 8); i += blockDim.x) {
-        const int r = i / (DP / 8), c = i % (DP / 8);
-        cp_async16(sQ + r * LDS + c * 8, qkv + tok(q0 + r) * ld + head * DP + c * 8);
+    // Loads: thread = (row slot = tid / 8, 16-byte chunk = tid % 8; chunks >= DP/8 idle), blockDim/8 rows per pass.  The token index of
+    // a row (an integer division by the patch-grid width) is computed once and then advanced incrementally: the old
+    // i / (DP/8), i % (DP/8), l / npw per 16-byte copy was a third of all instructions executed by this kernel.
+    const int  lrow = threadIdx.x >> 3, lchunk = threadIdx.x & 7;
+    const bool lact = lchunk < DP / 8;
+    const int  rpp    = blockDim.x >> 3;                        // rows per pass (the block has 32 threads per 16 queries)
+    const int  step_h = rpp / npw, step_w = rpp - step_h * npw;  // rpp rows further = step_h grid rows + step_w columns
+    auto row_token = [&](int iph, int ipw) -> int64_t { return ((int64_t)n * H + (iph * 2 + ph)) * W + (ipw * 2 + pw); };
+    {
+        int l0 = q0 + lrow, iph = l0 / npw, ipw = l0 - iph * npw;
+        for (int r = lrow; r < nq; r += rpp) {
+            if (lact) cp_async16(sQ + r * LDS + lchunk * 8, qkv + row_token(iph, ipw) * ld + head * DP + lchunk * 8);
+            iph += step_h; ipw += step_w;
+            if (ipw >= npw) { ipw -= npw; iph++; }
+        }
     }
 
     const bool warp_active = warp * 16 < nq;
@@ -616,11 +628,17 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
     for (int kc0 = 0; kc0 < L; kc0 += kAttnLK) {
         const int nk = min(kAttnLK, L - kc0);
         __syncthreads();  // previous chunk fully consumed
-        for (int i = threadIdx.x; i < nk * (DP / 8); i += blockDim.x) {
-            const int      r = i / (DP / 8), c = i % (DP / 8);
-            const __half * src = qkv + tok(kc0 + r) * ld + (heads + head) * DP + c * 8;
-            cp_async16(sK + r * LDS + c * 8, src);
-            cp_async16(sV + r * LDS + c * 8, src + heads * DP);
+        {
+            int l0 = kc0 + lrow, iph = l0 / npw, ipw = l0 - iph * npw;
+            for (int r = lrow; r < nk; r += rpp) {
+                if (lact) {
+                    const __half * src = qkv + row_token(iph, ipw) * ld + (heads + head) * DP + lchunk * 8;
+                    cp_async16(sK + r * LDS + lchunk * 8, src);
+                    cp_async16(sV + r * LDS + lchunk * 8, src + heads * DP);
+                }
+                iph += step_h; ipw += step_w;
+                if (ipw >= npw) { ipw -= npw; iph++; }
+            }
         }
         cp_async_wait_all();
         __syncthreads();
