@@ -366,3 +366,31 @@ def test_compute_u8_equals_f32_path_on_preprocessed_images(G, oracle, weight_fil
             np.testing.assert_array_equal(ps, p_ref)
     finally:
         m.close()
+
+
+# ---- BASELINE.json's full size (MobileViT-S, batch 256, 256x256) through size-independent properties --------------------
+def test_full_size_batch_256_is_batch_independent_and_matches_the_oracle_sample(G, oracle, weight_files):
+    """At the bench's own shape the oracle would need minutes, so: (1) every copy of an image inside the batch of 256 gives
+    bit-identical features (tiles, CTAs and batch position must not leak into the result), (2) the same 8 images run as a batch
+    of 8 give the same bits as inside the batch of 256, (3) those 8 are checked against the oracle with the north_star gate."""
+    from ggml_experiments_b200 import mobilevit as MV
+    base = W.synthetic_images(8, 256, 256, seed=7)
+    imgs = np.tile(base, (32, 1, 1, 1))
+    MV.set_mode(MV.FAST)
+    m = G.MobileViT(weight_files["s"])
+    try:
+        feat, pooled = m.extract_features(imgs)
+        info = m.plan_info(256, 256, 256)
+        feat8, pooled8 = m.extract_features(base)
+    finally:
+        m.close()
+    assert info["mode"] == MV.FAST
+    f = feat.reshape(32, 8, *feat.shape[1:])
+    assert np.array_equal(f, np.broadcast_to(f[0], f.shape)), "copies of the same image differ inside the batch"
+    np.testing.assert_array_equal(feat8, f[0])
+    np.testing.assert_array_equal(pooled8, pooled[:8])
+    ref_f, ref_p = oracle.OracleModel(weight_files["s"]).forward(base)
+    r = parity_report(feat8, ref_f, rtol=1e-2, atol_rms=1e-2)
+    t = top1_report(pooled8, ref_p)
+    assert r["violations"] <= r["n"] * 1e-4 and r["rel_l2"] < 5e-3, r
+    assert t["agree"] == 1.0, t
