@@ -272,11 +272,17 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const uint32_t fb = smem_u32(&full_bar[s]);
             const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
             if (lane == 0) {
-                mbar_expect_tx(fb, (uint32_t)b_bytes);
-                tma_load_2d(sa + a_bytes, &map_b, 0, n0, fb);
+                // one k-block: the B tile (weights) is the same for every M tile of this CTA -> fill each stage's B slot once
+                if (it < (uint32_t)p.stages) {
+                    mbar_expect_tx(fb, (uint32_t)b_bytes);
+                    tma_load_2d(sa + a_bytes, &map_b, 0, n0, fb);
+                } else {
+                    mbar_arrive(fb);
+                }
             }
+            const int cshift = cpr == 2 ? 1 : 2;
             for (int i = lane; i < chunks; i += 32) {
-                const int      row = i / cpr, ch = i - row * cpr;
+                const int      row = i >> cshift, ch = i & (cpr - 1);
                 const uint32_t sw  = cpr == 2 ? ((uint32_t)row >> 2) & 1u : ((uint32_t)row >> 1) & 3u;
                 const uint32_t dst = sa + (uint32_t)row * row_bytes + (((uint32_t)ch ^ sw) << 4);
                 const int      m   = m0 + row;
@@ -305,11 +311,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
-                    mbar_expect_tx(fb, (uint32_t)stage_bytes);
                     if (!p.conv) {
+                        // single k-block GEMMs (K <= 64: every expand layer): B is loaded into each stage's slot once
+                        const bool load_b = p.num_kb > 1 || it < (uint32_t)p.stages;
+                        mbar_expect_tx(fb, (uint32_t)(load_b ? stage_bytes : a_bytes));
                         tma_load_2d(sa, &map_a0, kb * p.kb_elems, m0, fb);
-                        tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
+                        if (load_b) tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
                     } else {
+                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
                         const int tap = kb / cblk_tot, r = kb % cblk_tot;
                         const int src = r >= p.cblk0;
                         const int cb  = src ? r - p.cblk0 : r;
