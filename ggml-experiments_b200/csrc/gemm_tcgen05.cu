@@ -203,19 +203,25 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     uint8_t * smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int       a_bytes     = kBlockM * p.kb_elems * 2;
     const int       b_bytes     = p.block_n * p.kb_elems * 2;
-    const int       stage_bytes = a_bytes + b_bytes;
-    uint64_t *      bars        = (uint64_t *)(smem + (size_t)p.stages * stage_bytes);
+    // Plain GEMMs keep the whole weight tile (all K blocks) resident: it is the same for every M tile of a persistent CTA, and
+    // re-loading it per tile made the output-heavy transformer GEMMs L2->SM bound (qkv: 754 MB of operand traffic per launch,
+    // 60 % of it weights).  The ring then holds A only.  The implicit-GEMM conv (9 taps x C of weights) keeps B in the ring.
+    const int       stage_bytes = a_bytes + (p.b_resident ? 0 : b_bytes);
+    uint8_t *       smem_bres   = smem;
+    uint8_t *       ring        = smem + (p.b_resident ? (size_t)p.num_kb * b_bytes : 0);
+    uint64_t *      bars        = (uint64_t *)(ring + (size_t)p.stages * stage_bytes);
     uint64_t *      full_bar    = bars;
     uint64_t *      empty_bar   = bars + kMaxStage;
     uint64_t *      tmem_full   = bars + 2 * kMaxStage;      // [4]
     uint64_t *      tmem_empty  = bars + 2 * kMaxStage + 4;  // [4]
     uint64_t *      res_full    = bars + 2 * kMaxStage + 8;  // [2] residual slab landed (per epilogue group)
     uint32_t *      tmem_slot   = (uint32_t *)(bars + 2 * kMaxStage + 10);
+    uint64_t *      bres_full   = bars + 2 * kMaxStage + 11;  // resident weight tile landed
     float *         s_scale     = (float *)(bars + 2 * kMaxStage + 16);  // 16-byte aligned: read back with LDS.128
     float *         s_shift     = s_scale + 256;
     float *         s_c1        = s_shift + 256;  // LayerNorm folding: per-column sum of the gamma-scaled weights
     // epilogue staging (per epilogue warp group): 128 rows x 128 B tiles in the TMA 128B-swizzle layout
-    uint8_t *       stage_base  = smem + (size_t)p.stages * stage_bytes + kCtrlBytes;
+    uint8_t *       stage_base  = ring + (size_t)p.stages * stage_bytes + kCtrlBytes;
     const int       stg16_bytes = p.ep.out16 ? kBlockM * 128 : 0;      // 64 f16 columns per row
     const int       stg32_bytes = (p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0;  // 2 x 32 f32 columns per row
 
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             mbar_init(smem_u32(&tmem_empty[a]), 4);  // one arrive per epilogue warp
         }
         for (int a = 0; a < 2; a++) mbar_init(smem_u32(&res_full[a]), 1);
+        mbar_init(smem_u32(bres_full), 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -270,14 +277,17 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const uint32_t ph = (it / p.stages) & 1u;
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
             const uint32_t fb = smem_u32(&full_bar[s]);
-            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
             if (lane == 0) {
-                // one k-block: the B tile (weights) is the same for every M tile of this CTA -> fill each stage's B slot once
-                if (it < (uint32_t)p.stages) {
+                if (p.b_resident) {
+                    if (it == 0) {  // the (single k-block) weight tile, once
+                        mbar_expect_tx(smem_u32(bres_full), (uint32_t)b_bytes);
+                        tma_load_2d(smem_u32(smem_bres), &map_b, 0, n0, smem_u32(bres_full));
+                    }
+                    mbar_arrive(fb);
+                } else {
                     mbar_expect_tx(fb, (uint32_t)b_bytes);
                     tma_load_2d(sa + a_bytes, &map_b, 0, n0, fb);
-                } else {
-                    mbar_arrive(fb);
                 }
             }
             const int cshift = cpr == 2 ? 1 : 2;
@@ -296,6 +306,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;  // k-block counter across all tiles of this CTA
+            if (p.b_resident && (int)blockIdx.x < num_m_tiles) {
+                mbar_expect_tx(smem_u32(bres_full), (uint32_t)(p.num_kb * b_bytes));
+                for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(smem_u32(smem_bres + (size_t)kb * b_bytes), &map_b, kb * p.kb_elems, n0, smem_u32(bres_full));
+            }
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
                 const int m0 = tile * kBlockM;
                 int img = 0, y0 = 0;
@@ -309,14 +323,12 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     const uint32_t ph = (it / p.stages) & 1u;
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                     const uint32_t fb = smem_u32(&full_bar[s]);
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
                     if (!p.conv) {
-                        // single k-block GEMMs (K <= 64: every expand layer): B is loaded into each stage's slot once
-                        const bool load_b = p.num_kb > 1 || it < (uint32_t)p.stages;
-                        mbar_expect_tx(fb, (uint32_t)(load_b ? stage_bytes : a_bytes));
+                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
                         tma_load_2d(sa, &map_a0, kb * p.kb_elems, m0, fb);
-                        if (load_b) tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
+                        if (!p.b_resident) tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
                     } else {
                         mbar_expect_tx(fb, (uint32_t)stage_bytes);
                         const int tap = kb / cblk_tot, r = kb % cblk_tot;
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.block_n);
             uint32_t it = 0, t = 0;
+            if (p.b_resident && (int)blockIdx.x < num_m_tiles) mbar_wait(smem_u32(bres_full), 0);
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
                 const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;
                 mbar_wait(smem_u32(&tmem_empty[acc]), aph ^ 1u);  // epilogue has drained this accumulator
@@ -346,8 +359,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     mbar_wait(smem_u32(&full_bar[s]), ph);
                     if (p.a_cp_async) fence_proxy_async();  // cp.async wrote through the generic proxy
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
+                    const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint32_t sb = p.b_resident ? smem_u32(smem_bres + (size_t)kb * b_bytes) : sa + a_bytes;
                     int rem;
                     if (!p.conv) {
                         rem = p.K - kb * p.kb_elems;
@@ -626,21 +639,36 @@ static void choose_tiling(GemmLaunch & L, int N) {
     p.acc_stages           = (p.block_n <= 64 && getenv("GGML_B200_GEMM_ACC2") == nullptr) ? 4 : 2;
     const int need         = p.acc_stages * p.block_n;
     p.tmem_cols            = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-    const int stage_bytes  = kBlockM * p.kb_elems * 2 + p.block_n * p.kb_elems * 2;
-    const int staging      = 2 * ((p.ep.out16 ? kBlockM * 128 : 0) + ((p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0));
-    // TMEM (512 columns) and shared memory (~220 KiB usable) decide how many persistent CTAs share an SM
-    int stages = 0;
-    for (L.ctas_per_sm = p.block_n <= 128 ? 2 : 1; L.ctas_per_sm >= 1; L.ctas_per_sm--) {
-        const int budget = (216 * 1024) / L.ctas_per_sm - 1024 - kCtrlBytes - staging;
-        stages           = budget / stage_bytes;
-        if (stages >= 2 || L.ctas_per_sm == 1) break;
-    }
+    const int a_bytes = kBlockM * p.kb_elems * 2, b_bytes = p.block_n * p.kb_elems * 2;
+    const int b_total = p.num_kb * b_bytes;
+    const int staging = 2 * ((p.ep.out16 ? kBlockM * 128 : 0) + ((p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0));
+    // TMEM (512 columns) and shared memory (~220 KiB usable) decide how many persistent CTAs share an SM.  The weight tile
+    // stays resident (ring = A only) when that does not cost a CTA per SM: one CTA with resident weights was measured slower
+    // than two CTAs re-loading them (ffn up-projection 87 -> 99 us), while with equal occupancy it is faster (qkv 96 -> 91 us,
+    // expand 16->64 214 -> 129 us).
+    auto fit = [&](int stage_bytes, int fixed, int & ctas) {
+        int stages = 0;
+        for (ctas = p.block_n <= 128 ? 2 : 1; ctas >= 1; ctas--) {
+            const int budget = (216 * 1024) / ctas - 1024 - kCtrlBytes - staging - fixed;
+            stages           = budget > 0 ? budget / stage_bytes : 0;
+            if (stages >= 2 || ctas == 1) break;
+        }
+        return stages;
+    };
+    int       ctas_ring = 1, ctas_res = 1;
+    const int st_ring = fit(a_bytes + b_bytes, 0, ctas_ring);
+    const int st_res  = fit(a_bytes, b_total, ctas_res);
+    p.b_resident      = (!p.conv && st_res >= 2 && ctas_res >= ctas_ring && getenv("GGML_B200_GEMM_NO_BRES") == nullptr) ? 1 : 0;
+    const int stage_bytes = a_bytes + (p.b_resident ? 0 : b_bytes);
+    const int fixed       = p.b_resident ? b_total : 0;
+    int       stages      = p.b_resident ? st_res : st_ring;
+    L.ctas_per_sm         = p.b_resident ? ctas_res : ctas_ring;
     if (stages > kMaxStage) stages = kMaxStage;
     if (stages < 1) stages = 1;
     if (const char * e = getenv("GGML_B200_GEMM_STAGES")) stages = atoi(e);      // tuning probes
     if (const char * e = getenv("GGML_B200_GEMM_CTAS")) L.ctas_per_sm = atoi(e);
     p.stages     = stages;
-    L.smem_bytes = 1024 + (size_t)stages * stage_bytes + kCtrlBytes + staging;
+    L.smem_bytes = 1024 + (size_t)fixed + (size_t)stages * stage_bytes + kCtrlBytes + staging;
 }
 
 // output tensor maps for the TMA-store epilogue: 128-row x 128-byte boxes, 128B swizzle

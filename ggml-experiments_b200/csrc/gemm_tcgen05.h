@@ -42,6 +42,7 @@ struct GemmLaunch {
     struct Params {
         int M, N, K;
         int block_n, n_tiles, num_kb, stages, tmem_cols;
+        int b_resident;             // 1: all K blocks of this CTA's weight tile stay in shared memory (loaded once), the ring holds A only
         int acc_stages;             // TMEM accumulator stages: 2, or 4 for tiles of at most 64 columns (the MMA issuer runs further ahead)
         int kb_elems;               // K elements per smem stage: 64 (128B swizzle), 32 (64B swizzle) or 16 (32B swizzle)
         int a_cp_async;             // 1: A tile loaded by the producer warp with cp.async (K = 16 / 32: TMA rows would be 32-64 B)
