@@ -94,13 +94,29 @@ if os.path.exists(mpath):
             except Exception:
                 pass
     print("metrics:", len(data), "launches")
-fam = {"k_gemm_tcgen05": ["gemm_tcgen05_conv1x1", "gemm_tcgen05_linear", "gemm_tcgen05_qkv", "conv3x3_tcgen05_implicit_gemm"],
-       "k_dwconv_tma<1>": ["dwconv3x3_tma_bn_silu"], "k_dwconv_tma<2>": ["dwconv3x3_tma_bn_silu"],
-       "k_attention_mma<48>": ["attention_mma_flash"], "k_attention_mma<64>": ["attention_mma_flash"],
-       "k_layernorm": ["layernorm_f32_to_f16"], "k_stem<16>": ["stem_conv3x3s2_bn_silu"]}
-tj = {}
-for k, v in traffic.items():
-    for name in fam.get(k, [k]):
-        tj.setdefault(name, []).extend(v)
+# bench.py names kernels by what they compute (gemm_tcgen05_conv1x1 / _linear / _qkv ...), ncu by symbol (k_gemm_tcgen05<EPI>).
+# The profiled launches are the first forward pass in plan order, so gpurun_out/layers_<tag>.txt (tests/profile_layers.py,
+# same plan) maps launch i to its bench name; without that file the symbol name is used.
+order = []
+lpath = os.path.join(src, f"layers_{tag}.txt")
+if os.path.exists(lpath):
+    for line in open(lpath):
+        m = re.match(r"\s*[\d.]+ us\s+\d+ GB/s\s+[\d.]+ TF/s\s+[\d.]+ MB\s+(\S+)", line)
+        if m:
+            order.append(m.group(1))
+    import shutil
+    shutil.copy(lpath, os.path.join(out, f"layers_{tag}.txt"))
+tj = defaultdict(list)
+flat = []  # (symbol, bytes) in launch order
+if os.path.exists(mpath):
+    for r in data:
+        try:
+            rd = float(r[ix["dram__bytes_read.sum"]].replace(",", "")); wr = float(r[ix["dram__bytes_write.sum"]].replace(",", ""))
+            sc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            flat.append((short(r[ix["Kernel Name"]]), rd * sc.get(units[ix["dram__bytes_read.sum"]], 1.0) + wr * sc.get(units[ix["dram__bytes_write.sum"]], 1.0)))
+        except Exception:
+            pass
+for i, (sym, b) in enumerate(flat):
+    tj[order[i] if i < len(order) else sym].append(b)
 json.dump({k: sum(v) / len(v) for k, v in tj.items()}, open(os.path.join(out, "traffic.json"), "w"), indent=1)
-print({k: round(sum(v) / len(v) / 1e6, 1) for k, v in tj.items()})
+print({k: (len(v), round(sum(v) / len(v) / 1e6, 1)) for k, v in tj.items()})
