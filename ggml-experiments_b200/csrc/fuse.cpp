@@ -731,7 +731,7 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     for (FNode * n : P.order) {
         if (n->kind == FK_CONV3) {
             const FVal * v = n->in[0];
-            const bool ok = v->W <= 128 && 128 % v->W == 0 && ((v->H * v->W >= 128) ? (v->H * v->W) % 128 == 0 : 128 % (v->H * v->W) == 0);
+            const bool ok = v->W <= 128;  // a tile is a whole number of image rows (conv3x3_prepare)
             if (!ok) { plan->n_folded = 0; return false; }
         }
     }

@@ -87,6 +87,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap * ma
                  : "memory");
 }
 // smem tile -> global through the TMA engine (full-line writes, M/N tails clipped by the tensor map)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap * map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap * map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
@@ -227,7 +231,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * p.block_n;
-    const int num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    const int tile_m      = p.tile_m;  // 128 except for conv tiles that are a whole number of image rows
+    const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const uint32_t row_bytes = (uint32_t)p.kb_elems * 2;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, it++) {
-            const int      m0 = tile * kBlockM;
+            const int      m0 = tile * tile_m;
             const int      s  = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1u;
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(smem_u32(smem_bres + (size_t)kb * b_bytes), &map_b, kb * p.kb_elems, n0, smem_u32(bres_full));
             }
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
-                const int m0 = tile * kBlockM;
+                const int m0 = tile * tile_m;
                 int img = 0, y0 = 0;
                 if (p.conv) {
                     const int hw = p.H * p.W;
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         tma_load_2d(sa, &map_a0, kb * p.kb_elems, m0, fb);
                         if (!p.b_resident) tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
                     } else {
-                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                        mbar_expect_tx(fb, (uint32_t)(p.a_tx_bytes + b_bytes));  // the activation box may be shorter than 128 rows
                         const int tap = kb / cblk_tot, r = kb % cblk_tot;
                         const int src = r >= p.cblk0;
                         const int cb  = src ? r - p.cblk0 : r;
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         uint32_t t = 0, ri = 0;
         for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
             if ((t & 1u) != group) continue;
-            const int      m0  = tile * kBlockM;
+            const int      m0  = tile * tile_m;
             const int      m   = m0 + row;
             const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;  // (t & 1) == group
             // folded LayerNorm: this row's mean and 1/std from the producer's (sum, sum of squares)
@@ -527,10 +532,19 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     __syncwarp();
                     if (lane == 0) {
                         const uint32_t woff = (uint32_t)q * 32u * 128u;
-                        if (f_out16) tma_store_2d(&map_o16, stg16 + woff, n0 + cc, m0 + q * 32);
-                        if (f_out32) {
-                            tma_store_2d(&map_o32, stg32 + woff, n0 + cc, m0 + q * 32);
-                            if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_2d(&map_o32, stg32 + kBlockM * 128 + woff, n0 + cc + 32, m0 + q * 32);
+                        if (p.conv) {
+                            // conv output maps are 3-D {N, tile_m, tiles}: rows >= tile_m of the 128-row MMA tile are clipped by the TMA
+                            if (f_out16) tma_store_3d(&map_o16, stg16 + woff, n0 + cc, q * 32, tile);
+                            if (f_out32) {
+                                tma_store_3d(&map_o32, stg32 + woff, n0 + cc, q * 32, tile);
+                                if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_3d(&map_o32, stg32 + kBlockM * 128 + woff, n0 + cc + 32, q * 32, tile);
+                            }
+                        } else {
+                            if (f_out16) tma_store_2d(&map_o16, stg16 + woff, n0 + cc, m0 + q * 32);
+                            if (f_out32) {
+                                tma_store_2d(&map_o32, stg32 + woff, n0 + cc, m0 + q * 32);
+                                if (cc + 32 < p.block_n && n0 + cc + 32 < p.N) tma_store_2d(&map_o32, stg32 + kBlockM * 128 + woff, n0 + cc + 32, m0 + q * 32);
+                            }
                         }
                         tma_store_commit();
                     }
@@ -685,6 +699,23 @@ static void make_output_maps(GemmLaunch & L) {
     }
     L.p.ep_warp = (!ep.res32 && getenv("GGML_B200_GEMM_GROUP_EPILOGUE") == nullptr) ? 1 : 0;
     const uint32_t box_rows = L.p.ep_warp ? 32u : (uint32_t)kBlockM;
+    if (L.p.conv) {
+        // {N, tile_m, tiles}: M is a multiple of tile_m by construction, and a 32-row warp box that reaches past tile_m is clipped
+        const uint64_t tm = (uint64_t)L.p.tile_m, nt = (uint64_t)(L.p.M / L.p.tile_m);
+        if (ep.out16) {
+            const uint64_t dims[3] = {(uint64_t)L.p.N, tm, nt};
+            const uint64_t str[2]  = {(uint64_t)ep.ld16 * 2, tm * (uint64_t)ep.ld16 * 2};
+            const uint32_t box[3]  = {64, 32, 1};
+            make_map(&L.map_o16, ep.out16, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+        }
+        if (ep.out32) {
+            const uint64_t dims[3] = {(uint64_t)L.p.N, tm, nt};
+            const uint64_t str[2]  = {(uint64_t)ep.ld32 * 4, tm * (uint64_t)ep.ld32 * 4};
+            const uint32_t box[3]  = {32, 32, 1};
+            make_map(&L.map_o32, ep.out32, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        }
+        return;
+    }
     if (ep.out16) {
         const uint64_t dims[2] = {(uint64_t)L.p.N, (uint64_t)L.p.M};
         const uint64_t str[1]  = {(uint64_t)ep.ld16 * 2};
@@ -700,7 +731,7 @@ static void make_output_maps(GemmLaunch & L) {
 }
 
 static void choose_grid(GemmLaunch & L) {
-    const int num_m_tiles = (L.p.M + kBlockM - 1) / kBlockM;
+    const int num_m_tiles = (L.p.M + L.p.tile_m - 1) / L.p.tile_m;
     int       per_n       = (L.ctas_per_sm * runtime().sm_count) / L.p.n_tiles;
     if (per_n < 1) per_n = 1;
     L.grid = dim3((unsigned)(num_m_tiles < per_n ? num_m_tiles : per_n), (unsigned)L.p.n_tiles, 1);
@@ -715,6 +746,7 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
     GemmLaunch::Params & p = L.p;
     p.M = M; p.N = N; p.K = K;
     p.conv   = 0;
+    p.tile_m = kBlockM;
     // TMA cost is per box row: with K = 16 / 32 the rows are 32 / 64 bytes (or mostly out-of-bounds fill in a 64-wide
     // box) and the load runs at 2.2 TB/s (tests/gemm_probe.py).  Those shapes use one exact K block in the 32B / 64B
     // swizzled layout, filled by cp.async from the producer warp.
@@ -750,23 +782,27 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
 bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x1, int C1, int Nimg, int H, int W,
                      const __half * Wt, int OC, const GemmEpilogue & ep) {
     if (Nimg <= 0 || H <= 0 || W <= 0 || OC % 8 || C0 % 8 || C1 % 8 || C0 <= 0) return false;
-    if (W > 128 || 128 % W) return false;
+    if (W > 128 || ep.res32 || ep.res16 || ep.stats_out || ep.ln_stats) return false;
+    // An M tile is a whole number of image rows (or of whole images when an image has fewer than 128 pixels) that divides the
+    // image (the batch), at most 128 pixels: 128 % W == 0 gives full tiles, other widths leave the last MMA rows unused.
     int box_h, box_n, rows_per_tile;
-    if (H * W >= 128) {
-        if ((H * W) % 128) return false;
-        box_h         = 128 / W;
+    if (H * W > 128) {
+        box_h = 128 / W;
+        while (box_h > 1 && H % box_h) box_h--;
         box_n         = 1;
         rows_per_tile = box_h;
     } else {
-        if (128 % (H * W)) return false;
-        box_h         = H;
-        box_n         = 128 / (H * W);
+        box_h = H;
+        box_n = 128 / (H * W);
+        while (box_n > 1 && Nimg % box_n) box_n--;
         rows_per_tile = 0;
     }
+    const int tile_m = box_n * box_h * W;
     L = GemmLaunch();
     GemmLaunch::Params & p = L.p;
     p.M = Nimg * H * W; p.N = OC; p.K = 9 * (C0 + C1);
     p.conv = 1; p.H = H; p.W = W; p.rows_per_tile = rows_per_tile;
+    p.tile_m = tile_m; p.a_tx_bytes = tile_m * 128;
     p.C0 = C0; p.C1 = C1;
     p.cblk0  = (C0 + kBlockK - 1) / kBlockK;
     p.cblk1  = C1 > 0 ? (C1 + kBlockK - 1) / kBlockK : 0;

@@ -50,6 +50,8 @@ struct GemmLaunch {
         int lda;
         int ep_warp;                // 1: every epilogue warp stages and TMA-stores its own 32 rows (no residual slab to share)
         int conv;                   // 0: plain GEMM, 1: 3x3 stride-1 pad-1 implicit GEMM over NHWC
+        int tile_m;                 // output rows (pixels) per M tile: 128, or less when a conv tile is a whole number of image rows
+        int a_tx_bytes;             // conv: bytes one activation box delivers (tile_m * 128)
         int H, W, rows_per_tile;    // conv: image rows covered by one 128-pixel tile (0 if a tile spans whole images)
         int cblk0, cblk1, C0, C1;   // conv: 64-channel blocks / channels of source 0 and source 1 (concat fusion)
         GemmEpilogue ep;

@@ -64,7 +64,11 @@ def test_gemm_tcgen05_matches_numpy(G, M, N, K):
 
 @pytest.mark.parametrize("n_img,H,Wd,C0,C1,OC", [(2, 32, 32, 96, 0, 96), (3, 16, 16, 128, 128, 128), (5, 8, 8, 160, 160, 160),
                                                   (1, 8, 8, 64, 0, 80), (2, 64, 64, 48, 0, 48), (3, 4, 4, 80, 80, 80),
-                                                  (1, 16, 16, 24, 24, 24)])
+                                                  (1, 16, 16, 24, 24, 24),
+                                                  # widths that do not divide 128: a tile is a whole number of image rows / images
+                                                  (2, 24, 24, 96, 0, 96), (3, 40, 40, 96, 96, 96), (2, 20, 20, 128, 0, 128),
+                                                  (4, 10, 10, 160, 160, 160), (5, 12, 12, 64, 0, 64), (3, 6, 6, 80, 0, 80),
+                                                  (1, 28, 56, 48, 0, 48), (7, 5, 5, 32, 0, 40)])
 def test_conv3x3_tcgen05_matches_numpy(G, n_img, H, Wd, C0, C1, OC):
     L = G.lib_ggml()
     rng = np.random.default_rng(H * 31 + C0 + OC)
@@ -230,6 +234,19 @@ def test_unmodified_reference_rnn_runs_on_libggml_b200(G, tmp_path):
     assert n_cmp > len(prompt) + 20, margins[:40]
     assert got[:n_cmp] == ref_text[:n_cmp], (got[:80], ref_text[:80])
     print("GRU: %d of %d generated tokens compared equal; min margin %.3g" % (n_cmp, len(ref_text), min(margins)))
+
+
+@pytest.mark.parametrize("hw", [192, 320])
+def test_fast_mode_at_resolutions_whose_maps_do_not_divide_128(G, oracle, weight_files, hw):
+    """192 / 320 / 384 / 448 give 24 / 40 / 48 / 56-wide maps in the first ViT block: the fused plan must still cover them."""
+    from ggml_experiments_b200 import mobilevit as MV
+    imgs = W.synthetic_images(2, hw, hw, seed=7)
+    ref_f, ref_p = oracle.OracleModel(weight_files["xs"]).forward(imgs)
+    feat, pooled, info = _run_model(G, weight_files["xs"], imgs, MV.FAST)
+    assert info["mode"] == MV.FAST, info
+    r = parity_report(feat, ref_f, rtol=1e-2, atol_rms=1e-2)
+    assert r["violations"] <= r["n"] * 1e-4 and r["rel_l2"] < 5e-3, r
+    assert top1_report(pooled, ref_p)["agree"] == 1.0
 
 
 def test_non_square_and_odd_batch_fast_equals_exact(G, weight_files):
