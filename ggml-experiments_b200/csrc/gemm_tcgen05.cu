@@ -58,11 +58,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
+#ifndef GGML_B200_GEMM_WAIT_NS
+#define GGML_B200_GEMM_WAIT_NS 32
+#endif
 // Bounded wait: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#if GGML_B200_GEMM_WAIT_NS > 0
+        __nanosleep(GGML_B200_GEMM_WAIT_NS);  // park the polling warp: it shares a scheduler with two epilogue warps
+#endif
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
