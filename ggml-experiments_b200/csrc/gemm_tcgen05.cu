@@ -572,7 +572,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
         }
-        if (f_warp ? lane == 0 : leader) tma_store_wait_all();  // all bulk stores have been written before the CTA exits
+        // the staging slabs must have been READ by the TMA before the CTA (and its shared memory) goes away; the global writes
+        // themselves complete by grid end (same contract as CUTLASS's tma_store_wait), no need to wait for them here
+        if (f_warp ? lane == 0 : leader) tma_store_wait_read();
     }
     tc_fence_before();
     __syncthreads();
