@@ -577,13 +577,16 @@ constexpr int kAttnLK = 256;  // keys staged in shared memory at a time
 
 template <int DP>
 __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict__ qkv, int H, int W, int C, int heads, int d,
-                                                       __half * __restrict__ out, float sl2, int lk) {
+                                                       __half * __restrict__ out, float sl2, int lk, int qblocks) {
     constexpr int LDS = DP + 8;  // padded smem row (halves): conflict-free ldmatrix
     constexpr int KS  = DP / 16; // k-steps of Q K^T
     constexpr int DT  = DP / 8;  // n-tiles of P V
     extern __shared__ __align__(16) unsigned char smem_attn[];
+    // qblocks > 1 (whole sequence staged once, L <= kAttnLK): the CTA walks all 128-query blocks of its (sequence, head) against
+    // one copy of K/V -- half the K/V loads and half the load-phase stalls per unit of work at L = 256
+    const int qrows = kAttnQB * qblocks;
     __half * sQ = reinterpret_cast<__half *>(smem_attn);
-    __half * sK = sQ + kAttnQB * LDS;
+    __half * sK = sQ + qrows * LDS;
     __half * sV = sK + lk * LDS;  // lk = min(L, kAttnLK) keys staged at a time
 
     const int npw = W >> 1, nph = H >> 1, L = npw * nph;
@@ -596,8 +599,8 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
         const int iph = l / npw, ipw = l - iph * npw;
         return ((int64_t)n * H + (iph * 2 + ph)) * W + (ipw * 2 + pw);
     };
-    const int q0 = blockIdx.y * kAttnQB;
-    const int nq = min(kAttnQB, L - q0);
+    const int qbase = blockIdx.y * qrows;
+    const int nqall = min(qrows, L - qbase);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
@@ -610,20 +613,43 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
     const int  step_h = rpp / npw, step_w = rpp - step_h * npw;  // rpp rows further = step_h grid rows + step_w columns
     auto row_token = [&](int iph, int ipw) -> int64_t { return ((int64_t)n * H + (iph * 2 + ph)) * W + (ipw * 2 + pw); };
     {
-        int l0 = q0 + lrow, iph = l0 / npw, ipw = l0 - iph * npw;
-        for (int r = lrow; r < nq; r += rpp) {
+        int l0 = qbase + lrow, iph = l0 / npw, ipw = l0 - iph * npw;
+        for (int r = lrow; r < nqall; r += rpp) {
             if (lact) cp_async16(sQ + r * LDS + lchunk * 8, qkv + row_token(iph, ipw) * ld + head * DP + lchunk * 8);
             iph += step_h; ipw += step_w;
             if (ipw >= npw) { ipw -= npw; iph++; }
         }
     }
 
-    const bool warp_active = warp * 16 < nq;
     uint32_t qf[KS][4];
     float    o[DT][4];
-    float    m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float    m[2], l[2];
+    auto reset = [&]() {
+        m[0] = m[1] = -INFINITY;
+        l[0] = l[1] = 0.f;
 #pragma unroll
-    for (int i = 0; i < DT; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        for (int i = 0; i < DT; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    };
+    auto finish = [&](int q0) {  // normalise and store this warp's 16 query rows
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+            l[r] = 1.f / l[r];
+        }
+        const int qa = q0 + warp * 16 + g, qb = qa + 8;
+        __half *  oa = out + tok(qa) * (int64_t)C + head * d;
+        __half *  ob = out + tok(qb) * (int64_t)C + head * d;
+#pragma unroll
+        for (int i = 0; i < DT; i++) {
+            const int col = i * 8 + 2 * t;
+            if (col < d) {
+                *reinterpret_cast<__half2 *>(oa + col) = __floats2half2_rn(o[i][0] * l[0], o[i][1] * l[0]);
+                *reinterpret_cast<__half2 *>(ob + col) = __floats2half2_rn(o[i][2] * l[1], o[i][3] * l[1]);
+            }
+        }
+    };
+    reset();
 
     for (int kc0 = 0; kc0 < L; kc0 += kAttnLK) {
         const int nk = min(kAttnLK, L - kc0);
@@ -642,38 +668,28 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
         }
         cp_async_wait_all();
         __syncthreads();
-        if (!warp_active) continue;
-        if (kc0 == 0) {
-#pragma unroll
-            for (int ks = 0; ks < KS; ks++) ldmatrix_x4(qf[ks], sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
-        }
         // per-lane ldmatrix base addresses in the shared window (one cvta per chunk instead of one per ldmatrix)
         const uint32_t kaddr0 = (uint32_t)__cvta_generic_to_shared(sK + (((lane >> 4) * 8 + (lane & 7)) * LDS + ((lane >> 3) & 1) * 8));
         const uint32_t vaddr0 = (uint32_t)__cvta_generic_to_shared(sV + ((((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + (lane >> 4) * 8));
-        for (int kb = 0; kb < nk; kb += 64) {
-            const uint32_t kaddr = kaddr0 + (uint32_t)(kb * LDS * 2), vaddr = vaddr0 + (uint32_t)(kb * LDS * 2);
-            if (nk - kb >= 64) attn_block<DP, 8>(qf, o, m, l, kaddr, vaddr, sl2, 8);
-            else attn_block<DP, 0>(qf, o, m, l, kaddr, vaddr, sl2, (nk - kb) >> 3);
+        for (int qb = 0; qb < qblocks; qb++) {
+            const int qoff = qb * kAttnQB;
+            if (qoff + warp * 16 >= nqall) break;  // this warp has no query rows in this block (nor in later ones)
+            if (kc0 == 0 || qblocks > 1) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) ldmatrix_x4(qf[ks], sQ + (qoff + warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
+            }
+            for (int kb = 0; kb < nk; kb += 64) {
+                const uint32_t kaddr = kaddr0 + (uint32_t)(kb * LDS * 2), vaddr = vaddr0 + (uint32_t)(kb * LDS * 2);
+                if (nk - kb >= 64) attn_block<DP, 8>(qf, o, m, l, kaddr, vaddr, sl2, 8);
+                else attn_block<DP, 0>(qf, o, m, l, kaddr, vaddr, sl2, (nk - kb) >> 3);
+            }
+            if (qblocks > 1) {  // the whole sequence was in this chunk: this block is complete
+                finish(qbase + qoff);
+                reset();
+            }
         }
     }
-    if (!warp_active) return;
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
-        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
-        l[r] = 1.f / l[r];
-    }
-    const int     qa = q0 + warp * 16 + g, qb = qa + 8;
-    __half *      oa = out + tok(qa) * (int64_t)C + head * d;
-    __half *      ob = out + tok(qb) * (int64_t)C + head * d;
-#pragma unroll
-    for (int i = 0; i < DT; i++) {
-        const int col = i * 8 + 2 * t;
-        if (col < d) {
-            *reinterpret_cast<__half2 *>(oa + col) = __floats2half2_rn(o[i][0] * l[0], o[i][1] * l[0]);
-            *reinterpret_cast<__half2 *>(ob + col) = __floats2half2_rn(o[i][2] * l[1], o[i][3] * l[1]);
-        }
-    }
+    if (qblocks == 1 && warp * 16 < nqall) finish(qbase);
 }
 
 // CUDA-core fallback for sequence lengths that are not a multiple of 16 (tiny feature maps); same qkv layout.
@@ -766,14 +782,16 @@ void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads,
     if (L % 16 == 0 && getenv("GGML_B200_ATTN_V1") == nullptr) {
         const int    warps = L >= kAttnQB ? 8 : L / 16;
         const int    lk    = L < kAttnLK ? L : kAttnLK;
-        const size_t smem  = (size_t)(kAttnQB + 2 * lk) * (dp + 8) * sizeof(__half);
-        dim3         grid(N * 4 * heads, (L + kAttnQB - 1) / kAttnQB);
+        const int    nqb   = (L + kAttnQB - 1) / kAttnQB;
+        const int    qblocks = (L <= kAttnLK && nqb > 1 && getenv("GGML_B200_ATTN_QB1") == nullptr) ? nqb : 1;
+        const size_t smem  = (size_t)(kAttnQB * qblocks + 2 * lk) * (dp + 8) * sizeof(__half);
+        dim3         grid(N * 4 * heads, nqb / qblocks);
         const float  sl2 = 1.4426950408889634f / sqrtf((float)d);  // log2(e) / sqrt(d)
         switch (dp) {
-            case 16: k_attention_mma<16><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
-            case 32: k_attention_mma<32><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
-            case 48: k_attention_mma<48><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
-            default: k_attention_mma<64><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk); break;
+            case 16: k_attention_mma<16><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            case 32: k_attention_mma<32><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            case 48: k_attention_mma<48><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            default: k_attention_mma<64><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
         }
         return;
     }
