@@ -208,11 +208,14 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ("value") -------------------------------------------------------------
+    # the clock sampler (nvidia-smi -lms 100) needs a few hundred ms to deliver its first row, more on an 8-GPU box, while the
+    # timed region is ~0.1 s: it is started before the warm-up so that it is already streaming during the timed steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         model.forward_device(n, h, w)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    n_before = len(sampler.rows)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -220,7 +223,17 @@ def main():
     ev1.record(stream)
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    extra_s = 0.0
+    if len(sampler.rows) - n_before < 2:  # region shorter than the sampling period: keep the identical load running until sampled
+        t_extra = time.perf_counter()
+        while len(sampler.rows) - n_before < 2 and time.perf_counter() - t_extra < 3.0:
+            for _ in range(4):
+                model.forward_device(n, h, w)
+            torch.cuda.synchronize()
+        extra_s = time.perf_counter() - t_extra
+    sampler.rows = sampler.rows[n_before:]
     clocks = sampler.stop()
+    clocks["window"] = "timed steps" if extra_s == 0.0 else f"timed steps + {extra_s:.2f} s of the identical load (region shorter than the 100 ms sampling period)"
     value = args.batch * world * args.steps / (dev_ms / 1e3)
 
     # ---- end to end through the host API ("e2e") ------------------------------------------------------------
@@ -258,12 +271,13 @@ def main():
 
     # Same pipeline fed with uint8 images: the resize / 1/255 of sam_image_preprocess (main.cpp:538-601) runs on
     # the device, 4x fewer bytes cross PCIe.  Reported next to the f32 headline, not instead of it.
-    img_u8 = np.random.default_rng(3).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    img_u8 = np.clip(np.rint(host_in * 255.0), 0, 255).astype(np.uint8)  # the same pictures as the f32 path, as 8-bit pixels
     for s in range(2):
         model.slot_input_u8(n, h, w, s, h, w)[:] = img_u8
         model.slot_submit_u8(n, h, w, s, h, w)
     for s in range(2):
-        model.slot_wait(n, h, w, s)
+        fu, pu = model.slot_wait(n, h, w, s)
+        assert (pu.argmax(1) == pooled0.argmax(1)).mean() > 0.99, "u8 path disagrees with the f32 path on top-1"
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -339,11 +353,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ggml conv rounding points), f32 residual stream",
             "data": "synthetic", "config": dict(workload_config(args), mode=("fast" if info["mode"] == 0 else "exact")),
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mvit_slot_submit/mvit_slot_wait, 2 slots in flight",
-                    "synchronous_call_ms": 1e3 * sync_s / args.steps,
-                    "synchronous_call_images_per_s": args.batch * world * args.steps / sync_s,
-                    "u8_input": e2e_u8},
+            # headline e2e = the reference's own entry: raw u8 images in (what stbi_load hands to sam_image_preprocess, main.cpp:
+            # 517-601), features + logits out; the resize / 1/255 runs on the device.  The f32-image variant (the caller has
+            # already run sam_image_preprocess on the CPU) is reported next to it: 4x the PCIe bytes, and with 8 GPUs on one
+            # host it is bound by host memory / PCIe (133 GB/s aggregate measured), not by the GPUs.
+            "e2e": dict(e2e_u8, f32_input={"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                           "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mvit_slot_submit/mvit_slot_wait, 2 slots in flight",
+                                           "synchronous_call_ms": 1e3 * sync_s / args.steps,
+                                           "synchronous_call_images_per_s": args.batch * world * args.steps / sync_s}),
             "gpu_launches": info["launches"] * args.steps,
             "clocks": clocks,
             "roofline": roofline,
