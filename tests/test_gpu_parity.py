@@ -236,9 +236,10 @@ def test_unmodified_reference_rnn_runs_on_libggml_b200(G, tmp_path):
     print("GRU: %d of %d generated tokens compared equal; min margin %.3g" % (n_cmp, len(ref_text), min(margins)))
 
 
-@pytest.mark.parametrize("hw", [192, 320])
+@pytest.mark.parametrize("hw", [64, 192, 320, 384, 448])
 def test_fast_mode_at_resolutions_whose_maps_do_not_divide_128(G, oracle, weight_files, hw):
-    """192 / 320 / 384 / 448 give 24 / 40 / 48 / 56-wide maps in the first ViT block: the fused plan must still cover them."""
+    """192 / 320 / 384 / 448 give 24 / 40 / 48 / 56-wide maps in the first ViT block: the fused plan must still cover them
+    (384 and 448 also take the multi-chunk K/V path of the attention kernel: 576 / 784 keys); 64 is the smallest valid input."""
     from ggml_experiments_b200 import mobilevit as MV
     imgs = W.synthetic_images(2, hw, hw, seed=7)
     ref_f, ref_p = oracle.OracleModel(weight_files["xs"]).forward(imgs)
