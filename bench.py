@@ -223,6 +223,7 @@ def main():
     ev1.record(stream)
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    info = model.plan_info(n, h, w)  # re-read after the replays: `cuda_graph` says whether they went through the captured graph
     extra_s = 0.0
     if len(sampler.rows) - n_before < 2:  # region shorter than the sampling period: keep the identical load running until sampled
         t_extra = time.perf_counter()

@@ -11,6 +11,7 @@
 //     scale/shift + SiLU, 128-bit coalesced stores (8 lanes = one pixel's 128 bytes).
 #include "gemm_tcgen05.h"
 #include "internal.h"
+#include "pdl.cuh"
 
 namespace b200 {
 
@@ -89,6 +90,8 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();  // PDL: the input tile loads and the output stores below must see the previous kernel complete
+    pdl_trigger();
 
     auto issue = [&](int tile, int buf) {
         int t = tile;
@@ -255,8 +258,8 @@ void dw_launch(const DwLaunch & L, cudaStream_t st) {
         attr = true;
     }
     const int threads = 8 * L.p.TW * L.p.RS;
-    if (L.p.stride == 1) k_dwconv_tma<1><<<L.grid, threads, L.smem_bytes, st>>>(L.map_x, L.p);
-    else k_dwconv_tma<2><<<L.grid, threads, L.smem_bytes, st>>>(L.map_x, L.p);
+    if (L.p.stride == 1) launch_pdl(k_dwconv_tma<1>, dim3(L.grid), dim3(threads), L.smem_bytes, st, L.map_x, L.p);
+    else launch_pdl(k_dwconv_tma<2>, dim3(L.grid), dim3(threads), L.smem_bytes, st, L.map_x, L.p);
 }
 
 }  // namespace b200

@@ -3,6 +3,7 @@
 #include "fast_kernels.h"
 
 #include "internal.h"
+#include "pdl.cuh"
 
 namespace b200 {
 
@@ -173,6 +174,8 @@ __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, 
     const int n   = b / tiles_y;
     const int iy0 = 2 * ty0 - 1, ix0 = 2 * tx0 - 1;
     const float * xn = x + n * sn;
+    pdl_wait();  // PDL: weights / scale / shift above are constants; the image and the output are not
+    pdl_trigger();
     // stage the (2*TH+2) x (2*TW+1) x 3 patch as f16 (ggml's im2col rounding point); warp = row, lanes = (x, c) pairs
     for (int yy = warp; yy < IH + 1; yy += 8) {
         const int  iy     = iy0 + yy;
@@ -236,10 +239,10 @@ void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc
     static const bool v1 = getenv("GGML_B200_STEM_V1") != nullptr;
     if (!out32 && out16 && !v1) {
         switch (OC) {
-            case 8: k_stem_mma<8><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
-            case 16: k_stem_mma<16><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
-            case 24: k_stem_mma<24><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
-            case 32: k_stem_mma<32><<<grid, 256, 0, st>>>(x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 8: launch_pdl(k_stem_mma<8>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 16: launch_pdl(k_stem_mma<16>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 24: launch_pdl(k_stem_mma<24>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 32: launch_pdl(k_stem_mma<32>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
             default: break;
         }
     }
@@ -601,6 +604,8 @@ __global__ void __launch_bounds__(256) k_attention_mma(const __half * __restrict
     };
     const int qbase = blockIdx.y * qrows;
     const int nqall = min(qrows, L - qbase);
+    pdl_wait();  // PDL: q/k/v come from the previous kernel
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
@@ -788,10 +793,10 @@ void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads,
         dim3         grid(N * 4 * heads, nqb / qblocks);
         const float  sl2 = 1.4426950408889634f / sqrtf((float)d);  // log2(e) / sqrt(d)
         switch (dp) {
-            case 16: k_attention_mma<16><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
-            case 32: k_attention_mma<32><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
-            case 48: k_attention_mma<48><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
-            default: k_attention_mma<64><<<grid, warps * 32, smem, st>>>(qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            case 16: launch_pdl(k_attention_mma<16>, grid, dim3(warps * 32), smem, st, qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            case 32: launch_pdl(k_attention_mma<32>, grid, dim3(warps * 32), smem, st, qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            case 48: launch_pdl(k_attention_mma<48>, grid, dim3(warps * 32), smem, st, qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
+            default: launch_pdl(k_attention_mma<64>, grid, dim3(warps * 32), smem, st, qkv, H, W, C, heads, d, out16, sl2, lk, qblocks); break;
         }
         return;
     }
@@ -827,6 +832,8 @@ void launch_add(const float * a, const float * b, int64_t n, float * out32, __ha
 
 // NHWC -> [W,H,C,N] f32 via a 32x32 smem transpose of (pixel, channel) per image
 __global__ void k_nhwc_to_nchw(const __half * __restrict__ x16, const float * __restrict__ x32, int HW, int C, float * __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tile[32][33];
     const int     n  = blockIdx.z;
     const int     p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -846,10 +853,12 @@ __global__ void k_nhwc_to_nchw(const __half * __restrict__ x16, const float * __
 void launch_nhwc_to_nchw(const __half * x16, const float * x32, int N, int H, int W, int C, float * out, cudaStream_t st) {
     const int HW = H * W;
     dim3      grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-    k_nhwc_to_nchw<<<grid, block, 0, st>>>(x16, x32, HW, C, out);
+    launch_pdl(k_nhwc_to_nchw, grid, block, 0, st, x16, x32, HW, C, out);
 }
 
 __global__ void k_pool_mean(const __half * __restrict__ x16, const float * __restrict__ x32, int HW, int C, float * __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int n = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -860,7 +869,7 @@ __global__ void k_pool_mean(const __half * __restrict__ x16, const float * __res
 }
 void launch_pool_mean(const __half * x16, const float * x32, int N, int HW, int C, float * out, cudaStream_t st) {
     dim3 grid((C + 127) / 128, N);
-    k_pool_mean<<<grid, 128, 0, st>>>(x16, x32, HW, C, out);
+    launch_pdl(k_pool_mean, grid, dim3(128), 0, st, x16, x32, HW, C, out);
 }
 
 // small device-to-device copy as a kernel: between two CUDA-graph launches a copy-engine memcpy costs two engine hand-overs

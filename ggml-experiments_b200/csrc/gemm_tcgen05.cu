@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "pdl.cuh"
 
 namespace b200 {
 
@@ -270,6 +271,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above (barriers, TMEM, per-column constants) overlapped the tail of the previous kernel; activations,
+    // residuals and row statistics are only touched, and outputs only written, once that kernel has completed
+    pdl_wait();
+    pdl_trigger();
 
     const int cblk_tot = p.cblk0 + p.cblk1;
 
@@ -845,7 +850,7 @@ static void gemm_launch_variant(const GemmLaunch & L, cudaStream_t st) {
         B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k_gemm_tcgen05<EPI><<<L.grid, kThreads, L.smem_bytes, st>>>(L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
+    launch_pdl(k_gemm_tcgen05<EPI>, L.grid, dim3(kThreads), L.smem_bytes, st, L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
 }
 
 void gemm_launch(const GemmLaunch & L, cudaStream_t st) {
