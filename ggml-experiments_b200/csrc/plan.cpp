@@ -134,6 +134,7 @@ void * device_ptr_of(Plan * plan, const ggml_tensor * t) {
 // ---- plan registry ------------------------------------------------------------------------------------
 static std::mutex                               g_plans_mu;
 static std::multimap<ggml_context *, Plan *>    g_plans;
+static std::mutex g_reg_mu;  // guards g_external / g_feedback (one host thread per device may register concurrently)
 static std::unordered_map<const ggml_tensor *, void *> g_external;  // leaf -> caller-owned device memory
 static std::unordered_map<const ggml_cgraph *, std::vector<std::pair<ggml_tensor *, ggml_tensor *>>> g_feedback;
 
@@ -175,6 +176,7 @@ void destroy_plans_of(ggml_context * ctx) {
     // mem_buffer usually does), and a stale feedback pair would then point at unrelated tensors
     const char * lo = ctx->mem_buffer, * hi = ctx->mem_buffer + ctx->mem_size;
     auto inside = [&](const void * p) { return (const char *)p >= lo && (const char *)p < hi; };
+    std::lock_guard<std::mutex> rk(g_reg_mu);
     for (auto it = g_feedback.begin(); it != g_feedback.end();) it = inside(it->first) ? g_feedback.erase(it) : std::next(it);
     for (auto it = g_external.begin(); it != g_external.end();) it = inside(it->first) ? g_external.erase(it) : std::next(it);
 }
@@ -185,6 +187,12 @@ void destroy_plans_of(ggml_context * ctx) {
 //   * leafs of the compute context, or flagged input/param, are INPUTS: uploaded on every compute
 //     (main.cpp:627-634 writes the image through ggml_get_data; rnn.cpp:303-310 rewrites id and state).
 static void place_leafs(Plan * plan, ggml_cgraph * gf) {
+    std::unordered_map<const ggml_tensor *, void *> g_external_snapshot;
+    {
+        std::lock_guard<std::mutex> rk(g_reg_mu);
+        g_external_snapshot = g_external;
+    }
+    const auto & g_external = g_external_snapshot;  // shadows the global inside this function
     int64_t const_bytes = 0, input_bytes = 0;
     auto    is_input    = [&](const ggml_tensor * t) {
         if (t->flags & 0x100) return false;
@@ -286,9 +294,14 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
     }
     // device-side feedback copies (autoregressive loops): node -> input leaf, after the last kernel of each compute
     {
-        auto fb = g_feedback.find(gf);
-        if (fb != g_feedback.end())
-            for (auto & pr : fb->second) {
+        std::vector<std::pair<ggml_tensor *, ggml_tensor *>> feedback;
+        {
+            std::lock_guard<std::mutex> rk(g_reg_mu);
+            auto fb = g_feedback.find(gf);
+            if (fb != g_feedback.end()) feedback = fb->second;
+        }
+        if (!feedback.empty())
+            for (auto & pr : feedback) {
                 void *       src   = device_ptr_of(plan, pr.first);
                 void *       dst   = device_ptr_of(plan, pr.second);
                 const size_t bytes = (size_t)ggml_nelements(pr.second) * ggml_type_size(pr.second->type);
@@ -512,6 +525,7 @@ extern "C" int ggml_b200_tensor_download(struct ggml_cgraph * gf, struct ggml_te
 
 extern "C" void ggml_b200_graph_add_feedback(struct ggml_cgraph * gf, struct ggml_tensor * src, struct ggml_tensor * dst) {
     GGML_ASSERT(dst->op == GGML_OP_NONE);
+    std::lock_guard<std::mutex> rk(g_reg_mu);
     g_feedback[gf].push_back({src, dst});
 }
 
@@ -538,6 +552,7 @@ extern "C" void   ggml_b200_synchronize(void) { ensure_device(); B200_CHECK(cuda
 
 extern "C" void ggml_b200_tensor_set_device_data(struct ggml_tensor * leaf, void * device_ptr) {
     GGML_ASSERT(leaf->op == GGML_OP_NONE && leaf->view_src == nullptr);
+    std::lock_guard<std::mutex> rk(g_reg_mu);
     if (device_ptr) g_external[leaf] = device_ptr; else g_external.erase(leaf);
 }
 extern "C" void * ggml_b200_tensor_get_device_data(struct ggml_cgraph * gf, struct ggml_tensor * t) {
