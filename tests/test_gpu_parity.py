@@ -412,3 +412,24 @@ def test_full_size_batch_256_is_batch_independent_and_matches_the_oracle_sample(
     t = top1_report(pooled8, ref_p)
     assert r["violations"] <= r["n"] * 1e-4 and r["rel_l2"] < 5e-3, r
     assert t["agree"] == 1.0, t
+
+
+@pytest.mark.parametrize("variant,hw", [("s", 256), ("xxs", 128), ("xs", 192)])
+def test_every_batch_size_gives_the_same_bits_per_image(G, weight_files, variant, hw):
+    """Tail handling of every kernel (partial M tiles, partial depthwise tiles, odd image counts per conv tile, attention grids):
+    for batch sizes that are not multiples of anything, image i must come out bit-identical to the same image in a batch of 8."""
+    from ggml_experiments_b200 import mobilevit as MV
+    base = W.synthetic_images(8, hw, hw, seed=7)
+    MV.set_mode(MV.FAST)
+    m = G.MobileViT(weight_files[variant])
+    try:
+        feat8, pooled8 = m.extract_features(base)
+        for b in (1, 2, 3, 5, 7, 9, 33, 100, 255, 257):
+            imgs = base[np.arange(b) % 8]
+            feat, pooled = m.extract_features(imgs)
+            assert m.plan_info(b, hw, hw)["mode"] == MV.FAST
+            np.testing.assert_array_equal(feat, feat8[np.arange(b) % 8], err_msg=f"batch {b}")
+            np.testing.assert_array_equal(pooled, pooled8[np.arange(b) % 8], err_msg=f"batch {b}")
+            m.release(b, hw, hw)
+    finally:
+        m.close()
