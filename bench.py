@@ -112,7 +112,7 @@ def run_reference(args, weight_path: str):
     return {
         "impl": "reference", "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16 conv operands / f32 accumulate, f32 dense (ggml CPU semantics)",
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f16 conv operands / f32 accumulate, f32 dense (ggml CPU semantics)",
         "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
                          "note": "CPU oracle restatement of the reference's ggml algorithm; upstream ggml is not vendored"},
@@ -122,15 +122,16 @@ def run_reference(args, weight_path: str):
 
 
 def metric_name(args):
-    return f"MobileViT-{args.variant.upper()} images/sec at batch {args.batch}"
+    return f"MobileViT-{args.variant.upper()} images/sec at batch {args.global_images if args.strong else args.batch}" + (" (total, strong scaling)" if args.strong else "")
 
 
 def workload_config(args):
     return {"workload": f"MobileViT-{args.variant.upper()} forward (extract_features), conv weights f16, {args.hw}x{args.hw} synthetic images, "
                         f"random-init weights in convert-tf-to-ggml layout",
-            "variant": args.variant, "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "image": args.hw,
+            "variant": args.variant, "per_gpu_batch": args.batch, "global_batch": args.global_images, "image": args.hw,
             "parallelism": f"independent sub-batches x{args.gpus} (no collective)",
-            "l2": "inputs larger than L2: %.0f MB of f32 images per step per GPU" % (args.batch * args.hw * args.hw * 12 / 1e6)}
+            "l2": ("inputs larger than L2: %.0f MB of f32 images per step per GPU" if args.batch * args.hw * args.hw * 12 > 126e6 else
+                   "%.0f MB of f32 images per step per GPU (< L2), evicted between steps by the forward itself, which streams its whole activation arena through L2") % (args.batch * args.hw * args.hw * 12 / 1e6)}
 
 
 def main():
@@ -140,7 +141,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="s", choices=["s", "xs", "xxs"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU (with --strong: images in total)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --batch images in TOTAL, batch/N per GPU (BASELINE configs[2] as literally written: 256/128/64/32 "
+                         "per GPU on 1/2/4/8 GPUs); the default is weak scaling, 256 per GPU")
     ap.add_argument("--hw", type=int, default=256)
     ap.add_argument("--mode", default=os.environ.get("GGML_B200_MODE", "fast"), choices=["fast", "exact"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
@@ -151,6 +155,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.global_images = args.batch * (1 if args.strong else max(args.gpus, world))
+    if args.strong:  # the total stays --batch; every GPU takes an equal share
+        if args.batch % world:
+            raise SystemExit(f"--strong: batch {args.batch} is not divisible by {world} GPUs")
+        args.batch //= world
 
     from ggml_experiments_b200 import weights as W
     tmpdir = tempfile.mkdtemp(prefix=f"mvit_bench_r{rank}_")
@@ -351,7 +360,7 @@ def main():
         per_gpu = value / world
         out = {
             "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ggml conv rounding points), f32 residual stream",
             "data": "synthetic", "config": dict(workload_config(args), mode=("fast" if info["mode"] == 0 else "exact")),
             # headline e2e = the reference's own entry: raw u8 images in (what stbi_load hands to sam_image_preprocess, main.cpp:
