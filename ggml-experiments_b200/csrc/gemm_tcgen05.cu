@@ -661,6 +661,17 @@ static void choose_tiling(GemmLaunch & L, int N) {
     p.n_tiles              = (N + max_bn - 1) / max_bn;
     int per                = (N + p.n_tiles - 1) / p.n_tiles;
     p.block_n              = p.n_tiles > 1 ? (per + 63) / 64 * 64 : (per + 31) / 32 * 32;
+    // Small problems (few M tiles: small batches, the last ViT block) are latency chains of K blocks on a handful of SMs:
+    // spread them over more SMs by splitting N into 64-column tiles while (M tiles x N tiles) stays below half the SMs.
+    if (!p.ep.stats_out && getenv("GGML_B200_GEMM_BN") == nullptr && getenv("GGML_B200_GEMM_NO_NSPLIT") == nullptr) {
+        const int mt = (p.M + p.tile_m - 1) / p.tile_m;
+        while (p.block_n > 64 && 2 * mt * p.n_tiles <= runtime().sm_count) {
+            const int nb = ((p.block_n / 2) + 63) / 64 * 64;
+            if (nb >= p.block_n) break;
+            p.block_n = nb;
+            p.n_tiles = (N + nb - 1) / nb;
+        }
+    }
     // accumulator stages in TMEM (tile i+1.. accumulate while tile i drains); power-of-two column count >= 32.  Narrow tiles
     // take 4 stages: with one 64-column chunk per tile the MMA turnaround after a release would otherwise be exposed
     p.acc_stages           = (p.block_n <= 64 && getenv("GGML_B200_GEMM_ACC2") == nullptr) ? 4 : 2;
