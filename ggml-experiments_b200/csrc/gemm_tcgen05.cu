@@ -271,8 +271,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // PDL: everything above (barriers, TMEM, per-column constants) overlapped the tail of the previous kernel; activations,
-    // residuals and row statistics are only touched, and outputs only written, once that kernel has completed
+    // The resident weight tile is a constant: its TMA loads are issued before the PDL wait so that they, too, overlap the
+    // tail of the previous kernel (both producer flavours: one k-block per load, num_kb == 1 in the cp.async mode)
+    if (warp == 0 && lane == 0 && p.b_resident && (int)blockIdx.x < num_m_tiles) {
+        mbar_expect_tx(smem_u32(bres_full), (uint32_t)(p.num_kb * b_bytes));
+        for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(smem_u32(smem_bres + (size_t)kb * b_bytes), &map_b, kb * p.kb_elems, n0, smem_u32(bres_full));
+    }
+    // PDL: everything above (barriers, TMEM, per-column constants, weights) overlapped the tail of the previous kernel;
+    // activations, residuals and row statistics are only touched, and outputs only written, once that kernel has completed
     pdl_wait();
     pdl_trigger();
 
@@ -296,11 +302,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
             if (lane == 0) {
                 if (p.b_resident) {
-                    if (it == 0) {  // the (single k-block) weight tile, once
-                        mbar_expect_tx(smem_u32(bres_full), (uint32_t)b_bytes);
-                        tma_load_2d(smem_u32(smem_bres), &map_b, 0, n0, smem_u32(bres_full));
-                    }
-                    mbar_arrive(fb);
+                    mbar_arrive(fb);  // the weight tile was requested before the PDL wait
                 } else {
                     mbar_expect_tx(fb, (uint32_t)b_bytes);
                     tma_load_2d(sa + a_bytes, &map_b, 0, n0, fb);
@@ -322,10 +324,6 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;  // k-block counter across all tiles of this CTA
-            if (p.b_resident && (int)blockIdx.x < num_m_tiles) {
-                mbar_expect_tx(smem_u32(bres_full), (uint32_t)(p.num_kb * b_bytes));
-                for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(smem_u32(smem_bres + (size_t)kb * b_bytes), &map_b, kb * p.kb_elems, n0, smem_u32(bres_full));
-            }
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
                 const int m0 = tile * tile_m;
                 int img = 0, y0 = 0;
