@@ -2,6 +2,7 @@
 // tests can check each kernel against the oracle / numpy before it is trusted inside a fused plan.
 #include <vector>
 
+#include "fast_kernels.h"
 #include "gemm_tcgen05.h"
 #include "internal.h"
 
@@ -62,6 +63,193 @@ extern "C" int ggml_b200_debug_conv3x3(const uint16_t * x0, int C0, const uint16
     B200_CHECK(cudaStreamSynchronize(st));
     B200_CHECK(cudaMemcpy(out32, dO.p, px * OC * 4, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// K3 in isolation: depthwise 3x3 (stride 1|2, pad 1) + scale/shift + SiLU.  x [N,H,W,C] f16, Wt [3][3][C] f16, out [N,H/s,W/s,C] f16.
+// variant 0 = the TMA kernel of the fused plan (k_dwconv_tma), 1 = the register-window fallback (k_dwconv).
+extern "C" int ggml_b200_debug_dwconv(const uint16_t * x, int N, int H, int W, int C, int stride, const uint16_t * Wt, const float * scale,
+                                      const float * shift, int act, int variant, uint16_t * out16) {
+    ensure_device();
+    if (stride < 1 || H % stride || W % stride) return 1;
+    const size_t in_e = (size_t)N * H * W * C, out_e = (size_t)N * (H / stride) * (W / stride) * C;
+    DevBuf dX(x, in_e * 2), dW(Wt, (size_t)9 * C * 2), dS(scale, scale ? (size_t)C * 4 : 0), dH(shift, shift ? (size_t)C * 4 : 0), dO(nullptr, out_e * 2);
+    cudaStream_t st = current_stream();
+    if (variant == 0) {
+        DwLaunch L;
+        if (!dw_prepare(L, (const __half *)dX.p, N, H, W, C, stride, (const __half *)dW.p, (const float *)dS.p, (const float *)dH.p, act, (__half *)dO.p)) return 1;
+        dw_launch(L, st);
+    } else {
+        launch_dwconv((const __half *)dX.p, N, H, W, C, stride, (const __half *)dW.p, (const float *)dS.p, (const float *)dH.p, act, (__half *)dO.p, st);
+    }
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    B200_CHECK(cudaMemcpy(out16, dO.p, out_e * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// K2 in isolation: stem 3x3 / stride 2 / pad 1 over f32 images (HWC: chw == 0, CHW: chw == 1), Wt [OC][3][3][3] f16.
+extern "C" int ggml_b200_debug_stem(const float * x, int chw, int N, int H, int W, const uint16_t * Wt, int OC, const float * scale, const float * shift,
+                                    int act, uint16_t * out16, float * out32) {
+    ensure_device();
+    if (H % 2 || W % 2) return 1;
+    const size_t out_e = (size_t)N * (H / 2) * (W / 2) * OC;
+    DevBuf dX(x, (size_t)N * H * W * 3 * 4), dW(Wt, (size_t)OC * 27 * 2), dS(scale, scale ? (size_t)OC * 4 : 0), dH(shift, shift ? (size_t)OC * 4 : 0);
+    DevBuf dO16(nullptr, out16 ? out_e * 2 : 0), dO32(nullptr, out32 ? out_e * 4 : 0);
+    int64_t sn, sy, sx, sc;
+    if (chw) { sn = (int64_t)3 * H * W; sy = W; sx = 1; sc = (int64_t)H * W; }
+    else { sn = (int64_t)H * W * 3; sy = (int64_t)W * 3; sx = 3; sc = 1; }
+    cudaStream_t st = current_stream();
+    launch_stem((const float *)dX.p, sn, sy, sx, sc, N, H, W, (const __half *)dW.p, OC, (const float *)dS.p, (const float *)dH.p, act, (__half *)dO16.p,
+                (float *)dO32.p, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    if (out16) B200_CHECK(cudaMemcpy(out16, dO16.p, out_e * 2, cudaMemcpyDeviceToHost));
+    if (out32) B200_CHECK(cudaMemcpy(out32, dO32.p, out_e * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// K7 in isolation.  qkv: f16 [N*H*W][3][heads][DP] (DP = ggml_b200_debug_attention_dp(C/heads), padding zero), pixel order;
+// out: f16 [N*H*W][C].  A sequence = the (H/2)*(W/2) pixels of one image sharing (y%2, x%2)  (main.cpp:721-747, 1073-1086).
+extern "C" int ggml_b200_debug_attention_dp(int d) { return attention_padded_head_dim(d); }
+extern "C" int ggml_b200_debug_attention(const uint16_t * qkv, int N, int H, int W, int C, int heads, uint16_t * out16) {
+    ensure_device();
+    if (heads <= 0 || C % heads || H % 2 || W % 2) return 1;
+    const int    dp = attention_padded_head_dim(C / heads);
+    const size_t px = (size_t)N * H * W;
+    DevBuf dQ(qkv, px * 3 * heads * dp * 2), dO(nullptr, px * C * 2);
+    cudaStream_t st = current_stream();
+    launch_attention((const __half *)dQ.p, N, H, W, C, heads, (__half *)dO.p, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    B200_CHECK(cudaMemcpy(out16, dO.p, px * C * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// LayerNorm folded around two GEMMs, in isolation:
+//   producer  x = A[M,K] . B[C,K]^T + shift0[C]      -> f32 x, f16 x, per-row (sum, sum of squares)
+//   consumer  y = act( LN(x; gamma, beta, eps) . W[N,C]^T + bias[N] ), computed as r * (f16(x) . W'^T - mu * c1) + shift'
+// W is f32 [N][C]; the host folding below is the one fuse.cpp applies (W' = f16(W * gamma), c1 = row sums of W',
+// shift' = bias + sum_k beta_k W[n][k]).  x32 (optional) returns the producer's f32 output for the two-pass reference.
+extern "C" int ggml_b200_debug_gemm_ln(const uint16_t * A, const uint16_t * B, int M, int C, int K, const float * shift0, const float * gamma,
+                                       const float * beta, float eps, const float * Wf, const float * bias, int N, int act, float * x32, float * y32) {
+    ensure_device();
+    if (C > 256 || C % 8 || N % 8 || K % 8) return 1;
+    std::vector<uint16_t> wt((size_t)N * C);
+    std::vector<float>    c1(N), sh(N);
+    for (int n = 0; n < N; n++) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int k = 0; k < C; k++) {
+            const float    w  = Wf[(size_t)n * C + k];
+            const uint16_t wg = ggml_fp32_to_fp16(w * gamma[k]);
+            wt[(size_t)n * C + k] = wg;
+            a1 += (double)ggml_fp16_to_fp32(wg);
+            a2 += (double)beta[k] * (double)w;
+        }
+        c1[n] = (float)a1;
+        sh[n] = (bias ? bias[n] : 0.f) + (float)a2;
+    }
+    DevBuf dA(A, (size_t)M * K * 2), dB(B, (size_t)C * K * 2), dS0(shift0, shift0 ? (size_t)C * 4 : 0);
+    DevBuf dX32(nullptr, (size_t)M * C * 4), dX16(nullptr, (size_t)M * C * 2), dSt(nullptr, (size_t)M * 8);
+    DevBuf dW(wt.data(), wt.size() * 2), dC1(c1.data(), (size_t)N * 4), dSh(sh.data(), (size_t)N * 4), dY(nullptr, (size_t)M * N * 4);
+    GemmEpilogue e0;
+    e0.shift = (const float *)dS0.p;
+    e0.out32 = (float *)dX32.p; e0.ld32 = C;
+    e0.out16 = (__half *)dX16.p; e0.ld16 = C;
+    e0.stats_out = (float *)dSt.p;
+    GemmLaunch L0, L1;
+    if (!gemm_prepare(L0, (const __half *)dA.p, K, (const __half *)dB.p, K, M, C, K, e0)) return 1;
+    GemmEpilogue e1;
+    e1.shift = (const float *)dSh.p;
+    e1.act   = act;
+    e1.out32 = (float *)dY.p; e1.ld32 = N;
+    e1.ln_stats = (const float *)dSt.p;
+    e1.ln_c1    = (const float *)dC1.p;
+    e1.ln_inv_c = 1.0f / (float)C;
+    e1.ln_eps   = eps;
+    if (!gemm_prepare(L1, (const __half *)dX16.p, C, (const __half *)dW.p, C, M, N, C, e1)) return 1;
+    cudaStream_t st = current_stream();
+    gemm_launch(L0, st);
+    gemm_launch(L1, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    if (x32) B200_CHECK(cudaMemcpy(x32, dX32.p, (size_t)M * C * 4, cudaMemcpyDeviceToHost));
+    B200_CHECK(cudaMemcpy(y32, dY.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// K4 in isolation: expand 1x1 (+BN+SiLU) -> depthwise 3x3 (+BN+SiLU) -> reduce 1x1 (+BN) [+ f32 residual].
+// x [N,H,W,Cin], We [E][Cin], Wd [3][3][E], Wr [Cout][E] (all f16); returns 2 if the shape is outside the fused kernel's envelope.
+extern "C" int ggml_b200_debug_ir_fused(const uint16_t * x, int N, int H, int W, int Cin, int E, int Cout, int stride, const uint16_t * We,
+                                        const float * se, const float * he, const uint16_t * Wd, const float * sd, const float * hd, const uint16_t * Wr,
+                                        const float * sr, const float * hr, const float * res32, uint16_t * out16, float * out32) {
+    ensure_device();
+    if (stride < 1 || H % stride || W % stride) return 2;
+    const size_t opx = (size_t)N * (H / stride) * (W / stride);
+    DevBuf dX(x, (size_t)N * H * W * Cin * 2), dWe(We, (size_t)E * Cin * 2), dWd(Wd, (size_t)9 * E * 2), dWr(Wr, (size_t)Cout * E * 2);
+    DevBuf dse(se, (size_t)E * 4), dhe(he, (size_t)E * 4), dsd(sd, (size_t)E * 4), dhd(hd, (size_t)E * 4), dsr(sr, (size_t)Cout * 4), dhr(hr, (size_t)Cout * 4);
+    DevBuf dR(res32, res32 ? opx * Cout * 4 : 0), dO16(nullptr, out16 ? opx * Cout * 2 : 0), dO32(nullptr, out32 ? opx * Cout * 4 : 0);
+    IrLaunch L;
+    if (!ir_fused_prepare(L, (const __half *)dX.p, N, H, W, Cin, E, Cout, stride, (const __half *)dWe.p, (const float *)dse.p, (const float *)dhe.p,
+                          (const __half *)dWd.p, (const float *)dsd.p, (const float *)dhd.p, (const __half *)dWr.p, (const float *)dsr.p,
+                          (const float *)dhr.p, (const float *)dR.p, (__half *)dO16.p, (float *)dO32.p))
+        return 2;
+    cudaStream_t st = current_stream();
+    ir_fused_launch(L, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    if (out16) B200_CHECK(cudaMemcpy(out16, dO16.p, opx * Cout * 2, cudaMemcpyDeviceToHost));
+    if (out32) B200_CHECK(cudaMemcpy(out32, dO32.p, opx * Cout * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+// timing probe (uninitialised device buffers): mean ms per launch of the fused block, and of the three separate kernels it replaces
+extern "C" float ggml_b200_debug_ir_time(int N, int H, int W, int Cin, int E, int Cout, int stride, int with_res, int reps, float * unfused_ms) {
+    ensure_device();
+    const size_t ipx = (size_t)N * H * W, opx = (size_t)N * (H / stride) * (W / stride);
+    DevBuf dX(nullptr, ipx * Cin * 2), dWe(nullptr, (size_t)E * Cin * 2), dWd(nullptr, (size_t)9 * E * 2), dWr(nullptr, (size_t)Cout * E * 2);
+    DevBuf dse(nullptr, (size_t)E * 4), dhe(nullptr, (size_t)E * 4), dsr(nullptr, (size_t)Cout * 4);
+    DevBuf dR(nullptr, with_res ? opx * Cout * 4 : 0), dO16(nullptr, opx * Cout * 2), dO32(nullptr, with_res ? opx * Cout * 4 : 0);
+    DevBuf dE(nullptr, ipx * E * 2), dD(nullptr, opx * E * 2);
+    cudaStream_t st = current_stream();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms = -1.f;
+    IrLaunch L;
+    if (ir_fused_prepare(L, (const __half *)dX.p, N, H, W, Cin, E, Cout, stride, (const __half *)dWe.p, (const float *)dse.p, (const float *)dhe.p,
+                         (const __half *)dWd.p, (const float *)dse.p, (const float *)dhe.p, (const __half *)dWr.p, (const float *)dsr.p,
+                         (const float *)dsr.p, (const float *)dR.p, (__half *)dO16.p, (float *)dO32.p)) {
+        ir_fused_launch(L, st);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < reps; i++) ir_fused_launch(L, st);
+        cudaEventRecord(e1, st);
+        B200_CHECK(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= reps;
+        fprintf(stderr, "ir_fused %dx%dx%d %d->%d->%d s%d: tile %dx%d halo %d rows (%d blocks) NT=%d smem=%zu tmem=%d grid=%d  %.1f us\n", N, H, W, Cin, E, Cout,
+                stride, L.p.TH, L.p.TW, L.p.P_in, L.p.MBI, L.p.nthreads, L.smem_bytes, L.p.tmem_cols, L.grid, 1e3f * ms);
+    }
+    if (unfused_ms) {
+        GemmEpilogue e1x; e1x.scale = (const float *)dse.p; e1x.shift = (const float *)dhe.p; e1x.act = 1; e1x.out16 = (__half *)dE.p; e1x.ld16 = E;
+        GemmEpilogue e3x; e3x.scale = (const float *)dsr.p; e3x.shift = (const float *)dsr.p; e3x.out16 = (__half *)dO16.p; e3x.ld16 = Cout;
+        if (with_res) { e3x.res32 = (const float *)dR.p; e3x.ldr32 = Cout; e3x.out32 = (float *)dO32.p; e3x.ld32 = Cout; }
+        GemmLaunch G1, G3;
+        DwLaunch D;
+        if (gemm_prepare(G1, (const __half *)dX.p, Cin, (const __half *)dWe.p, Cin, (int)ipx, E, Cin, e1x) &&
+            dw_prepare(D, (const __half *)dE.p, N, H, W, E, stride, (const __half *)dWd.p, (const float *)dse.p, (const float *)dhe.p, 1, (__half *)dD.p) &&
+            gemm_prepare(G3, (const __half *)dD.p, E, (const __half *)dWr.p, E, (int)opx, Cout, E, e3x)) {
+            gemm_launch(G1, st); dw_launch(D, st); gemm_launch(G3, st);
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < reps; i++) { gemm_launch(G1, st); dw_launch(D, st); gemm_launch(G3, st); }
+            cudaEventRecord(e1, st);
+            B200_CHECK(cudaStreamSynchronize(st));
+            float u = 0;
+            cudaEventElapsedTime(&u, e0, e1);
+            *unfused_ms = u / reps;
+        } else {
+            *unfused_ms = -1.f;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
 }
 
 // Timing probe for kernel tuning: device buffers only (uninitialised A/B are fine for timing), returns mean ms per launch.

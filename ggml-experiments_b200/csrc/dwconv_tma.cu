@@ -12,47 +12,13 @@
 #include "gemm_tcgen05.h"
 #include "internal.h"
 #include "pdl.cuh"
+#include "ptx_sm100.cuh"
 
 namespace b200 {
 
 namespace {
 
-__device__ __forceinline__ uint32_t dw_smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void dw_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void dw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t dw_mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-__device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity) {
-    if (dw_mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!dw_mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();  // a protocol bug must trap, not hang the GPU
-    }
-}
-__device__ __forceinline__ void dw_tma_load_4d(uint32_t dst, const CUtensorMap * map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ float dw_silu(float x) {
-    const float h = 0.5f * x;
-    float       t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
-}
+using namespace ptx;
 
 // acc[0..7] += x[0..7] * w[0..7] for 8 packed halves each: 8 FHFMA, operands taken from the packed registers (.H0 / .H1)
 __device__ __forceinline__ void dw_fhfma8(float (&acc)[8], const uint4 & x, const uint4 & w) {
@@ -77,7 +43,7 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
     extern __shared__ __align__(128) unsigned char dw_smem[];
     __shared__ __align__(8) uint64_t full_bar[2];
     const uint32_t box_bytes = (uint32_t)p.box_w * p.box_h * 128u;
-    const uint32_t sbase     = dw_smem_u32(dw_smem);
+    const uint32_t sbase     = smem_u32(dw_smem);
 
     const int cg = threadIdx.x & 7;
     const int xl = (threadIdx.x >> 3) % p.TW;
@@ -85,9 +51,9 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
     const int rows_per = p.TH / p.RS;
 
     if (threadIdx.x == 0) {
-        dw_mbar_init(dw_smem_u32(&full_bar[0]), 1);
-        dw_mbar_init(dw_smem_u32(&full_bar[1]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(smem_u32(&full_bar[0]), 1);
+        mbar_init(smem_u32(&full_bar[1]), 1);
+        fence_barrier_init();
     }
     __syncthreads();
     pdl_wait();  // PDL: the input tile loads and the output stores below must see the previous kernel complete
@@ -99,9 +65,9 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int cb = t % p.cblocks;
         const int n  = t / p.cblocks;
-        const uint32_t bar = dw_smem_u32(&full_bar[buf]);
-        dw_mbar_expect_tx(bar, box_bytes);
-        dw_tma_load_4d(sbase + (uint32_t)buf * box_bytes, &map_x, cb * 64, tx * p.TW * STRIDE - 1, ty * p.TH * STRIDE - 1, n, bar);
+        const uint32_t bar = smem_u32(&full_bar[buf]);
+        mbar_expect_tx(bar, box_bytes);
+        tma_load_4d(sbase + (uint32_t)buf * box_bytes, &map_x, cb * 64, tx * p.TW * STRIDE - 1, ty * p.TH * STRIDE - 1, n, bar);
     };
 
     uint32_t it = 0;
@@ -136,7 +102,7 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
                 sh[j] = p.shift ? p.shift[c0 + j] : 0.f;
             }
         }
-        dw_mbar_wait(dw_smem_u32(&full_bar[buf]), (it >> 1) & 1u);
+        mbar_wait(smem_u32(&full_bar[buf]), (it >> 1) & 1u);
         if (lane_ok) {
             // running 32-bit shared addresses and one running output pointer: the row loops carry no index arithmetic
             const uint32_t pitch = (uint32_t)p.box_w * 128u;
@@ -165,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
                 for (int j = 0; j < 4; j++) {
                     float y0 = fmaf(acc[2 * j], sc[2 * j], sh[2 * j]);
                     float y1 = fmaf(acc[2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]);
-                    if (p.act) { y0 = dw_silu(y0); y1 = dw_silu(y1); }
+                    if (p.act) { y0 = silu_f(y0); y1 = silu_f(y1); }
                     o.h[j] = __floats2half2_rn(y0, y1);
                 }
                 *reinterpret_cast<H8 *>(op) = o;

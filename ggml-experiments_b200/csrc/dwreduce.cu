@@ -25,12 +25,6 @@ using namespace ptx;
 
 namespace {
 
-__device__ __forceinline__ float dwr_silu(float x) {
-    const float h = 0.5f * x;
-    float       t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
-}
 __device__ __forceinline__ uint32_t dwr_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
 struct alignas(16) H8 {
@@ -188,7 +182,7 @@ __global__ void __launch_bounds__(288, 2) k_dwreduce(const __grid_constant__ CUt
                         for (int j = 0; j < 4; j++) {
                             float y0 = fmaf(acc[r][2 * j], sc[2 * j], sh[2 * j]);
                             float y1 = fmaf(acc[r][2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]);
-                            if (p.dw_act) { y0 = dwr_silu(y0); y1 = dwr_silu(y1); }
+                            if (p.dw_act) { y0 = silu_f(y0); y1 = silu_f(y1); }
                             if (!lane_ok) { y0 = 0.f; y1 = 0.f; }
                             o.h[j] = __floats2half2_rn(y0, y1);
                         }
@@ -224,7 +218,7 @@ __global__ void __launch_bounds__(288, 2) k_dwreduce(const __grid_constant__ CUt
                             const float s_ = p.r_scale ? __ldg(p.r_scale + nn + j) : 1.f;
                             const float h_ = p.r_shift ? __ldg(p.r_shift + nn + j) : 0.f;
                             y[j] = fmaf(v[g * 8 + j], s_, h_);
-                            if (p.r_act) y[j] = dwr_silu(y[j]);
+                            if (p.r_act) y[j] = silu_f(y[j]);
                         }
                         if (p.res32) {
                             const float4 r0 = *reinterpret_cast<const float4 *>(p.res32 + pix * p.Cout + nn);

@@ -47,7 +47,7 @@ struct FVal {  // an activation in pixel-major NHWC order: [N*H*W, C]
     int64_t rows() const { return (int64_t)N * H * W; }
 };
 
-enum FKind { FK_INPUT, FK_STEM, FK_CONV1, FK_CONV3, FK_DW, FK_LN, FK_LINEAR, FK_QKV, FK_ATTN, FK_ADD, FK_POOL };
+enum FKind { FK_INPUT, FK_STEM, FK_CONV1, FK_CONV3, FK_DW, FK_LN, FK_LINEAR, FK_QKV, FK_ATTN, FK_ADD, FK_POOL, FK_IR };
 
 struct BNParams {
     const ggml_tensor *mean = nullptr, *var = nullptr, *gamma = nullptr, *beta = nullptr;
@@ -71,6 +71,9 @@ struct FNode {
     bool  chw  = false;
     bool  dead = false;
     bool  fused_into_reduce = false;  // depthwise node executed inside the following reduce conv's kernel (K4a)
+    // K4: a reduce conv of kind FK_IR runs the whole inverted residual; ir_expand / ir_dw are the (dead) nodes it absorbed
+    FNode *ir_expand = nullptr, *ir_dw = nullptr;
+    bool   fused_ir  = false;         // this (dead) node's constants are still needed: it runs inside an FK_IR kernel
     int   order = -1;
     // folded constants (offsets into the plan's constant pool)
     int64_t c_w = -1, c_scale = -1, c_shift = -1, c_c1 = -1;
@@ -85,7 +88,17 @@ struct Fail {};  // thrown by matchers; caught in build_fast_plan
 
 // ---- small predicates on ggml tensors ---------------------------------------------------------------------
 bool is_op(const ggml_tensor * t, enum ggml_op op) { return t && t->op == op; }
-bool is_weight_leaf(const ggml_tensor * t) { return t && t->op == GGML_OP_NONE && t->view_src == nullptr && t->data != nullptr; }
+// A leaf may be constant-folded only if the caller cannot rewrite it between computes: leafs flagged input / param are
+// re-uploaded on every compute by the exact plan (place_leafs), so the fused plan must not freeze them either.
+// The same holds for leafs of the compute context itself (place_leafs treats them as per-call inputs), except the
+// ggml_new_f32 scalars (flag 0x100), which are constants by construction.
+thread_local const ggml_context * t_compute_ctx = nullptr;
+bool is_weight_leaf(const ggml_tensor * t) {
+    if (!t || t->op != GGML_OP_NONE || t->view_src != nullptr || t->data == nullptr) return false;
+    if (t->flags & 0x100) return true;
+    if (t->flags & (GGML_TENSOR_FLAG_INPUT | GGML_TENSOR_FLAG_PARAM)) return false;
+    return t->ctx != t_compute_ctx;
+}
 bool same_ne(const ggml_tensor * a, const ggml_tensor * b) {
     return a->ne[0] == b->ne[0] && a->ne[1] == b->ne[1] && a->ne[2] == b->ne[2] && a->ne[3] == b->ne[3];
 }
@@ -479,9 +492,9 @@ struct Planner {
     void fold_constants() {
         for (auto & up : nodes) {
             FNode * n = up.get();
-            if (n->dead) continue;
+            if (n->dead && !n->fused_ir) continue;
             switch (n->kind) {
-                case FK_STEM: case FK_CONV1: case FK_CONV3: case FK_DW: {
+                case FK_STEM: case FK_CONV1: case FK_CONV3: case FK_DW: case FK_IR: {
                     const ggml_tensor * k = n->w;  // f16, ne=(OC,IC,KW,KH): memory index ((kh*KW+kw)*IC+ic)*OC+oc
                     const int OC = (int)k->ne[0], IC = (int)k->ne[1], KW = (int)k->ne[2], KH = (int)k->ne[3];
                     const uint16_t * src = (const uint16_t *)k->data;
@@ -605,6 +618,7 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     Planner P;
     P.plan = plan;
     P.gf   = gf;
+    t_compute_ctx = plan->ctx;
     // graph outputs: every node flagged as output (features, pooled, debug taps)
     std::vector<ggml_tensor *> outs;
     for (int i = 0; i < gf->n_nodes; i++)
@@ -695,6 +709,35 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
         rebuild_users();
     }
 
+    // ---- K4: expand 1x1 (+BN+SiLU) -> depthwise 3x3 (+BN+SiLU) -> reduce 1x1 (+BN) [+ residual] as ONE kernel: the expanded
+    // activation and the depthwise output never reach HBM (inverted_residual_layer::forward, main.cpp:854-870) ----
+    if (!getenv("GGML_B200_NO_IR_FUSE")) {
+        for (auto & up : P.nodes) {
+            FNode * c = up.get();
+            if (c->dead || c->kind != FK_CONV1 || c->ln_g || c->act || !c->has_bn || c->out->need_stats) continue;
+            FVal *  dv = c->in[0];
+            FNode * b  = dv->prod;
+            if (!b || b->dead || b->kind != FK_DW || !b->has_bn || !b->act || dv->users.size() != 1 || out_set.count(dv)) continue;
+            FVal *  ev = b->in[0];
+            FNode * a  = ev->prod;
+            if (!a || a->dead || a->kind != FK_CONV1 || a->res || a->ln_g || !a->act || !a->has_bn || ev->users.size() != 1 || out_set.count(ev) || ev->need_stats) continue;
+            FVal * xv = a->in[0];
+            IrLaunch probe;
+            if (!ir_fused_prepare(probe, nullptr, xv->N, xv->H, xv->W, xv->C, ev->C, c->out->C, b->stride, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr))
+                continue;
+            c->kind      = FK_IR;
+            c->name      = "inverted_residual";
+            c->ir_expand = a;
+            c->ir_dw     = b;
+            c->in[0]     = xv;
+            a->dead = b->dead = true;
+            a->fused_ir = b->fused_ir = true;
+            plan->n_folded += 2;
+        }
+        rebuild_users();
+    }
+
     // ---- topological order ----
     std::set<FNode *> seen;
     for (FVal * v : out_vals) P.topo(v->prod, seen);
@@ -704,7 +747,7 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     // ---- representation needs ----
     for (FNode * n : P.order) {
         switch (n->kind) {
-            case FK_CONV1: case FK_CONV3: case FK_DW: case FK_LINEAR: case FK_QKV: case FK_ATTN:
+            case FK_CONV1: case FK_CONV3: case FK_DW: case FK_LINEAR: case FK_QKV: case FK_ATTN: case FK_IR:
                 for (FVal * v : n->in) v->need16 = true;
                 break;
             case FK_LN: case FK_ADD:
@@ -889,6 +932,23 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const double bytes = (double)in->rows() * in->C * 2 + (double)o->C * in->C * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0)) +
                                      (n->res ? (double)o->rows() * o->C * 4 : 0.0);
                 add_launch(plan, kname, [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * in->rows() * o->C * in->C, bytes, what);
+            } break;
+            case FK_IR: {
+                FVal *  in = n->in[0];
+                FNode * a = n->ir_expand, * b = n->ir_dw;
+                const int E = a->out->C;
+                auto IL = std::make_shared<IrLaunch>();
+                if (!ir_fused_prepare(*IL, in->p16, in->N, in->H, in->W, in->C, E, o->C, b->stride, P.pool.ptr<__half>(a->c_w), P.pool.ptr<float>(a->c_scale),
+                                      P.pool.ptr<float>(a->c_shift), P.pool.ptr<__half>(b->c_w), P.pool.ptr<float>(b->c_scale), P.pool.ptr<float>(b->c_shift),
+                                      P.pool.ptr<__half>(n->c_w), P.pool.ptr<float>(n->c_scale), P.pool.ptr<float>(n->c_shift), n->res ? n->res->p32 : nullptr, o->p16,
+                                      o->p32))
+                    return false;
+                char cfg[96];
+                snprintf(cfg, sizeof cfg, " expand %d s%d tile %dx%d", E, b->stride, IL->p.TH, IL->p.TW);
+                const double flops = 2.0 * in->rows() * E * in->C + 2.0 * o->rows() * E * 9 + 2.0 * o->rows() * o->C * E;
+                const double bytes = (double)in->rows() * in->C * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0) + (n->res ? 4 : 0)) +
+                                     2.0 * ((double)E * in->C + 9.0 * E + (double)o->C * E);
+                add_launch(plan, "ir_fused_expand_dw_reduce", [IL](cudaStream_t st) { ir_fused_launch(*IL, st); }, flops, bytes, what + cfg);
             } break;
             case FK_CONV3: {
                 FVal * a = n->in[0];

@@ -121,4 +121,29 @@ bool dwreduce_prepare(DwRedLaunch & L, const __half * x, int N, int H, int W, in
                       const float * r_shift, int r_act, const float * res32, __half * out16, float * out32);
 void dwreduce_launch(const DwRedLaunch & L, cudaStream_t st);
 
+// K4: the whole inverted-residual block (expand 1x1 -> depthwise 3x3 -> reduce 1x1 [+ residual]) in one kernel; see ir_fused.cu
+struct IrLaunch {
+    CUtensorMap map_x, map_we, map_wr;
+    struct Params {
+        int N, H, W, Cin, E, Cout, Cout_pad, stride, OH, OW;
+        int TH, TW, IH, IW, P_in, P_out, MBI, MBO, tiles_x, tiles_y, ntiles, nthreads;
+        int kb_elems, row_bytes, num_kb, ksteps;  // K blocking of the expand GEMM (x and We tiles)
+        int NC;                                   // 64-channel chunks of the expanded width
+        int tmem_cols, red_stride;
+        uint32_t off_x, x_kb_stride, x_tx_bytes, off_e, off_a, off_we, we_bytes, we_kb_stride, off_wr, wr_bytes, off_par;
+        const __half * dwW;                       // [3][3][E]
+        const float *se, *he, *sd, *hd, *sr, *hr; // folded BatchNorm of expand / depthwise / reduce
+        const float * res32;                      // [N*OH*OW, Cout] or null
+        __half *      out16;
+        float *       out32;
+    } p;
+    size_t smem_bytes;
+    int    grid;
+};
+// x == nullptr: shape query only (returns whether the fused kernel covers the shape, fills the tiling)
+bool ir_fused_prepare(IrLaunch & L, const __half * x, int N, int H, int W, int Cin, int E, int Cout, int stride, const __half * We,
+                      const float * se, const float * he, const __half * dwW, const float * sd, const float * hd, const __half * Wr,
+                      const float * sr, const float * hr, const float * res32, __half * out16, float * out32);
+void ir_fused_launch(const IrLaunch & L, cudaStream_t st);
+
 }  // namespace b200

@@ -118,6 +118,7 @@ struct Plan {
     std::vector<Transfer> uploads, downloads;
     std::vector<void *>   pinned;        // host ranges registered with cudaHostRegister
     void *                host_mirror = nullptr;  // pinned host copies of small intermediates (tiny graphs only, see plan.cpp)
+    std::vector<ggml_tensor *> mirrored;          // tensors whose ->data points into host_mirror (reset when the plan dies)
     bool                  upload_inputs = true, download_outputs = true;
     cudaGraphExec_t       graph_exec = nullptr;
     bool                  graph_failed = false;

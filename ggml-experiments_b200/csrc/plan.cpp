@@ -149,6 +149,9 @@ Plan::~Plan() {
     if (history) cudaFree(history);
     for (void * p : owned_device) cudaFree(p);
     for (void * p : pinned) cudaHostUnregister(p);
+    // tensors (and views of them) whose ->data points into the mirror must not keep a dangling pointer: a rebuilt plan would
+    // skip them ("already has host data") and the host would read -- or a download would write -- freed pinned memory
+    for (ggml_tensor * t : mirrored) t->data = nullptr;
     if (host_mirror) cudaFreeHost(host_mirror);
 }
 
@@ -162,7 +165,13 @@ static uint64_t graph_signature(const ggml_cgraph * gf) {
         mix((uint64_t)(uintptr_t)t);
         mix((uint64_t)t->op);
         for (int d = 0; d < 4; d++) { mix((uint64_t)t->ne[d]); mix((uint64_t)t->nb[d]); }
+        // flags (ggml_set_output on an interior node needs a new host shadow), sources and op parameters (eps, strides edited in
+        // place) all change what the plan must do: a stale plan must never be replayed for them
+        mix((uint64_t)(uint32_t)t->flags);
+        for (int s = 0; s < GGML_MAX_SRC; s++) mix((uint64_t)(uintptr_t)t->src[s]);
+        for (size_t k = 0; k < sizeof(t->op_params) / sizeof(t->op_params[0]); k++) mix((uint64_t)(uint32_t)t->op_params[k]);
     }
+    for (int i = 0; i < gf->n_leafs; i++) mix((uint64_t)(uint32_t)gf->leafs[i]->flags);
     mix((uint64_t)runtime().mode);
     return h;
 }
@@ -176,6 +185,10 @@ void destroy_plans_of(ggml_context * ctx) {
     // mem_buffer usually does), and a stale feedback pair would then point at unrelated tensors
     const char * lo = ctx->mem_buffer, * hi = ctx->mem_buffer + ctx->mem_size;
     auto inside = [&](const void * p) { return (const char *)p >= lo && (const char *)p < hi; };
+    for (auto & kv : g_plans) {  // plans of OTHER contexts that mirrored tensors of this arena forget them
+        auto & m = kv.second->mirrored;
+        m.erase(std::remove_if(m.begin(), m.end(), [&](ggml_tensor * t) { return inside(t); }), m.end());
+    }
     std::lock_guard<std::mutex> rk(g_reg_mu);
     for (auto it = g_feedback.begin(); it != g_feedback.end();) it = inside(it->first) ? g_feedback.erase(it) : std::next(it);
     for (auto it = g_external.begin(); it != g_external.end();) it = inside(it->first) ? g_external.erase(it) : std::next(it);
@@ -252,13 +265,16 @@ static void place_leafs(Plan * plan, ggml_cgraph * gf) {
 Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
     ensure_device();
     uint64_t sig = graph_signature(gf);
+    bool had_private_stream = false;
     if (gf->plan) {
         Plan * p = (Plan *)gf->plan;
         if (p->graph_sig == sig) return p;
-        // the graph was extended or the mode changed: rebuild
+        // the graph was extended or the mode changed: rebuild (a pipelined slot keeps running on a stream of its own)
+        had_private_stream = p->private_stream != nullptr;
         ggml_graph_release_plan(gf);
     }
     Plan * plan      = new Plan();
+    if (had_private_stream) B200_CHECK(cudaStreamCreateWithFlags(&plan->private_stream, cudaStreamNonBlocking));
     plan->ctx        = ctx;
     plan->graph_sig  = sig;
     plan->n_nodes_at_build = gf->n_nodes;
@@ -331,13 +347,18 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
                 const size_t bytes = (size_t)ggml_nelements(t) * ggml_type_size(t->type);
                 if (bytes > (64u << 10)) continue;
                 t->data = (char *)plan->host_mirror + off;
+                plan->mirrored.push_back(t);
                 off += (bytes + 255) & ~size_t(255);
                 plan->downloads.push_back({t, plan->slots[t].dptr, bytes});
             }
         }
         for (int i = 0; i < gf->n_nodes; i++) {  // views of mirrored tensors read through their base
             ggml_tensor * t = gf->nodes[i];
-            if (is_view_op(t->op) && !t->data && t->view_src && t->view_src->data) t->data = (char *)t->view_src->data + t->view_offs;
+            if (is_view_op(t->op) && !t->data && t->view_src && t->view_src->data) {
+                t->data = (char *)t->view_src->data + t->view_offs;
+                const char * hm = (const char *)plan->host_mirror;
+                if (hm && (const char *)t->data >= hm && (const char *)t->data < hm + total) plan->mirrored.push_back(t);
+            }
         }
     }
     gf->plan = plan;
@@ -375,7 +396,9 @@ void run_plan(Plan * plan, bool wait_for_results) {
                 (void)cudaGetLastError();
                 plan->graph_failed = true;
                 plan->graph_exec   = nullptr;
-                if (rt.verbose) fprintf(stderr, "libggml_b200: CUDA graph capture failed (%s); launching directly\n", cudaGetErrorString(err));
+                static bool warned = false;
+                if (rt.verbose || !warned) fprintf(stderr, "libggml_b200: CUDA graph capture failed (%s); launching the %zu kernels directly\n", cudaGetErrorString(err), plan->launches.size());
+                warned = true;
             }
         }
     }

@@ -1,5 +1,5 @@
 // ptx_sm100.cuh -- inline-PTX wrappers for the Blackwell (sm_100a) async machinery: mbarrier, TMA (cp.async.bulk.tensor),
-// tcgen05 (alloc / mma / commit / ld), proxy fences.  Shared by the kernels that are not in gemm_tcgen05.cu.
+// tcgen05 (alloc / mma / commit / ld), proxy fences.  The one copy shared by every kernel file (gemm_tcgen05.cu, dwconv_tma.cu, dwreduce.cu, ir_fused.cu, ...).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -144,6 +144,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
     d |= (uint64_t)1 << 46;                         // descriptor version = 1
     d |= layout << 61;
     return d;
+}
+
+// SiLU with ONE transcendental: x*sigmoid(x) = h + h*tanh(h), h = x/2 (MUFU.TANH; the exp+rcp form costs two MUFU ops
+// and ~9 instructions per element, which made the SiLU epilogues XU/issue-bound: profiles/README.md).
+// tanh.approx.f32 has ~2^-11 relative error, i.e. the result is good to about one f16 ulp -- the precision the value
+// is stored at anyway.  -DGGML_B200_SILU_EXACT restores x / (1 + exp(-x)).
+__device__ __forceinline__ float silu_f(float x) {
+#ifdef GGML_B200_SILU_EXACT
+    return __fdividef(x, 1.0f + __expf(-x));
+#else
+    const float h = 0.5f * x;
+    float       t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+#endif
 }
 
 }  // namespace ptx

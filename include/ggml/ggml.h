@@ -300,6 +300,20 @@ int ggml_b200_debug_gemm(const uint16_t * A, const uint16_t * B, int M, int N, i
 int ggml_b200_debug_conv3x3(const uint16_t * x0, int C0, const uint16_t * x1, int C1, int n_img, int H, int W,
                             const uint16_t * Wt, int OC, const float * scale, const float * shift, int act,
                             float * out32);
+/* K3 depthwise 3x3 (stride 1|2, pad 1) + scale/shift + SiLU (main.cpp:788,809-850); x [N,H,W,C], Wt [3][3][C];
+ * variant 0 = TMA kernel of the fused plan, 1 = register-window fallback */
+int ggml_b200_debug_dwconv(const uint16_t * x, int N, int H, int W, int C, int stride, const uint16_t * Wt, const float * scale,
+                           const float * shift, int act, int variant, uint16_t * out16);
+/* K2 stem 3x3/s2 over f32 images (chw = 0: [N,H,W,3], chw = 1: [N,3,H,W] as main.cpp:627-634 writes it), Wt [OC][3][3][3] */
+int ggml_b200_debug_stem(const float * x, int chw, int N, int H, int W, const uint16_t * Wt, int OC, const float * scale, const float * shift,
+                         int act, uint16_t * out16, float * out32);
+/* K7 attention core (main.cpp:1073-1086) on a head-padded qkv buffer [N*H*W][3][heads][DP], DP = ..._attention_dp(C/heads) */
+int ggml_b200_debug_attention_dp(int d);
+int ggml_b200_debug_attention(const uint16_t * qkv, int N, int H, int W, int C, int heads, uint16_t * out16);
+/* LayerNorm folded around two GEMMs (main.cpp:1002-1019 + the following dense): producer x = A.B^T + shift0 with row statistics,
+ * consumer y = act(LN(x).W^T + bias); Wf f32 [N][C]; x32 (optional) returns the producer's f32 output */
+int ggml_b200_debug_gemm_ln(const uint16_t * A, const uint16_t * B, int M, int C, int K, const float * shift0, const float * gamma,
+                            const float * beta, float eps, const float * Wf, const float * bias, int N, int act, float * x32, float * y32);
 
 #ifdef __cplusplus
 }

@@ -174,7 +174,7 @@ def test_fast_mode_matches_oracle(G, oracle, weight_files, variant, n, hw):
     print(variant, n, hw, r, t, info)
     if info["mode"] != MV.FAST:
         pytest.xfail("fused planner not yet covering this graph; exact plan was used")
-    assert r["violations"] <= r["n"] * 1e-4, r
+    assert r["violations"] == 0, r  # north_star: EVERY element inside 1e-2*|ref| + 1e-2*rms
     assert r["rel_l2"] < 5e-3, r
     assert t["agree"] == 1.0, t
 
@@ -199,7 +199,9 @@ def test_unmodified_reference_main_runs_on_libggml_b200(G, oracle, weight_files,
     ref_f, _ = oracle.OracleModel(weight_files["s"]).forward(W.synthetic_images(1, 256, 256))
     ref = np.concatenate([ref_f[0, :5, 0, 0], ref_f[0, -5:, 0, 0]])
     print("reference main.cpp printed:", vals, "oracle:", ref.tolist(), r.stderr[-300:])
-    assert np.abs(np.array(vals) - ref).max() < 3e-2
+    # same element gate as the whole-model tests (the program prints 6 significant digits: +1e-5 relative)
+    rms = float(np.sqrt((ref_f.astype(np.float64) ** 2).mean()))
+    assert (np.abs(np.array(vals) - ref) <= 1e-2 * rms + 1e-2 * np.abs(ref) + 1e-5 * np.abs(ref)).all(), (vals, ref.tolist(), rms)
 
 
 def test_unmodified_reference_rnn_runs_on_libggml_b200(G, tmp_path):
@@ -246,7 +248,7 @@ def test_fast_mode_at_resolutions_whose_maps_do_not_divide_128(G, oracle, weight
     feat, pooled, info = _run_model(G, weight_files["xs"], imgs, MV.FAST)
     assert info["mode"] == MV.FAST, info
     r = parity_report(feat, ref_f, rtol=1e-2, atol_rms=1e-2)
-    assert r["violations"] <= r["n"] * 1e-4 and r["rel_l2"] < 5e-3, r
+    assert r["violations"] == 0 and r["rel_l2"] < 5e-3, r
     assert top1_report(pooled, ref_p)["agree"] == 1.0
 
 
@@ -261,7 +263,7 @@ def test_non_square_and_odd_batch_fast_equals_exact(G, weight_files):
     assert ie["mode"] == MV.EXACT and i_f["mode"] == MV.FAST
     r = parity_report(ff, fe, rtol=1e-2, atol_rms=1e-2)
     print(r)
-    assert r["violations"] <= r["n"] * 1e-3 and r["rel_l2"] < 5e-3, r
+    assert r["violations"] == 0 and r["rel_l2"] < 5e-3, r
     assert (pf.argmax(1) == pe.argmax(1)).all()
 
 
@@ -410,7 +412,7 @@ def test_full_size_batch_256_is_batch_independent_and_matches_the_oracle_sample(
     ref_f, ref_p = oracle.OracleModel(weight_files["s"]).forward(base)
     r = parity_report(feat8, ref_f, rtol=1e-2, atol_rms=1e-2)
     t = top1_report(pooled8, ref_p)
-    assert r["violations"] <= r["n"] * 1e-4 and r["rel_l2"] < 5e-3, r
+    assert r["violations"] == 0 and r["rel_l2"] < 5e-3, r
     assert t["agree"] == 1.0, t
 
 
