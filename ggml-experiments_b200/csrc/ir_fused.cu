@@ -223,6 +223,7 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
             mbar_wait(exp_full, g & 1u);
             tc_fence_after();
             if (tid == 0 && last_chunk && next_tile) issue_x(tile + gridDim.x);  // every expand MMA of this tile has read xs
+            __syncwarp();  // warp 0 reconverges before the warp-aligned tcgen05.ld below
 
             // ---- expand epilogue: TMEM -> BN + SiLU -> mask -> f16 -> es ----
             for (int mb = 0; mb < p.MBI; mb++) {
@@ -334,6 +335,7 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         // ---- reduce epilogue: TMEM -> BN (+ residual) -> global ----
         mbar_wait(red_done, (g - 1) & 1u);
         tc_fence_after();
+        __syncwarp();
         for (int mo = 0; mo < p.MBO; mo++) {
             const int row = quad * 32 + lane;
             const int qi  = mo * 128 + row;
@@ -343,12 +345,12 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
             const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
             for (int cc = wsub; cc * 32 < p.Cout_pad; cc += WQ) {
                 float v[32];
+                __syncwarp();  // tcgen05.ld is warp-aligned: lanes whose pixel lies outside the image skip the stores, not the load
                 tmem_ld_32x32(tmem_red + (uint32_t)mo * (uint32_t)p.red_stride + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cc * 32), v);
-                if (!ok) continue;
 #pragma unroll
                 for (int g8 = 0; g8 < 4; g8++) {
                     const int nn = cc * 32 + g8 * 8;
-                    if (nn + 8 > p.Cout) continue;
+                    if (!ok || nn + 8 > p.Cout) continue;
                     float y[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) y[j] = fmaf(v[g8 * 8 + j], s_sr[nn + j], s_hr[nn + j]);

@@ -314,6 +314,14 @@ int ggml_b200_debug_attention(const uint16_t * qkv, int N, int H, int W, int C, 
  * consumer y = act(LN(x).W^T + bias); Wf f32 [N][C]; x32 (optional) returns the producer's f32 output */
 int ggml_b200_debug_gemm_ln(const uint16_t * A, const uint16_t * B, int M, int C, int K, const float * shift0, const float * gamma,
                             const float * beta, float eps, const float * Wf, const float * bias, int N, int act, float * x32, float * y32);
+/* K4 fused inverted residual (inverted_residual_layer::forward, main.cpp:854-870): expand 1x1 (+BN+SiLU) -> depthwise 3x3 stride 1|2
+ * (+BN+SiLU) -> reduce 1x1 (+BN) [+ f32 residual].  x [N,H,W,Cin], We [E][Cin], Wd [3][3][E], Wr [Cout][E] f16; s* / h* = folded BatchNorm
+ * scale / shift.  Returns 2 when the shape is outside the fused kernel's envelope (the plan then runs the three separate kernels). */
+int ggml_b200_debug_ir_fused(const uint16_t * x, int N, int H, int W, int Cin, int E, int Cout, int stride, const uint16_t * We,
+                             const float * se, const float * he, const uint16_t * Wd, const float * sd, const float * hd, const uint16_t * Wr,
+                             const float * sr, const float * hr, const float * res32, uint16_t * out16, float * out32);
+/* timing probe: mean ms per launch of the fused block and (optionally) of the three separate kernels it replaces */
+float ggml_b200_debug_ir_time(int N, int H, int W, int Cin, int E, int Cout, int stride, int with_res, int reps, float * unfused_ms);
 
 #ifdef __cplusplus
 }
