@@ -61,6 +61,8 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> dict:
             o = os.path.join(OUT, os.path.basename(s) + ".o")
             if force or _newer(o, [s] + [d for d in deps if d.endswith((".h", ".cuh"))]):
                 extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+                if os.environ.get("GGML_B200_IR_PROFILE"):  # clock64 phase profile inside the fused inverted-residual kernel
+                    extra.append("-DGGML_B200_IR_PROFILE")
                 _run([NVCC, *ARCH, *COMMON, *extra, "-c", s, "-o", o])
             objs.append(o)
         _run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-lcudart"])

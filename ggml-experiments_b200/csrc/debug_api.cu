@@ -224,8 +224,26 @@ extern "C" float ggml_b200_debug_ir_time(int N, int H, int W, int Cin, int E, in
         B200_CHECK(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= reps;
-        fprintf(stderr, "ir_fused %dx%dx%d %d->%d->%d s%d: tile %dx%d halo %d rows (%d blocks) NT=%d smem=%zu tmem=%d grid=%d  %.1f us\n", N, H, W, Cin, E, Cout,
-                stride, L.p.TH, L.p.TW, L.p.P_in, L.p.MBI, L.p.nthreads, L.smem_bytes, L.p.tmem_cols, L.grid, 1e3f * ms);
+        if (getenv("GGML_B200_IR_PHASES")) {  // clock64 profile of compute thread 0 and of the control thread, averaged over the CTAs
+            DevBuf dT(nullptr, (size_t)L.grid * 16 * sizeof(long long));
+            L.p.timing = (long long *)dT.p;
+            ir_fused_launch(L, st);
+            B200_CHECK(cudaStreamSynchronize(st));
+            std::vector<long long> hT((size_t)L.grid * 16);
+            B200_CHECK(cudaMemcpy(hT.data(), dT.p, hT.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            static const char * nm[2][8] = {{"wait exp_full", "expand epilogue", "barrier", "reduce epilogue", "wait red_done", "depthwise", "barrier", "other"},
+                                            {"other", "wait es_done", "wait x", "wait we", "wait as_full", "wait wr", "MMA issue", "TMA issue"}};
+            for (int who = 0; who < 2; who++) {
+                double sum[8] = {0}, tot = 0;
+                for (int b = 0; b < L.grid; b++) for (int j = 0; j < 8; j++) sum[j] += (double)hT[((size_t)b * 2 + who) * 8 + j];
+                for (int j = 0; j < 8; j++) tot += sum[j];
+                for (int j = 0; j < 8; j++)
+                    if (sum[j] > 0) fprintf(stderr, "   %s %-26s %6.1f %%  (%.0f cycles per CTA)\n", who ? "control" : "compute", nm[who][j], 100.0 * sum[j] / tot, sum[j] / L.grid);
+            }
+            L.p.timing = nullptr;
+        }
+        fprintf(stderr, "ir_fused %dx%dx%d %d->%d->%d s%d: tile %dx%d halo %d rows (%d blocks) NT=%d nxb=%d smem=%zu tmem=%d grid=%d  %.1f us\n", N, H, W, Cin, E, Cout,
+                stride, L.p.TH, L.p.TW, L.p.P_in, L.p.MBI, L.p.nthreads, L.p.nxb, L.smem_bytes, L.p.tmem_cols, L.grid, 1e3f * ms);
     }
     if (unfused_ms) {
         GemmEpilogue e1x; e1x.scale = (const float *)dse.p; e1x.shift = (const float *)dhe.p; e1x.act = 1; e1x.out16 = (__half *)dE.p; e1x.ld16 = E;

@@ -586,6 +586,8 @@ void build_exact_plan(Plan * plan, ggml_cgraph * gf) {
     }
     for (int i = 0; i < n; i++)
         if (gf->nodes[i]->flags & GGML_TENSOR_FLAG_OUTPUT) last_use[base_of(gf->nodes[i])] = n;  // outputs live forever
+    if (getenv("GGML_B200_DUMP_NODES") != nullptr)  // node-by-node comparison with the CPU reference run: nothing is ever overwritten
+        for (int i = 0; i < n; i++) last_use[base_of(gf->nodes[i])] = n;
     // fused kernels read their operands at the ROOT node and a folded bias-add lives in its mul_mat's buffer
     for (int i = 0; i < n; i++) {
         const ggml_tensor * t = gf->nodes[i];

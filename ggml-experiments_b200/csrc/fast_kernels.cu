@@ -788,7 +788,10 @@ void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads,
         const int    warps = L >= kAttnQB ? 8 : L / 16;
         const int    lk    = L < kAttnLK ? L : kAttnLK;
         const int    nqb   = (L + kAttnQB - 1) / kAttnQB;
-        const int    qblocks = (L <= kAttnLK && nqb > 1 && getenv("GGML_B200_ATTN_QB1") == nullptr) ? nqb : 1;
+        int          qblocks = (L <= kAttnLK && nqb > 1 && getenv("GGML_B200_ATTN_QB1") == nullptr) ? nqb : 1;
+        // all query blocks of a sequence share one staged K/V only while the CTA still fits the 100 KiB it may use (two per SM):
+        // head dim 64 at L = 256 would need 108 KiB
+        if ((size_t)(kAttnQB * qblocks + 2 * lk) * (dp + 8) * sizeof(__half) > 100 * 1024) qblocks = 1;
         const size_t smem  = (size_t)(kAttnQB * qblocks + 2 * lk) * (dp + 8) * sizeof(__half);
         dim3         grid(N * 4 * heads, nqb / qblocks);
         const float  sl2 = 1.4426950408889634f / sqrtf((float)d);  // log2(e) / sqrt(d)

@@ -711,7 +711,9 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
 
     // ---- K4: expand 1x1 (+BN+SiLU) -> depthwise 3x3 (+BN+SiLU) -> reduce 1x1 (+BN) [+ residual] as ONE kernel: the expanded
     // activation and the depthwise output never reach HBM (inverted_residual_layer::forward, main.cpp:854-870) ----
-    if (!getenv("GGML_B200_NO_IR_FUSE")) {
+    // Opt-in (GGML_B200_IR_FUSE=1): parity-green, but on B200 the fused block is ALU-bound -- depthwise + two SiLU epilogues on one
+    // SM at 18 warps -- and measured 5-20 % SLOWER than the three HBM-bound kernels it replaces (profiles/README.md, round 2).
+    if (getenv("GGML_B200_IR_FUSE") != nullptr && atoi(getenv("GGML_B200_IR_FUSE")) > 0) {
         for (auto & up : P.nodes) {
             FNode * c = up.get();
             if (c->dead || c->kind != FK_CONV1 || c->ln_g || c->act || !c->has_bn || c->out->need_stats) continue;

@@ -123,19 +123,21 @@ void dwreduce_launch(const DwRedLaunch & L, cudaStream_t st);
 
 // K4: the whole inverted-residual block (expand 1x1 -> depthwise 3x3 -> reduce 1x1 [+ residual]) in one kernel; see ir_fused.cu
 struct IrLaunch {
-    CUtensorMap map_x, map_we, map_wr;
+    CUtensorMap map_x, map_we, map_wr, map_o32, map_o16, map_r32;
     struct Params {
         int N, H, W, Cin, E, Cout, Cout_pad, stride, OH, OW;
         int TH, TW, IH, IW, P_in, P_out, MBI, MBO, tiles_x, tiles_y, ntiles, nthreads;
         int kb_elems, row_bytes, num_kb, ksteps;  // K blocking of the expand GEMM (x and We tiles)
         int NC;                                   // 64-channel chunks of the expanded width
         int tmem_cols, red_stride;
-        uint32_t off_x, x_kb_stride, x_tx_bytes, off_e, off_a, off_we, we_bytes, we_kb_stride, off_wr, wr_bytes, off_par;
+        int nxb;                                  // input-halo buffers in shared memory: 2 (next tile prefetched a tile ahead) or 1
+        uint32_t off_x, x_kb_stride, x_buf_stride, x_tx_bytes, off_e, st16_off, off_a, off_we, we_bytes, we_kb_stride, off_wr, wr_bytes, off_par;
         const __half * dwW;                       // [3][3][E]
         const float *se, *he, *sd, *hd, *sr, *hr; // folded BatchNorm of expand / depthwise / reduce
         const float * res32;                      // [N*OH*OW, Cout] or null
         __half *      out16;
         float *       out32;
+        long long *   timing;                     // debug probe: [grid][2][8] clock64 sums (compute thread 0, control thread), or null
     } p;
     size_t smem_bytes;
     int    grid;

@@ -527,11 +527,43 @@ extern "C" struct ggml_cgraph ggml_build_forward(struct ggml_tensor * tensor) {
     return gf;  // pointers are re-fixed on next use
 }
 
+// GGML_B200_DUMP_NODES=<file> (per-node plans only, graphs of more than 256 nodes): after the compute, one line per node --
+// index, op, shape, sum and sum of |x| in double -- in the format oracle/ggml_cpu_ref.c writes with GGML_CPU_REF_DUMP, so the
+// unmodified reference program can be compared node by node between its CPU run and its run on this library.
+static void dump_nodes(Plan * plan, ggml_cgraph * gf, const char * path) {
+    static const char * names[GGML_OP_COUNT] = {"NONE", "ADD", "SUB", "MUL", "DIV", "SQRT", "SILU", "TANH", "NORM", "SOFT_MAX", "MUL_MAT", "REPEAT", "CONCAT",
+                                                "GET_ROWS", "CONT", "RESHAPE", "VIEW", "PERMUTE", "TRANSPOSE", "CONV_2D", "CONV_DEPTHWISE_2D", "POOL_MEAN_HW",
+                                                "ARGMAX"};
+    FILE * f = fopen(path, "w");
+    if (!f) return;
+    B200_CHECK(cudaDeviceSynchronize());
+    std::vector<char> host;
+    for (int i = 0; i < gf->n_nodes; i++) {
+        const ggml_tensor * t = gf->nodes[i];
+        double s = 0.0, sa = 0.0;
+        auto it = plan->slots.find(t);
+        if (!is_view_op(t->op) && it != plan->slots.end() && it->second.dptr && (t->type == GGML_TYPE_F32 || t->type == GGML_TYPE_F16)) {
+            const size_t n = (size_t)ggml_nelements(t);
+            host.resize(n * ggml_type_size(t->type));
+            B200_CHECK(cudaMemcpy(host.data(), it->second.dptr, host.size(), cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < n; k++) {
+                const double v = t->type == GGML_TYPE_F32 ? (double)((const float *)host.data())[k] : (double)ggml_fp16_to_fp32(((const ggml_fp16_t *)host.data())[k]);
+                s += v;
+                sa += fabs(v);
+            }
+        }
+        fprintf(f, "%d %s %lld %lld %lld %lld %.9e %.9e\n", i, names[t->op], (long long)t->ne[0], (long long)t->ne[1], (long long)t->ne[2], (long long)t->ne[3], s, sa);
+    }
+    fclose(f);
+}
+
 extern "C" void ggml_graph_compute_with_ctx(struct ggml_context * ctx, struct ggml_cgraph * gf, int n_threads) {
     (void)n_threads;  // main.cpp:640 passes 1; device execution ignores it (SURVEY 8b "Threading")
     fix_graph_pointers(gf);
     Plan * plan = get_or_build_plan(ctx, gf);
     run_plan(plan);
+    if (const char * dump = getenv("GGML_B200_DUMP_NODES"))
+        if (plan->mode != GGML_B200_MODE_FAST && gf->n_nodes > 256) dump_nodes(plan, gf, dump);
 }
 
 extern "C" void ggml_b200_graph_prepare(struct ggml_context * ctx, struct ggml_cgraph * gf) {

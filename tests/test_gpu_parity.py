@@ -435,3 +435,36 @@ def test_every_batch_size_gives_the_same_bits_per_image(G, weight_files, variant
             m.release(b, hw, hw)
     finally:
         m.close()
+
+
+# ---- K4: fused inverted residual inside the whole model (opt-in: GGML_B200_IR_FUSE=1) ---------------------------------
+@pytest.mark.parametrize("variant,n,hw", [("s", 3, 256), ("xs", 2, 256), ("xxs", 5, 128), ("s", 1, 512)])
+def test_fast_mode_with_fused_inverted_residuals_matches_oracle(G, oracle, weight_files, variant, n, hw, monkeypatch):
+    """The seven inverted-residual blocks (main.cpp:854-870) run as ONE kernel each (expand -> depthwise -> reduce on chip, ir_fused.cu):
+    same north_star gate as the default plan, and fewer launches."""
+    from ggml_experiments_b200 import mobilevit as MV
+    imgs = W.synthetic_images(n, hw, hw, seed=7)
+    ref_f, ref_p = oracle.OracleModel(weight_files[variant]).forward(imgs)
+    _, _, info0 = _run_model(G, weight_files[variant], imgs, MV.FAST)
+    monkeypatch.setenv("GGML_B200_IR_FUSE", "1")
+    feat, pooled, info = _run_model(G, weight_files[variant], imgs, MV.FAST)
+    monkeypatch.delenv("GGML_B200_IR_FUSE")
+    assert info["mode"] == MV.FAST and info["launches"] <= info0["launches"] - 10, (info0, info)
+    r = parity_report(feat, ref_f, rtol=1e-2, atol_rms=1e-2)
+    print(variant, n, hw, r, info)
+    assert r["violations"] == 0 and r["rel_l2"] < 5e-3, r
+    assert top1_report(pooled, ref_p)["agree"] == 1.0
+
+
+def test_dwreduce_fusion_matches_oracle(G, oracle, weight_files, monkeypatch):
+    """K4a (depthwise + reduce in one kernel, dwreduce.cu; opt-in GGML_B200_DWREDUCE=1) keeps the same gate."""
+    from ggml_experiments_b200 import mobilevit as MV
+    imgs = W.synthetic_images(2, 256, 256, seed=7)
+    ref_f, ref_p = oracle.OracleModel(weight_files["s"]).forward(imgs)
+    monkeypatch.setenv("GGML_B200_DWREDUCE", "1")
+    feat, pooled, info = _run_model(G, weight_files["s"], imgs, MV.FAST)
+    monkeypatch.delenv("GGML_B200_DWREDUCE")
+    assert info["mode"] == MV.FAST
+    r = parity_report(feat, ref_f, rtol=1e-2, atol_rms=1e-2)
+    assert r["violations"] == 0 and r["rel_l2"] < 5e-3, r
+    assert top1_report(pooled, ref_p)["agree"] == 1.0
