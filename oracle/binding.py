@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libmvit_oracle.so")
 PURE_F32 = 1
 NO_ACT_ROUND = 2
+LEGACY_F16_TABLES = 4  # SiLU / softmax-exp through f16 lookup tables (the ggml the author ran)
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 

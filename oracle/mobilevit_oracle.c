@@ -30,6 +30,8 @@
 
 #define MVO_MAX_TENSORS 512
 #define MVO_FLAG_PURE_F32 1 /* skip every f16 rounding point: == HF torch f32 semantics */
+#define MVO_FLAG_LEGACY_F16_TABLES 4 /* SiLU and the softmax exponential through f16 lookup tables, y = f16(f(f16(x))) -- the ggml the
+                                      author ran (GGML_SILU_FP16 / ggml_table_exp_f16; mobilevit/README.md:39-45 prints f16-representable values) */
 #define MVO_FLAG_NO_ACT_ROUND 2 /* weights stay f16-rounded (as loaded, main.cpp:928-932) but activations are not rounded:
                                   a smooth function, used to validate the GPU EXACT_F32 mode to max-abs 1e-3 */
 
@@ -37,6 +39,24 @@
  * fp16 rounding: [ggml] GGML_FP32_TO_FP16 on x86 with F16C = _cvtss_sh(x, 0) (round-to-nearest-even)
  * ------------------------------------------------------------------------------------------------ */
 static inline float round_f16(float x) { return _cvtsh_ss(_cvtss_sh(x, 0)); }
+
+/* legacy f16 lookup tables ([ggml] ggml_table_silu_f16 / ggml_table_exp_f16), built on first use; the flag is process-wide state set by
+ * mvo_forward / mvo_forward_batch before any worker thread starts */
+static int g_legacy_tables = 0;
+static uint16_t *g_tab_silu = NULL, *g_tab_exp = NULL;
+static void build_legacy_tables(void) {
+    if (g_tab_silu) return;
+    uint16_t *ts = (uint16_t *)malloc(65536 * 2), *te = (uint16_t *)malloc(65536 * 2);
+    for (int i = 0; i < 65536; i++) {
+        const float f = _cvtsh_ss((uint16_t)i);
+        ts[i] = _cvtss_sh(f / (1.0f + expf(-f)), 0);
+        te[i] = _cvtss_sh(expf(f), 0);
+    }
+    g_tab_exp = te;
+    g_tab_silu = ts;
+}
+static inline float silu_op(float x) { return g_legacy_tables ? _cvtsh_ss(g_tab_silu[_cvtss_sh(x, 0)]) : x / (1.0f + expf(-x)); }
+static inline float exp_op(float x) { return g_legacy_tables ? _cvtsh_ss(g_tab_exp[_cvtss_sh(x, 0)]) : expf(x); }
 
 static void round_f16_array(const float *src, float *dst, size_t n, int pure_f32) {
     if (pure_f32) {
@@ -368,7 +388,7 @@ void mvo_bn_silu(float *x, int C, size_t P, const float *mean, const float *var,
             for (size_t i = 0; i < P; i++) xc[i] = ((xc[i] - mu) / sd) * g + b;
         }
         if (use_act)
-            for (size_t i = 0; i < P; i++) xc[i] = xc[i] / (1.0f + expf(-xc[i]));
+            for (size_t i = 0; i < P; i++) xc[i] = silu_op(xc[i]);
     }
 }
 
@@ -558,7 +578,7 @@ void mvo_softmax_rows(float *x, int n, size_t rows) {
         for (int i = 0; i < n; i++) mx = p[i] > mx ? p[i] : mx;
         double sum = 0.0;
         for (int i = 0; i < n; i++) {
-            float v = expf(p[i] - mx);
+            float v = exp_op(p[i] - mx);
             p[i] = v;
             sum += (double)v;
         }
@@ -609,7 +629,7 @@ static void transformer_layer(const mvo_tlayer *T, float *x, int C, int L, int B
     const int F = T->ik->dims[1];
     float *mid = (float *)malloc(rows * F * sizeof(float));
     linear(ln, rows, C, T->ik, T->ib, mid);                      /* :1134-1147 */
-    for (size_t i = 0; i < rows * F; i++) mid[i] = mid[i] / (1.0f + expf(-mid[i])); /* :1148 */
+    for (size_t i = 0; i < rows * F; i++) mid[i] = silu_op(mid[i]); /* :1148 */
     linear(mid, rows, F, T->dk, T->db, q);                       /* :1151-1163 */
     for (size_t i = 0; i < rows * C; i++) x[i] = q[i] + x[i];     /* :1165-1169 */
     free(mid); free(sc); free(ctx); free(v); free(k); free(q); free(ln);
@@ -656,6 +676,8 @@ static float *vit_layer(const mvo_model *m, const mvo_vit *L, const float *x, in
 int mvo_forward(void *model, const float *img_hwc, int H, int W, float *feat, float *pooled, int flags,
                 float **stage_out) {
     const mvo_model *m = (const mvo_model *)model;
+    if ((flags & MVO_FLAG_LEGACY_F16_TABLES) && !g_tab_silu) build_legacy_tables();
+    g_legacy_tables = (flags & MVO_FLAG_LEGACY_F16_TABLES) != 0; /* workers of one batch all write the same value */
     float *chw = (float *)malloc((size_t)3 * H * W * sizeof(float));
     for (int k = 0; k < 3; k++)
         for (int y = 0; y < H; y++)
@@ -722,6 +744,8 @@ int mvo_max_threads(void) {
 double mvo_forward_batch(void *model, const float *imgs_hwc, int N, int H, int W, float *feat, float *pooled,
                          int flags, int n_threads) {
     mvo_job j = {model, imgs_hwc, N, H, W, feat, pooled, flags, 0, 0, 0};
+    if (flags & MVO_FLAG_LEGACY_F16_TABLES) build_legacy_tables();
+    g_legacy_tables = (flags & MVO_FLAG_LEGACY_F16_TABLES) != 0;  /* before the workers start */
     j.OC = mvo_out_channels(model);
     j.fstride = (size_t)j.OC * (H / 32) * (W / 32);
     if (n_threads <= 0) n_threads = mvo_max_threads();
