@@ -30,10 +30,16 @@ static bool read_all_weights(model & m, std::ifstream & fin) {
         if (name_len <= 0 || name_len > 4096) return false;
         std::string name((size_t)name_len, '\0');
         if (!fin.read(&name[0], name_len)) return false;
-        if (!read_i32(fin, n_dims) || n_dims < 1 || n_dims > 4) return false;
+        if (!read_i32(fin, n_dims)) return false;
+        // record-format extension (convert-tf-to-ggml.py:13-14 TODOs; weights.py): flags in the upper half of the n_dims word
+        const bool disk_f16 = (n_dims & (1 << 16)) != 0;        // payload is f16
+        const bool disk_t   = (n_dims & (1 << 17)) != 0;        // 2-D dense kernel stored (out, in)
+        n_dims &= 0xFFFF;
+        if (n_dims < 1 || n_dims > 4 || (disk_t && n_dims != 2)) return false;
         int32_t dims[4] = {1, 1, 1, 1};
         for (int i = 0; i < n_dims; i++)
             if (!read_i32(fin, dims[i]) || dims[i] <= 0) return false;
+        if (disk_t) std::swap(dims[0], dims[1]);  // the tensor is created in the canonical (in, out) shape
         // main.cpp:887-889: every tensor whose name contains "convolution" is stored as F16
         const bool      is_f16 = name.find("convolution") != std::string::npos;
         const ggml_type type   = is_f16 ? GGML_TYPE_F16 : GGML_TYPE_F32;
@@ -46,7 +52,27 @@ static bool read_all_weights(model & m, std::ifstream & fin) {
         }
         const size_t count = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
         staging.resize(count);
-        if (!fin.read(reinterpret_cast<char *>(staging.data()), (std::streamsize)(count * sizeof(float)))) return false;
+        if (disk_f16) {
+            std::vector<ggml_fp16_t> half(count);
+            if (!fin.read(reinterpret_cast<char *>(half.data()), (std::streamsize)(count * sizeof(ggml_fp16_t)))) return false;
+            if (t->type == GGML_TYPE_F16 && !disk_t) {
+                memcpy(t->data, half.data(), ggml_nbytes(t));  // the same bits the f32 file would have been rounded to
+                ggml_set_name(t, name.size() > 60 ? name.c_str() + (name.size() - 60) : name.c_str());
+                m.tensors[name] = t;
+                m.total_weights += (int64_t)count;
+                continue;
+            }
+            ggml_fp16_to_fp32_row(half.data(), staging.data(), (int)count);
+        } else if (!fin.read(reinterpret_cast<char *>(staging.data()), (std::streamsize)(count * sizeof(float)))) {
+            return false;
+        }
+        if (disk_t) {  // file rows are output features: back to (in, out), the layout the graph builder transposes in-graph
+            std::vector<float> tr(count);
+            const size_t n_in = (size_t)dims[0], n_out = (size_t)dims[1];
+            for (size_t o = 0; o < n_out; o++)
+                for (size_t i = 0; i < n_in; i++) tr[i * n_out + o] = staging[o * n_in + i];
+            staging.swap(tr);
+        }
         if (t->type == GGML_TYPE_F16) {
             ggml_fp32_to_fp16_row(staging.data(), (ggml_fp16_t *)t->data, (int)count);  // main.cpp:928-932
         } else {

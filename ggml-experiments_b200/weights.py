@@ -109,19 +109,38 @@ def make_synthetic_weights(variant: str = "s", seed: int = 1234, num_classes: in
     return out
 
 
-def write_weight_file(path: str, tensors: "OrderedDict[str, np.ndarray]") -> int:
-    """Write tensors in the convert-tf-to-ggml.py record layout.  Returns the number of floats written."""
+# Record-format extension (the two TODOs of convert-tf-to-ggml.py:13-14).  The upper half of the n_dims word carries flags; a file
+# without flags is exactly the reference layout and is what the unmodified main.cpp reads.
+FLAG_F16 = 1 << 16            # payload is IEEE f16 instead of f32 ("f16 on disk")
+FLAG_PRETRANSPOSED = 1 << 17  # 2-D dense kernel stored as (out, in): the in-graph cont(permute(w)) of main.cpp:1024 is already applied
+
+
+def write_weight_file(path: str, tensors: "OrderedDict[str, np.ndarray]", f16: str = "none", pretransposed: bool = False) -> int:
+    """Write tensors in the convert-tf-to-ggml.py record layout.  Returns the number of elements written.
+
+    f16 = "none": the reference layout, f32 payloads (default).
+    f16 = "conv": convolution kernels -- the tensors main.cpp:887-889,928-932 rounds to f16 at load time anyway -- are stored as f16:
+                  the loaded model is bit-identical and the file is 23-40 % smaller (XXS ... S).
+    f16 = "all":  every tensor as f16 (dense kernels, biases and norms lose precision: opt-in).
+    pretransposed: 2-D dense kernels are stored (out, in), the layout the matmul consumes (main.cpp:1022-1035 transposes them in-graph)."""
+    assert f16 in ("none", "conv", "all")
     total = 0
     with open(path, "wb") as f:
         for name, arr in tensors.items():
             arr = np.ascontiguousarray(arr, dtype=np.float32)
+            flags = 0
+            if f16 == "all" or (f16 == "conv" and "convolution" in name):
+                flags |= FLAG_F16
+            if pretransposed and arr.ndim == 2 and name.endswith("/kernel:0"):
+                flags |= FLAG_PRETRANSPOSED
+                arr = np.ascontiguousarray(arr.T)
             nb = name.encode("utf-8")
             f.write(struct.pack("i", len(nb)))
             f.write(nb)
-            f.write(struct.pack("i", arr.ndim))
+            f.write(struct.pack("i", arr.ndim | flags))
             for d in arr.shape:
                 f.write(struct.pack("i", int(d)))
-            f.write(arr.tobytes())
+            f.write(arr.astype(np.float16).tobytes() if flags & FLAG_F16 else arr.tobytes())
             total += arr.size
     return total
 
@@ -136,9 +155,16 @@ def read_weight_file(path: str) -> "OrderedDict[str, np.ndarray]":
             (n,) = struct.unpack("i", head)
             name = f.read(n).decode("utf-8")
             (nd,) = struct.unpack("i", f.read(4))
+            flags, nd = nd & ~0xFFFF, nd & 0xFFFF
             dims = struct.unpack("i" * nd, f.read(4 * nd))
             cnt = int(np.prod(dims))
-            out[name] = np.frombuffer(f.read(4 * cnt), dtype=np.float32).reshape(dims).copy()
+            if flags & FLAG_F16:
+                arr = np.frombuffer(f.read(2 * cnt), dtype=np.float16).astype(np.float32).reshape(dims)
+            else:
+                arr = np.frombuffer(f.read(4 * cnt), dtype=np.float32).reshape(dims).copy()
+            if flags & FLAG_PRETRANSPOSED:
+                arr = np.ascontiguousarray(arr.T)  # back to the canonical (in, out)
+            out[name] = arr
     return out
 
 
@@ -224,14 +250,14 @@ def from_hf_state_dict(sd: dict) -> "OrderedDict[str, np.ndarray]":
     return out
 
 
-def export_hf_checkpoint(model_dir: str, out_path: str) -> int:
+def export_hf_checkpoint(model_dir: str, out_path: str, f16: str = "none", pretransposed: bool = False) -> int:
     """Write `weight.ggml` from a local Hugging Face MobileViT checkpoint directory (no network).  Returns the float count."""
     from transformers import AutoModelForImageClassification, MobileViTModel  # imported lazily: tooling, not the product path
     try:
         model = AutoModelForImageClassification.from_pretrained(model_dir, local_files_only=True)
     except Exception:
         model = MobileViTModel.from_pretrained(model_dir, local_files_only=True)
-    return write_weight_file(out_path, from_hf_state_dict(model.state_dict()))
+    return write_weight_file(out_path, from_hf_state_dict(model.state_dict()), f16=f16, pretransposed=pretransposed)
 
 
 def synthetic_images(n: int, h: int = 256, w: int = 256, seed: int = 7) -> np.ndarray:
@@ -260,11 +286,14 @@ if __name__ == "__main__":
     ap.add_argument("--synthetic", choices=sorted(VARIANTS), help="write random-init weights of this variant instead")
     ap.add_argument("--classes", type=int, default=0, help="with --synthetic: add a classifier head with this many classes")
     ap.add_argument("--out", default="weight.ggml")
+    ap.add_argument("--f16", default="none", choices=["none", "conv", "all"], help="store convolution kernels (lossless: the loader rounds them "
+                    "to f16 anyway) or every tensor as f16 (convert-tf-to-ggml.py:13 TODO); the unmodified main.cpp reads only 'none'")
+    ap.add_argument("--pretransposed", action="store_true", help="store dense kernels (out, in) (convert-tf-to-ggml.py:14 TODO)")
     a = ap.parse_args()
     if a.hf:
-        n = export_hf_checkpoint(a.hf, a.out)
+        n = export_hf_checkpoint(a.hf, a.out, a.f16, a.pretransposed)
     elif a.synthetic:
-        n = write_weight_file(a.out, make_synthetic_weights(a.synthetic, num_classes=a.classes))
+        n = write_weight_file(a.out, make_synthetic_weights(a.synthetic, num_classes=a.classes), f16=a.f16, pretransposed=a.pretransposed)
     else:
         ap.error("give --hf DIR or --synthetic VARIANT")
     print(f"{a.out}: {n} floats")

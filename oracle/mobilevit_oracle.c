@@ -173,7 +173,11 @@ void *mvo_load(const char *path) {
         mvo_tensor *t = &m->t[m->n_tensors];
         if (fread(t->name, 1, name_len, f) != (size_t)name_len) { fclose(f); mvo_free(m); return NULL; }
         t->name[name_len] = 0;
-        if (fread(&n_dims, 4, 1, f) != 1 || n_dims < 1 || n_dims > 4) { fclose(f); mvo_free(m); return NULL; }
+        if (fread(&n_dims, 4, 1, f) != 1) { fclose(f); mvo_free(m); return NULL; }
+        /* record-format extension (convert-tf-to-ggml.py:13-14 TODOs): bit 16 = f16 payload, bit 17 = dense kernel stored (out, in) */
+        const int disk_f16 = (n_dims >> 16) & 1, disk_t = (n_dims >> 17) & 1;
+        n_dims &= 0xFFFF;
+        if (n_dims < 1 || n_dims > 4 || (disk_t && n_dims != 2)) { fclose(f); mvo_free(m); return NULL; }
         t->n_dims = n_dims;
         t->n = 1;
         for (int i = 0; i < 4; i++) t->dims[i] = 1;
@@ -184,7 +188,21 @@ void *mvo_load(const char *path) {
             t->n *= (size_t)d;
         }
         t->data = (float *)malloc(t->n * sizeof(float));
-        if (fread(t->data, sizeof(float), t->n, f) != t->n) { fclose(f); free(t->data); mvo_free(m); return NULL; }
+        if (disk_f16) {
+            uint16_t *hbuf = (uint16_t *)malloc(t->n * 2);
+            if (fread(hbuf, 2, t->n, f) != t->n) { fclose(f); free(hbuf); free(t->data); mvo_free(m); return NULL; }
+            for (size_t i = 0; i < t->n; i++) t->data[i] = _cvtsh_ss(hbuf[i]);
+            free(hbuf);
+        } else if (fread(t->data, sizeof(float), t->n, f) != t->n) { fclose(f); free(t->data); mvo_free(m); return NULL; }
+        if (disk_t) { /* back to the canonical (in, out) */
+            const size_t n_out = (size_t)t->dims[0], n_in = (size_t)t->dims[1];
+            float *tr = (float *)malloc(t->n * sizeof(float));
+            for (size_t oo = 0; oo < n_out; oo++)
+                for (size_t ii = 0; ii < n_in; ii++) tr[ii * n_out + oo] = t->data[oo * n_in + ii];
+            free(t->data);
+            t->data = tr;
+            t->dims[0] = (int)n_in; t->dims[1] = (int)n_out;
+        }
         m->n_tensors++;
     }
     fclose(f);

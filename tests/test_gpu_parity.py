@@ -468,3 +468,19 @@ def test_dwreduce_fusion_matches_oracle(G, oracle, weight_files, monkeypatch):
     r = parity_report(feat, ref_f, rtol=1e-2, atol_rms=1e-2)
     assert r["violations"] == 0 and r["rel_l2"] < 5e-3, r
     assert top1_report(pooled, ref_p)["agree"] == 1.0
+
+
+def test_f16_on_disk_and_pretransposed_weight_files_give_identical_features(G, weight_files, tmp_path):
+    """the lossless file flavours (f16 convolution kernels, dense kernels stored (out, in)) load to the same model bit for bit."""
+    from ggml_experiments_b200 import mobilevit as MV
+    imgs = W.synthetic_images(3, 128, 128, seed=7)
+    MV.set_mode(MV.FAST)
+    f0, p0, _ = _run_model(G, weight_files["xs"], imgs, MV.FAST)
+    t = W.read_weight_file(weight_files["xs"])
+    for kw in ({"f16": "conv"}, {"pretransposed": True}, {"f16": "conv", "pretransposed": True}):
+        p = str(tmp_path / "w.ggml")
+        W.write_weight_file(p, t, **kw)
+        f, pp, info = _run_model(G, p, imgs, MV.FAST)
+        assert info["mode"] == MV.FAST
+        np.testing.assert_array_equal(f, f0, err_msg=str(kw))
+        np.testing.assert_array_equal(pp, p0, err_msg=str(kw))

@@ -212,3 +212,48 @@ def test_hf_exporter_on_a_real_hf_module(tmp_path, oracle):
     _, pooled = m.forward(imgs, oracle.PURE_F32)
     logits = m.classify(pooled)
     assert np.abs(logits - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), (np.abs(logits - ref).max(), np.abs(ref).max())
+
+
+# ---- f16-on-disk and pre-transposed dense kernels (convert-tf-to-ggml.py:13-14 TODOs) ----------------------------
+def test_f16_on_disk_and_pretransposed_files_load_to_the_same_model(oracle, tmp_path):
+    import os
+    t = W.make_synthetic_weights("xxs", seed=1234)
+    paths = {}
+    for tag, kw in {"ref": {}, "f16conv": {"f16": "conv"}, "pre": {"pretransposed": True}, "both": {"f16": "conv", "pretransposed": True},
+                    "f16all": {"f16": "all"}}.items():
+        paths[tag] = str(tmp_path / f"w_{tag}.ggml")
+        W.write_weight_file(paths[tag], t, **kw)
+    assert os.path.getsize(paths["f16conv"]) < 0.8 * os.path.getsize(paths["ref"])  # XXS: 47 % of the floats are convolution kernels
+    assert os.path.getsize(paths["f16all"]) < 0.52 * os.path.getsize(paths["ref"])
+    # python reader: canonical shapes come back; f16 conv payloads equal the f16 rounding the loader applies anyway
+    back = W.read_weight_file(paths["both"])
+    for k in t:
+        assert back[k].shape == t[k].shape
+        if "convolution" in k:
+            assert np.array_equal(back[k], t[k].astype(np.float16).astype(np.float32))
+        else:
+            assert np.array_equal(back[k], t[k])
+    # oracle loader: the lossless variants give BIT-identical features
+    imgs = W.synthetic_images(2, 64, 64, seed=7)
+    ref_f, ref_p = oracle.OracleModel(paths["ref"]).forward(imgs)
+    for tag in ("f16conv", "pre", "both"):
+        m = oracle.OracleModel(paths[tag])
+        assert (m.num_tensors, m.num_weights) == (313, 955136)
+        f, p = m.forward(imgs)
+        assert np.array_equal(f, ref_f) and np.array_equal(p, ref_p), tag
+    f, p = oracle.OracleModel(paths["f16all"]).forward(imgs)  # lossy for dense / norm tensors: close, not identical
+    assert np.linalg.norm(f - ref_f) / np.linalg.norm(ref_f) < 5e-3
+
+
+def test_host_loader_reads_the_extended_records(tmp_path):
+    """include/mobilevit_b200.h mvit_load on the CPU (no compute): tensor and weight counts for every file flavour."""
+    import ggml_experiments_b200 as G
+    t = W.make_synthetic_weights("xs", seed=1234)
+    for kw in ({}, {"f16": "conv"}, {"pretransposed": True}, {"f16": "all", "pretransposed": True}):
+        p = str(tmp_path / "w.ggml")
+        W.write_weight_file(p, t, **kw)
+        m = G.MobileViT(p)
+        try:
+            assert (m.num_tensors, m.num_weights) == (313, 1941296), kw
+        finally:
+            m.close()
