@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric: MobileViT-S images/sec at batch 256 (256x256) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variant s] [--batch 256] [--hw 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config s256|xs_sweep|s512|gru] [--weak]
 
 A "step" is one forward pass of the hot path (mobilevit_model::extract_features, main.cpp:604-646, generalised to a
-batch) over one batch of synthetic images.  One process per GPU (torchrun for N>1); the batch shards as independent
-per-GPU sub-batches with no data-path collective (weak scaling: `--batch` images per GPU); torch.distributed is used
-only for the barrier and the max-over-ranks of the timings.
+batch) over one batch of synthetic images.  One process per GPU (torchrun for N>1).  BASELINE configs[2] as written:
+batch 256 in TOTAL, sharded 256/128/64/32 per GPU on 1/2/4/8 GPUs (strong scaling, the default; `--weak` keeps 256 per
+GPU).  The batch shards as independent per-GPU sub-batches with no data-path collective; every rank writes the logits of
+its images into its slice of ONE shared host buffer (the "final host-side gather", ggml_experiments_b200/shard.py) and
+rank 0 checks that buffer bit for bit against its own single-GPU run of the whole batch.  torch.distributed is used
+only for barriers and the max-over-ranks of the timings.
 
   value         device-resident: inputs already in HBM, outputs stay in HBM; CUDA events on the launching stream
-  e2e           through the host API (write the pinned input buffer, mvit_compute, read the host outputs):
-                H2D of the step's images + forward + D2H of features and pooled logits, every step
-  roofline      dominant kernel of the step: algorithmic FLOPs (or bytes) / its CUDA-event time / measured peak
+  e2e           through the host API: H2D of the step's raw u8 images + device-side preprocessing + forward + D2H of
+                features and logits + host gather, every step (f32-image variant reported next to it)
+  roofline      dominant kernel of the step: algorithmic bytes (SURVEY 8d minimum: `bytes_min`) / its CUDA-event time /
+                measured peak; `frac_moved` is the same with the bytes this plan actually moves
   cpu_baseline  the CPU oracle (a port of the reference's ggml algorithm; upstream ggml itself is not available) on a
                 bounded sample of the same workload, all host cores
 
+Other BASELINE configs, same schema (not the driver's default line):
+  --config xs_sweep   configs[1]: MobileViT-XS, batch 1..256 on one GPU (value = batch 256, `sweep` has every batch)
+  --config s512       configs[3]: MobileViT-S at 512x512, 64 images per GPU
+  --config gru        configs[4]: rnn_text_gen GRU cell over 4096 streams, tokens/s
 `--impl reference` times the oracle port alone (rank 0 only), same metric/config.
 """
 from __future__ import annotations
@@ -95,43 +103,121 @@ def cpu_oracle_rate(weight_path: str, variant: str, hw: int, n_images: int, thre
     return n_images / secs, secs
 
 
+def metric_name(args):
+    if args.config == "gru":
+        return f"rnn_text_gen GRU tokens/sec over {args.streams} independent streams"
+    total = args.global_images
+    return f"MobileViT-{args.variant.upper()} images/sec at batch {total}" + (" in total" if args.world > 1 and not args.weak else "")
+
+
+def workload_config(args):
+    if args.config == "gru":
+        return {"workload": f"rnn_text_gen GRU cell (embed 256, units 1024, vocab 66) batched over {args.streams} independent streams, "
+                            f"{args.gru_steps} greedy steps per timed step, random-init weights in the gru.bin layout",
+                "streams": args.streams, "tokens_per_step": args.streams * args.gru_steps, "parallelism": "1 GPU"}
+    in_mb = args.batch * args.hw * args.hw * 12 / 1e6
+    return {"workload": f"MobileViT-{args.variant.upper()} forward (extract_features), conv weights f16, {args.hw}x{args.hw} synthetic images, "
+                        f"random-init weights in convert-tf-to-ggml layout",
+            "variant": args.variant, "per_gpu_batch": args.batch, "global_batch": args.global_images, "image": args.hw,
+            "parallelism": f"independent sub-batches x{args.world} (no collective; host-side gather of the logits into one shared buffer)",
+            "l2": ("inputs larger than L2: %.0f MB of f32 images per step per GPU" if in_mb > 126 else
+                   "%.0f MB of f32 images per step per GPU (< L2), evicted between steps by the forward itself, which streams its whole activation arena through L2") % in_mb}
+
+
 def run_reference(args, weight_path: str):
+    """--impl reference: the CPU oracle port alone, all host threads, a bounded sample of the workload per step."""
     from oracle import binding
     binding.build()
     cores = binding.lib().mvo_max_threads()
-    sample = min(args.batch, max(8, cores))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_rate(weight_path, args.variant, args.hw, min(sample, cores), cores)
-    times = []
-    for _ in range(args.steps):
-        rate, secs = cpu_oracle_rate(weight_path, args.variant, args.hw, sample, cores)
-        times.append(secs)
+    if args.config == "gru":
+        import numpy as np
+        from oracle import gru_oracle as GO
+        w = GO.make_synthetic_gru(seed=5)
+        streams, steps = 256, 10  # bounded sample: the numpy restatement is single-threaded BLAS-free matmul per step
+        first = (np.arange(streams) * 7 % 66).astype(np.int32)
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            GO.generate_batch(w, first, steps)
+            times.append(time.perf_counter() - t0)
+        value = streams * steps * args.steps / sum(times)
+        desc = f"{streams} of {args.streams} streams x {steps} of {args.gru_steps} steps per timed step, numpy restatement of gru_forward (rnn.cpp:186-263)"
+        unit = "tokens/s"
+    else:
+        sample = min(args.batch, max(8, cores))
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_oracle_rate(weight_path, args.variant, args.hw, min(sample, cores), cores)
+        times = []
+        for _ in range(args.steps):
+            _, secs = cpu_oracle_rate(weight_path, args.variant, args.hw, sample, cores)
+            times.append(secs)
+        value = sample * args.steps / sum(times)
+        desc = f"{sample} of {args.global_images} images per step, batch-1 graphs looped over {cores} host threads"
+        unit = "images/s"
     tot = sum(times)
-    value = sample * args.steps / tot
-    desc = f"{sample} of {args.batch} images per step, batch-1 graphs looped over {cores} host threads"
+    cfg = dict(workload_config(args), reference_sample=desc)
     return {
-        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f16 conv operands / f32 accumulate, f32 dense (ggml CPU semantics)",
-        "data": "synthetic", "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
-                         "note": "CPU oracle restatement of the reference's ggml algorithm; upstream ggml is not vendored"},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f16 conv operands / f32 accumulate, f32 dense (ggml CPU semantics)",
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "CPU oracle restatement of the reference's ggml algorithm; upstream ggml is not vendored (oracle/_ref runs the "
+                                 "reference's own programs on the same restatement, single-threaded like main.cpp:640)"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
 
 
-def metric_name(args):
-    return f"MobileViT-{args.variant.upper()} images/sec at batch {args.global_images if args.strong else args.batch}" + (" (total, strong scaling)" if args.strong else "")
+def ctypes_void(x):
+    import ctypes
+    return ctypes.c_void_p(x)
 
 
-def workload_config(args):
-    return {"workload": f"MobileViT-{args.variant.upper()} forward (extract_features), conv weights f16, {args.hw}x{args.hw} synthetic images, "
-                        f"random-init weights in convert-tf-to-ggml layout",
-            "variant": args.variant, "per_gpu_batch": args.batch, "global_batch": args.global_images, "image": args.hw,
-            "parallelism": f"independent sub-batches x{args.gpus} (no collective)",
-            "l2": ("inputs larger than L2: %.0f MB of f32 images per step per GPU" if args.batch * args.hw * args.hw * 12 > 126e6 else
-                   "%.0f MB of f32 images per step per GPU (< L2), evicted between steps by the forward itself, which streams its whole activation arena through L2") % (args.batch * args.hw * args.hw * 12 / 1e6)}
+def run_gru(args, rank, world):
+    """BASELINE configs[4]: the batched GRU generator through the ggml boundary, loop resident on the device."""
+    import numpy as np
+    import torch
+    from ggml_experiments_b200 import mobilevit as MV
+    from ggml_experiments_b200.gru import GRU
+    from oracle import gru_oracle as GO
+    assert torch.cuda.is_available()
+    MV.set_mode(MV.FAST)
+    w = GO.make_synthetic_gru(seed=5)
+    path = os.path.join(tempfile.mkdtemp(prefix="gru_bench_"), "gru.bin")
+    GO.write_gru_bin(path, w)
+    m = GRU(path)
+    B, T = args.streams, args.gru_steps
+    first = (np.arange(B) * 7 % 66).astype(np.int32)
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        m.generate(first, T)
+    n_before = len(sampler.rows)
+    dev_ms, wall = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        toks, state, ms = m.generate(first, T)  # ms: CUDA-event time of the T-step device loop
+        dev_ms += ms
+    wall = time.perf_counter() - wall
+    sampler.rows = sampler.rows[n_before:]
+    clocks = sampler.stop()
+    ref, margins, _ = GO.generate_batch(w, first[:64], 16)
+    agree = float((toks[:16, :64] == ref).mean())
+    peaks = load_peaks()
+    flop = 2.0 * B * (1024 * 3072 + 1024 * 66)  # per step; the embedding projection is a folded table lookup
+    value = B * T * args.steps / (dev_ms / 1e3)
+    out = {"metric": metric_name(args), "value": value, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f16 operands / f32 accumulate (tcgen05), f32 gates and state", "data": "synthetic", "config": workload_config(args),
+           "e2e": {"value": B * T * args.steps / wall, "unit": "tokens/s", "h2d_bytes_per_step": int(first.nbytes), "d2h_bytes_per_step": int(toks.nbytes + state.nbytes),
+                   "api": "gru_generate (include/gru_b200.h): first tokens up, T device-resident steps, all chosen tokens + final state down"},
+           "gpu_launches": 9 * T * args.steps, "clocks": clocks,
+           "roofline": {"kernel": "gemm_tcgen05 (recurrent 4096x3072x1024 + dense)", "bound": "tensor", "achieved": round(flop * T * args.steps / (dev_ms / 1e3) / 1e12, 2),
+                        "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(flop * T * args.steps / (dev_ms / 1e3) / 1e12 / peaks["tflops_sustained"], 4),
+                        "traffic": None, "note": "whole step (GEMMs + gate kernel + argmax + feedback copies) against the tensor peak; strictly sequential over T"},
+           "cpu_baseline": None, "token_agreement_with_numpy_oracle_first_16_steps": agree}
+    m.close()
+    return out
 
 
 def main():
@@ -140,26 +226,38 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="s", choices=["s", "xs", "xxs"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU (with --strong: images in total)")
-    ap.add_argument("--strong", action="store_true",
-                    help="strong scaling: --batch images in TOTAL, batch/N per GPU (BASELINE configs[2] as literally written: 256/128/64/32 "
-                         "per GPU on 1/2/4/8 GPUs); the default is weak scaling, 256 per GPU")
-    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--config", default="s256", choices=["s256", "xs_sweep", "s512", "gru"])
+    ap.add_argument("--variant", default=None, choices=["s", "xs", "xxs"])
+    ap.add_argument("--batch", type=int, default=None, help="images in TOTAL (default 256; with --weak: images per GPU)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --batch images per GPU (the default is BASELINE configs[2] as written: "
+                                                        "--batch images in total, batch/N per GPU)")
+    ap.add_argument("--strong", action="store_true", help="(default since round 2; kept for compatibility)")
+    ap.add_argument("--hw", type=int, default=None)
     ap.add_argument("--mode", default=os.environ.get("GGML_B200_MODE", "fast"), choices=["fast", "exact"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4096, help="--config gru: independent streams")
+    ap.add_argument("--gru-steps", type=int, default=200, help="--config gru: greedy steps per timed step")
+    ap.add_argument("--allow-no-cuda-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    args.global_images = args.batch * (1 if args.strong else max(args.gpus, world))
-    if args.strong:  # the total stays --batch; every GPU takes an equal share
-        if args.batch % world:
-            raise SystemExit(f"--strong: batch {args.batch} is not divisible by {world} GPUs")
-        args.batch //= world
+    args.world = world
+    defaults = {"s256": ("s", 256, 256), "xs_sweep": ("xs", 256, 256), "s512": ("s", 512, 64), "gru": ("s", 256, 256)}[args.config]
+    args.variant = args.variant or defaults[0]
+    args.hw = args.hw or defaults[1]
+    if args.config == "s512":
+        args.weak = True  # configs[3] is specified per GPU: 64 images per GPU
+    total = args.batch or defaults[2]
+    if args.weak:
+        args.batch, args.global_images = total, total * world
+    else:
+        if total % world:
+            raise SystemExit(f"batch {total} is not divisible by {world} GPUs")
+        args.batch, args.global_images = total // world, total
 
     from ggml_experiments_b200 import weights as W
     tmpdir = tempfile.mkdtemp(prefix=f"mvit_bench_r{rank}_")
@@ -172,12 +270,18 @@ def main():
         print(json.dumps(run_reference(args, weight_path)), flush=True)
         return 0
 
+    if args.config == "gru":
+        if rank == 0:
+            print(json.dumps(run_gru(args, rank, world)), flush=True)
+        return 0
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import ggml_experiments_b200 as G
     from ggml_experiments_b200 import mobilevit as MV
+    from ggml_experiments_b200 import shard
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product path)"
     torch.cuda.set_device(local_rank)
@@ -193,16 +297,20 @@ def main():
     model = G.MobileViT(weight_path)
     n, h, w = args.batch, args.hw, args.hw
     model.prepare(n, h, w)
-    info = model.plan_info(n, h, w)
 
-    # synthetic inputs, written in place into the library's pinned input buffer (main.cpp:627-634 flow)
-    host_in = model.host_input(n, h, w)
-    base = W.synthetic_images(min(n, 16), h, w, seed=7 + rank)
+    # synthetic inputs: ONE global batch (image g = pattern g % 16; image 0 = the reference's own test pattern, main.cpp:680-688);
+    # this rank owns the contiguous slice [lo, hi) of it
+    lo, hi = shard.shard_range(args.global_images, rank, world)
+    assert hi - lo == n
+    base = W.synthetic_images(16, h, w, seed=7)
+    host_in = model.host_input(n, h, w)  # written in place into the library's pinned input buffer (main.cpp:627-634 flow)
     for i in range(n):
-        host_in[i] = base[i % base.shape[0]]
+        host_in[i] = base[(lo + i) % 16]
     feat, pooled = model.compute(n, h, w)  # first full pass: H2D + forward + D2H (also warms everything up)
     pooled0 = pooled.copy()
     assert np.isfinite(feat).all()
+    gather = shard.HostGather(f"mvit_bench_gather_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}",
+                              args.global_images, pooled.shape[1], rank, world, dist if world > 1 else None)
 
     def barrier():
         if world > 1:
@@ -216,6 +324,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def device_rate(mdl, nb, steps, warm):
+        """device-resident: CUDA-graph replays back to back, CUDA events on the launching stream, max over ranks"""
+        for _ in range(warm):
+            mdl.forward_device(nb, h, w)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            mdl.forward_device(nb, h, w)
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # ---- device-resident throughput ("value") -------------------------------------------------------------
     # the clock sampler (nvidia-smi -lms 100) needs a few hundred ms to deliver its first row, more on an 8-GPU box, while the
     # timed region is ~0.1 s: it is started before the warm-up so that it is already streaming during the timed steps
@@ -225,13 +346,7 @@ def main():
         model.forward_device(n, h, w)
     barrier()
     n_before = len(sampler.rows)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        model.forward_device(n, h, w)
-    ev1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    dev_ms = device_rate(model, n, args.steps, 0)
     info = model.plan_info(n, h, w)  # re-read after the replays: `cuda_graph` says whether they went through the captured graph
     extra_s = 0.0
     if len(sampler.rows) - n_before < 2:  # region shorter than the sampling period: keep the identical load running until sampled
@@ -245,11 +360,25 @@ def main():
     clocks = sampler.stop()
     clocks["window"] = "timed steps" if extra_s == 0.0 else f"timed steps + {extra_s:.2f} s of the identical load (region shorter than the 100 ms sampling period)"
     value = args.batch * world * args.steps / (dev_ms / 1e3)
+    if info["mode"] == 0 and not info["cuda_graph"] and not args.allow_no_cuda_graph:
+        raise SystemExit("bench.py: the plan did not run as a captured CUDA graph (see the library's message above); a launch-bound number "
+                         "would be reported.  Pass --allow-no-cuda-graph to measure anyway.")
+
+    sweep = None
+    if args.config == "xs_sweep" and world == 1:  # configs[1]: batch sweep 1..256 on one GPU, device-resident
+        sweep = []
+        for b in (1, 2, 4, 8, 16, 32, 64, 128, 256):
+            model.prepare(b, h, w)
+            reps = max(args.steps, min(200, 4000 // b))
+            ms = device_rate(model, b, reps, 3)
+            sweep.append({"batch": b, "images_per_s": round(b * reps / (ms / 1e3), 1), "ms_per_step": round(ms / reps, 4)})
+            if b != n:
+                model.release(b, h, w)
 
     # ---- end to end through the host API ("e2e") ------------------------------------------------------------
-    # Two pipelined slots (mvit_slot_*): every step uploads ITS batch from pinned host memory, runs the forward and
-    # downloads features + logits; the copies of one slot overlap the kernels of the other.  The synchronous
-    # single-call latency (mvit_compute) is reported next to it.
+    # Two pipelined slots (mvit_slot_*): every step uploads ITS batch from pinned host memory, runs the forward,
+    # downloads features + logits and writes the logits into this rank's slice of the shared gather buffer; the copies
+    # of one slot overlap the kernels of the other.  The synchronous single-call latency (mvit_compute) is reported too.
     for _ in range(2):
         model.compute(n, h, w)
     barrier()
@@ -270,17 +399,19 @@ def main():
     for i in range(args.steps):
         s = i & 1
         if i >= 2:
-            model.slot_wait(n, h, w, s)    # step i-2 of this slot: its D2H has landed, buffers are reusable
+            f, p = model.slot_wait(n, h, w, s)    # step i-2 of this slot: its D2H has landed, buffers are reusable
+            gather.write(p)
         model.slot_submit(n, h, w, s)      # H2D(step i) + forward + D2H, asynchronous
     for s in range(2):
         f, p = model.slot_wait(n, h, w, s)
+        gather.write(p)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = args.batch * world * args.steps / e2e_s
     h2d = n * h * w * 3 * 4
     d2h = int(f.nbytes + p.nbytes)
 
     # Same pipeline fed with uint8 images: the resize / 1/255 of sam_image_preprocess (main.cpp:538-601) runs on
-    # the device, 4x fewer bytes cross PCIe.  Reported next to the f32 headline, not instead of it.
+    # the device, 4x fewer bytes cross PCIe.
     img_u8 = np.clip(np.rint(host_in * 255.0), 0, 255).astype(np.uint8)  # the same pictures as the f32 path, as 8-bit pixels
     for s in range(2):
         model.slot_input_u8(n, h, w, s, h, w)[:] = img_u8
@@ -293,10 +424,12 @@ def main():
     for i in range(args.steps):
         s = i & 1
         if i >= 2:
-            model.slot_wait(n, h, w, s)
+            fu, pu = model.slot_wait(n, h, w, s)
+            gather.write(pu)
         model.slot_submit_u8(n, h, w, s, h, w)
     for s in range(2):
-        model.slot_wait(n, h, w, s)
+        fu, pu = model.slot_wait(n, h, w, s)
+        gather.write(pu)
     u8_s = max_over_ranks(time.perf_counter() - t0)
     model.host_input_u8(n, h, w, h, w)[:] = img_u8
     model.compute_u8(n, h, w, h, w)
@@ -307,7 +440,29 @@ def main():
     u8_sync_s = max_over_ranks(time.perf_counter() - t0)
     e2e_u8 = {"value": args.batch * world * args.steps / u8_s, "unit": "images/s", "h2d_bytes_per_step": int(img_u8.nbytes),
               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * u8_s / args.steps, "synchronous_call_ms": 1e3 * u8_sync_s / args.steps,
-              "api": "mvit_slot_submit_u8 (device-side sam_image_preprocess), 2 slots in flight"}
+              "api": "mvit_slot_submit_u8 (device-side sam_image_preprocess), 2 slots in flight, logits gathered into one shared host buffer"}
+
+    # ---- the gathered logits of all ranks == one GPU running the whole batch, bit for bit ---------------------
+    barrier()
+    gather_check = None
+    if rank == 0:
+        got = gather.full.copy()  # u8 pipeline, last step of every rank
+        glob_u8 = np.clip(np.rint(base[np.arange(args.global_images) % 16] * 255.0), 0, 255).astype(np.uint8)
+        g = args.global_images
+        if world == 1 or g <= 512:  # one plan for the WHOLE batch on this GPU: what a 1-GPU run of the same job computes
+            model.host_input_u8(g, h, w, h, w)[:] = glob_u8
+            _, ref = model.compute_u8(g, h, w, h, w)
+            how = f"rank 0 ran all {g} images as one batch"
+        else:  # weak scaling with a huge global batch: rank 0 re-runs every rank's sub-batch
+            ref = np.empty_like(got)
+            for r in range(world):
+                a, b = shard.shard_range(g, r, world)
+                model.host_input_u8(n, h, w, h, w)[:] = glob_u8[a:b]
+                ref[a:b] = model.compute_u8(n, h, w, h, w)[1]
+            how = f"rank 0 re-ran the {world} sub-batches of {n} images"
+        equal = bool(np.array_equal(got, ref))
+        gather_check = {"rows": int(g), "width": int(got.shape[1]), "bytes_per_step_per_rank": int(pu.nbytes), "bit_equal_to_single_gpu": equal, "how": how}
+        assert equal, "the gathered logits of the N-rank run differ from the single-GPU run of the same images"
 
     # ---- per-kernel roofline (rank 0) -----------------------------------------------------------------------
     peaks = load_peaks()
@@ -316,18 +471,21 @@ def main():
         prof = model.profile(n, h, w, reps=3)
         agg = {}
         for r in prof:
-            a = agg.setdefault(r["kernel"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-            a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["launches"] += 1
+            a = agg.setdefault(r["kernel"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "bytes_min": 0.0, "launches": 0})
+            a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["bytes_min"] += r.get("bytes_min", r["bytes"]); a["launches"] += 1
         tot_ms = sum(a["ms"] for a in agg.values()) or 1.0
         ridge = peaks["tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            ai = a["flops"] / a["bytes"] if a["bytes"] else 0.0
+            ai = a["flops"] / a["bytes_min"] if a["bytes_min"] else 0.0
             bound = "tensor" if ai > ridge else "hbm"
-            ach = (a["flops"] / (a["ms"] * 1e-3) / 1e12) if bound == "tensor" else (a["bytes"] / (a["ms"] * 1e-3) / 1e9)
+            secs = a["ms"] * 1e-3
+            ach = (a["flops"] / secs / 1e12) if bound == "tensor" else (a["bytes_min"] / secs / 1e9)
             peak = peaks["tflops_sustained"] if bound == "tensor" else peaks["hbm_gbs"]
             kernels.append({"kernel": k, "launches": a["launches"], "ms_per_step": round(a["ms"], 4), "share": round(a["ms"] / tot_ms, 4),
                             "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
-                            "frac": round(ach / peak, 4), "gflop": round(a["flops"] / 1e9, 3), "mbytes": round(a["bytes"] / 1e6, 2)})
+                            "frac": round(ach / peak, 4), "gflop": round(a["flops"] / 1e9, 3), "mbytes_min": round(a["bytes_min"] / 1e6, 2),
+                            "mbytes_moved": round(a["bytes"] / 1e6, 2),
+                            "frac_moved": round((a["flops"] / secs / 1e12 if bound == "tensor" else a["bytes"] / secs / 1e9) / peak, 4)})
         if kernels:
             d = kernels[0]
             traffic = None
@@ -337,7 +495,10 @@ def main():
             except Exception:
                 pass
             roofline = {"kernel": d["kernel"], "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                        "frac": d["frac"], "traffic": traffic, "share_of_step": d["share"], "launches_per_step": d["launches"],
+                        "frac": d["frac"], "bytes_min": d["mbytes_min"] * 1e6, "bytes_moved": d["mbytes_moved"] * 1e6, "frac_moved": d["frac_moved"],
+                        "traffic": traffic, "traffic_source": "static: mean dram__bytes per launch of this kernel from the committed ncu capture "
+                                                              "(profiles/traffic.json), batch 256 per GPU; not measured in this run",
+                        "share_of_step": d["share"], "launches_per_step": d["launches"],
                         "peak_source": peaks["source"] + (" sustained" if d["bound"] == "tensor" else " copy bandwidth")}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------
@@ -360,17 +521,17 @@ def main():
         per_gpu = value / world
         out = {
             "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ggml conv rounding points), f32 residual stream",
             "data": "synthetic", "config": dict(workload_config(args), mode=("fast" if info["mode"] == 0 else "exact")),
             # headline e2e = the reference's own entry: raw u8 images in (what stbi_load hands to sam_image_preprocess, main.cpp:
             # 517-601), features + logits out; the resize / 1/255 runs on the device.  The f32-image variant (the caller has
-            # already run sam_image_preprocess on the CPU) is reported next to it: 4x the PCIe bytes, and with 8 GPUs on one
-            # host it is bound by host memory / PCIe (133 GB/s aggregate measured), not by the GPUs.
+            # already run sam_image_preprocess on the CPU, i.e. extract_features(sam_image_f32&), main.cpp:604) is reported next to it.
             "e2e": dict(e2e_u8, f32_input={"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                            "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mvit_slot_submit/mvit_slot_wait, 2 slots in flight",
                                            "synchronous_call_ms": 1e3 * sync_s / args.steps,
                                            "synchronous_call_images_per_s": args.batch * world * args.steps / sync_s}),
+            "gather": gather_check,
             "gpu_launches": info["launches"] * args.steps,
             "clocks": clocks,
             "roofline": roofline,
@@ -378,20 +539,19 @@ def main():
             "model_roofline": {"gflop_per_image": gf, "tflops_achieved_per_gpu": per_gpu * gf / 1e3,
                                "frac_of_tensor_peak": per_gpu * gf / 1e3 / peaks["tflops_sustained"],
                                "layerwise_hbm_bound_images_per_s": peaks["hbm_gbs"] * 1e3 / ACT_MB_PER_IMAGE.get(args.variant, 1e9) / (args.hw / 256.0) ** 2,
+                               "frac_of_layerwise_hbm_bound": per_gpu / (peaks["hbm_gbs"] * 1e3 / ACT_MB_PER_IMAGE.get(args.variant, 1e9) / (args.hw / 256.0) ** 2),
                                "peaks": peaks},
             "kernels": kernels,
             "plan": info,
         }
+        if sweep is not None:
+            out["sweep"] = sweep
         print(json.dumps(out), flush=True)
+    gather.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
-
-
-def ctypes_void(x):
-    import ctypes
-    return ctypes.c_void_p(x)
 
 
 if __name__ == "__main__":

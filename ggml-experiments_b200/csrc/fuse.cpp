@@ -862,7 +862,8 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const int N = in->N, OC = o->C, act = n->act;
                 __half * o16 = o->p16; float * o32 = o->p32;
                 add_launch(plan, "stem_conv3x3s2_bn_silu", [=](cudaStream_t st) { launch_stem(x, sn, sy, sx, sc, N, (int)H, (int)W, wt, OC, scale, shift, act, o16, o32, st); },
-                           2.0 * o->rows() * OC * 27, (double)in->rows() * 12 + (double)o->rows() * OC * (o16 ? 2 : 0) + (double)o->rows() * OC * (o32 ? 4 : 0), what);
+                           2.0 * o->rows() * OC * 27, (double)in->rows() * 12 + (double)o->rows() * OC * (o16 ? 2 : 0) + (double)o->rows() * OC * (o32 ? 4 : 0), what,
+                           (double)in->rows() * 6 + (double)o->rows() * OC * 2);
             } break;
             case FK_DW: {
                 FVal * in = n->in[0];
@@ -933,7 +934,8 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const char * kname = n->kind == FK_CONV1 ? "gemm_tcgen05_conv1x1" : (n->kind == FK_QKV ? "gemm_tcgen05_qkv" : "gemm_tcgen05_linear");
                 const double bytes = (double)in->rows() * in->C * 2 + (double)o->C * in->C * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0)) +
                                      (n->res ? (double)o->rows() * o->C * 4 : 0.0);
-                add_launch(plan, kname, [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * in->rows() * o->C * in->C, bytes, what);
+                add_launch(plan, kname, [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * in->rows() * o->C * in->C, bytes, what,
+                           (double)in->rows() * in->C * 2 + (double)o->C * in->C * 2 + (double)o->rows() * o->C * 2);
             } break;
             case FK_IR: {
                 FVal *  in = n->in[0];
@@ -950,7 +952,8 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const double flops = 2.0 * in->rows() * E * in->C + 2.0 * o->rows() * E * 9 + 2.0 * o->rows() * o->C * E;
                 const double bytes = (double)in->rows() * in->C * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0) + (n->res ? 4 : 0)) +
                                      2.0 * ((double)E * in->C + 9.0 * E + (double)o->C * E);
-                add_launch(plan, "ir_fused_expand_dw_reduce", [IL](cudaStream_t st) { ir_fused_launch(*IL, st); }, flops, bytes, what + cfg);
+                add_launch(plan, "ir_fused_expand_dw_reduce", [IL](cudaStream_t st) { ir_fused_launch(*IL, st); }, flops, bytes, what + cfg,
+                           (double)in->rows() * in->C * 2 + (double)o->rows() * o->C * 2 + 2.0 * ((double)E * in->C + 9.0 * E + (double)o->C * E));
             } break;
             case FK_CONV3: {
                 FVal * a = n->in[0];
@@ -965,7 +968,8 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 if (!conv3x3_prepare(*L, a->p16, a->C, b ? b->p16 : nullptr, b ? b->C : 0, a->N, a->H, a->W, P.pool.ptr<__half>(n->c_w), o->C, ep)) return false;
                 const int ict = a->C + (b ? b->C : 0);
                 const double bytes = (double)a->rows() * ict * 2 + (double)o->C * 9 * ict * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0));
-                add_launch(plan, "conv3x3_tcgen05_implicit_gemm", [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * a->rows() * o->C * 9 * ict, bytes, what);
+                add_launch(plan, "conv3x3_tcgen05_implicit_gemm", [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * a->rows() * o->C * 9 * ict, bytes, what,
+                           (double)a->rows() * ict * 2 + (double)o->C * 9 * ict * 2 + (double)o->rows() * o->C * 2);
             } break;
             case FK_LN: {
                 FVal * in = n->in[0];

@@ -528,7 +528,7 @@ extern "C" struct ggml_cgraph ggml_build_forward(struct ggml_tensor * tensor) {
 }
 
 // GGML_B200_DUMP_NODES=<file> (per-node plans only, graphs of more than 256 nodes): after the compute, one line per node --
-// index, op, shape, sum and sum of |x| in double -- in the format oracle/ggml_cpu_ref.c writes with GGML_CPU_REF_DUMP, so the
+// index, op, shape, sum and sum of |x| in double -- in the format the CPU run of the same program writes (test infrastructure, GGML_CPU_REF_DUMP), so the
 // unmodified reference program can be compared node by node between its CPU run and its run on this library.
 static void dump_nodes(Plan * plan, ggml_cgraph * gf, const char * path) {
     static const char * names[GGML_OP_COUNT] = {"NONE", "ADD", "SUB", "MUL", "DIV", "SQRT", "SILU", "TANH", "NORM", "SOFT_MAX", "MUL_MAT", "REPEAT", "CONCAT",

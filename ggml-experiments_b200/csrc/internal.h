@@ -100,7 +100,8 @@ using Launch = std::function<void(cudaStream_t)>;
 struct LaunchMeta {
     const char * kernel = "";
     std::string  what;
-    double       flops = 0, bytes = 0;
+    double       flops = 0, bytes = 0;  // bytes: what THIS plan moves (f32 side copies of the residual stream, residual reads, weights)
+    double       bytes_min = 0;         // SURVEY 8(d) layer-wise minimum: input f16 once + output f16 once (+ weights); <= bytes
 };
 
 struct Plan {
@@ -128,13 +129,15 @@ struct Plan {
     size_t                u8_stage_bytes = 0;
     cudaEvent_t           compute_done   = nullptr;  // recorded after this plan's kernels on its private stream
     cudaStream_t          private_stream = nullptr;  // set by ggml_b200_graph_use_private_stream (pipelined submission)
+    bool                  concurrent     = false;    // lane of a group (ggml_b200_graph_group_begin): overlaps its siblings, no FIFO chain
+    cudaEvent_t           group_ev = nullptr, fork_ev = nullptr;
     ~Plan();
 };
 
 // plan.cpp
 Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf);
 void   run_plan(Plan * plan, bool wait_for_results = true);
-void   add_launch(Plan * plan, const char * kernel, Launch l, double flops = 0, double bytes = 0, std::string what = "");
+void   add_launch(Plan * plan, const char * kernel, Launch l, double flops = 0, double bytes = 0, std::string what = "", double bytes_min = -1);
 void   destroy_plans_of(ggml_context * ctx);
 void   fix_graph_pointers(ggml_cgraph * gf);
 

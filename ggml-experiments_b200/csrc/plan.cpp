@@ -100,13 +100,14 @@ void ArenaPlanner::release(int64_t off, int64_t bytes) {
     }
 }
 
-void add_launch(Plan * plan, const char * kernel, Launch l, double flops, double bytes, std::string what) {
+void add_launch(Plan * plan, const char * kernel, Launch l, double flops, double bytes, std::string what, double bytes_min) {
     plan->launches.push_back(std::move(l));
     LaunchMeta m;
     m.kernel = kernel;
     m.what   = std::move(what);
     m.flops  = flops;
     m.bytes  = bytes;
+    m.bytes_min = bytes_min >= 0 ? bytes_min : bytes;
     plan->meta.push_back(std::move(m));
 }
 
@@ -145,6 +146,8 @@ Plan::~Plan() {
         cudaEventDestroy(compute_done);
     }
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (group_ev) cudaEventDestroy(group_ev);
+    if (fork_ev) cudaEventDestroy(fork_ev);
     if (u8_stage) cudaFree(u8_stage);
     if (history) cudaFree(history);
     for (void * p : owned_device) cudaFree(p);
@@ -405,14 +408,15 @@ void run_plan(Plan * plan, bool wait_for_results) {
     // Pipelined slots: the copies of one slot overlap the kernels of another, but the forwards themselves run FIFO --
     // two forwards sharing the SMs only thrash L2 and fight for CTA slots (bench e2e 9.4 -> see profiles/README.md).
     static const bool chain = getenv("GGML_B200_SLOT_OVERLAP") == nullptr;
-    if (plan->private_stream && chain && rt.compute_chain) B200_CHECK(cudaStreamWaitEvent(st, rt.compute_chain, 0));
+    const bool chained = plan->private_stream && chain && !plan->concurrent;
+    if (chained && rt.compute_chain) B200_CHECK(cudaStreamWaitEvent(st, rt.compute_chain, 0));
     if (plan->graph_exec) {
         B200_CHECK(cudaGraphLaunch(plan->graph_exec, st));
     } else {
         for (auto & l : plan->launches) l(st);
     }
     B200_CHECK(cudaGetLastError());
-    if (plan->private_stream && chain) {
+    if (chained) {
         if (!plan->compute_done) B200_CHECK(cudaEventCreateWithFlags(&plan->compute_done, cudaEventDisableTiming));
         B200_CHECK(cudaEventRecord(plan->compute_done, st));
         rt.compute_chain = plan->compute_done;
@@ -515,6 +519,38 @@ extern "C" int ggml_b200_graph_compute_steps(struct ggml_context * ctx, struct g
     plan->download_outputs = down;
     return 0;
 }
+// ---- concurrent lanes: several graphs (sub-batches of ONE request) on private streams at the same time ----------------------
+// A forward of a few images is a chain of ~80 short kernels, each filling a fraction of the 148 SMs and each paying its own
+// ramp-up / drain; run as S independent chains on S streams, the chains fill each other's gaps (strong scaling at 32 images per
+// GPU: DESIGN.md).  begin: every lane's stream waits for the owner stream (the library's current stream, or lane 0's own stream
+// for pipelined slots); the caller then enqueues uploads / ggml_b200_graph_compute_async per lane; end: the owner waits for all.
+static cudaStream_t group_owner(Plan ** pl, int on_current_stream) { return on_current_stream ? current_stream() : pl[0]->private_stream; }
+extern "C" void ggml_b200_graph_group_begin(struct ggml_cgraph ** gfs, int n, int on_current_stream) {
+    std::vector<Plan *> pl((size_t)n);
+    for (int i = 0; i < n; i++) {
+        if (!gfs[i]->plan) B200_ABORT("ggml_b200_graph_group_begin: call ggml_b200_graph_prepare first");
+        pl[(size_t)i] = (Plan *)gfs[i]->plan;
+        if (!pl[(size_t)i]->private_stream) B200_CHECK(cudaStreamCreateWithFlags(&pl[(size_t)i]->private_stream, cudaStreamNonBlocking));
+        pl[(size_t)i]->concurrent = true;  // lanes of one request overlap by design: no FIFO chain between them
+        if (!pl[(size_t)i]->group_ev) B200_CHECK(cudaEventCreateWithFlags(&pl[(size_t)i]->group_ev, cudaEventDisableTiming));
+    }
+    cudaStream_t owner = group_owner(pl.data(), on_current_stream);
+    if (!pl[0]->fork_ev) B200_CHECK(cudaEventCreateWithFlags(&pl[0]->fork_ev, cudaEventDisableTiming));
+    B200_CHECK(cudaEventRecord(pl[0]->fork_ev, owner));
+    for (int i = 0; i < n; i++)
+        if (pl[(size_t)i]->private_stream != owner) B200_CHECK(cudaStreamWaitEvent(pl[(size_t)i]->private_stream, pl[0]->fork_ev, 0));
+}
+extern "C" void ggml_b200_graph_group_end(struct ggml_cgraph ** gfs, int n, int on_current_stream) {
+    std::vector<Plan *> pl((size_t)n);
+    for (int i = 0; i < n; i++) pl[(size_t)i] = (Plan *)gfs[i]->plan;
+    cudaStream_t owner = group_owner(pl.data(), on_current_stream);
+    for (int i = 0; i < n; i++) {
+        if (pl[(size_t)i]->private_stream == owner) continue;
+        B200_CHECK(cudaEventRecord(pl[(size_t)i]->group_ev, pl[(size_t)i]->private_stream));
+        B200_CHECK(cudaStreamWaitEvent(owner, pl[(size_t)i]->group_ev, 0));
+    }
+}
+
 extern "C" void ggml_b200_graph_wait(struct ggml_cgraph * gf) {
     if (!gf->plan) return;
     Plan * p = (Plan *)gf->plan;
@@ -641,8 +677,8 @@ extern "C" int ggml_b200_graph_profile_json(struct ggml_cgraph * gf, int reps, c
     std::string out = "[";
     char        tmp[768];
     for (size_t i = 0; i < n; i++) {
-        snprintf(tmp, sizeof tmp, "%s{\"kernel\":\"%s\",\"what\":\"%.120s\",\"ms\":%.6f,\"flops\":%.0f,\"bytes\":%.0f}", i ? "," : "",
-                 p->meta[i].kernel, p->meta[i].what.c_str(), ms[i] / reps, p->meta[i].flops, p->meta[i].bytes);
+        snprintf(tmp, sizeof tmp, "%s{\"kernel\":\"%s\",\"what\":\"%.120s\",\"ms\":%.6f,\"flops\":%.0f,\"bytes\":%.0f,\"bytes_min\":%.0f}", i ? "," : "",
+                 p->meta[i].kernel, p->meta[i].what.c_str(), ms[i] / reps, p->meta[i].flops, p->meta[i].bytes, p->meta[i].bytes_min);
         out += tmp;
     }
     out += "]";

@@ -176,13 +176,9 @@ bool model::load(const std::string & path) {
     return true;
 }
 
+static void free_graph(forward_graph & g);
 model::~model() {
-    for (auto & kv : graphs) {
-        ggml_graph_release_plan(kv.second.gf);
-        ggml_free(kv.second.ctx);
-        ggml_b200_host_free(kv.second.pinned_arena);
-        ggml_b200_host_free(kv.second.input_u8);
-    }
+    for (auto & kv : graphs) free_graph(kv.second);
     if (ctx_w) ggml_free(ctx_w);
 }
 
@@ -324,13 +320,47 @@ ggml_tensor * model::build_forward(ggml_context * ctx, ggml_tensor * images_hwc,
     return x;
 }
 
+// Concurrent lanes (MVIT_LANES=S, default 1): a request of n images runs as S sub-batches on S streams at the same time.  Built to
+// attack the launch-latency chain at small per-GPU batches (strong scaling: 32 images per GPU at 8 GPUs).  Per-image results do not
+// depend on the batch they are computed in (bit for bit: the batch-independence tests), so a split changes nothing but the time --
+// and measured on B200 it does not help: 32 images take 1.18 / 1.22 / 1.43 ms as 1 / 2 / 4 lanes (64: 1.77 / 1.80 / 2.05).  The
+// persistent kernels of one lane already occupy every SM's shared memory and TMEM, so the lanes time-share the SMs instead of filling
+// each other's gaps.  Kept as an option (and tested); off by default.
+static int choose_lanes(int n, int h, int w) {
+    (void)h; (void)w;
+    int s = 1;
+    if (const char * e = getenv("MVIT_LANES")) s = atoi(e);
+    while (s > 1 && n % s) s--;
+    return s < 1 ? 1 : s;
+}
+
+static void build_graph_body(const model & m, forward_graph & g, int n, int h, int w, bool debug_stages) {
+    g.gf        = ggml_new_graph(g.ctx);
+    g.input_hwc = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, 3, w, h, n);
+    ggml_set_name(g.input_hwc, "inp");
+    ggml_set_input(g.input_hwc);
+    g.features = m.build_forward(g.ctx, g.input_hwc, &g.pooled, &g.stages);
+    ggml_set_name(g.features, "features");
+    ggml_set_name(g.pooled, "pooled");
+    ggml_build_forward_expand(g.gf, g.features);
+    ggml_build_forward_expand(g.gf, g.pooled);
+    if (m.classifier_w) {  // logits = pooled . kernel + bias
+        g.logits = dense(g.ctx, ggml_reshape_2d(g.ctx, g.pooled, g.pooled->ne[2], g.pooled->ne[3]), m.classifier_w, m.classifier_b);
+        ggml_set_name(g.logits, "logits");
+        ggml_build_forward_expand(g.gf, g.logits);
+    }
+    if (debug_stages)
+        for (ggml_tensor * t : g.stages) ggml_build_forward_expand(g.gf, t);  // marks them as outputs -> host shadows
+}
+
 forward_graph & model::graph_for(int n, int h, int w, int slot) {
     auto key = std::make_tuple(n, h, w, slot);
     auto it  = graphs.find(key);
     if (it != graphs.end()) return it->second;
     forward_graph g;
+    const int    C         = conv_1x1_exp.out_channels();
     const size_t in_bytes  = (size_t)n * h * w * 3 * sizeof(float);
-    size_t out_bytes = (size_t)n * conv_1x1_exp.out_channels() * ((size_t)(h / 32) * (w / 32) + 1) * sizeof(float);
+    size_t out_bytes = (size_t)n * C * ((size_t)(h / 32) * (w / 32) + 1) * sizeof(float);
     if (classifier_w) out_bytes += (size_t)n * (size_t)classifier_w->ne[0] * sizeof(float);
     const char * dbg = getenv("MVIT_DEBUG_STAGES");
     const bool   debug_stages = dbg && atoi(dbg) > 0;
@@ -342,32 +372,51 @@ forward_graph & model::graph_for(int n, int h, int w, int slot) {
     ggml_init_params params = {arena_bytes, g.pinned_arena, false};
     g.ctx                   = ggml_init(params);
     GGML_ASSERT(g.ctx != nullptr);
-    g.gf        = ggml_new_graph(g.ctx);
-    g.input_hwc = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, 3, w, h, n);
-    ggml_set_name(g.input_hwc, "inp");
-    ggml_set_input(g.input_hwc);
-    g.features = build_forward(g.ctx, g.input_hwc, &g.pooled, &g.stages);
-    ggml_set_name(g.features, "features");
-    ggml_set_name(g.pooled, "pooled");
-    ggml_build_forward_expand(g.gf, g.features);
-    ggml_build_forward_expand(g.gf, g.pooled);
-    if (classifier_w) {  // logits = pooled . kernel + bias
-        g.logits = dense(g.ctx, ggml_reshape_2d(g.ctx, g.pooled, g.pooled->ne[2], g.pooled->ne[3]), classifier_w, classifier_b);
-        ggml_set_name(g.logits, "logits");
-        ggml_build_forward_expand(g.gf, g.logits);
+    const int S = debug_stages ? 1 : choose_lanes(n, h, w);
+    if (S == 1) {
+        build_graph_body(*this, g, n, h, w, debug_stages);
+        return graphs.emplace(key, g).first->second;
     }
-    if (debug_stages)
-        for (ggml_tensor * t : g.stages) ggml_build_forward_expand(g.gf, t);  // marks them as outputs -> host shadows
+    // Split request: this record only owns the caller-visible host buffers (pinned): the input images and the outputs are plain
+    // leaf tensors here; every lane is a complete forward graph for n/S images whose input leaf and output shadows ALIAS the
+    // lane's slice of those buffers (the batch is the slowest dimension of every one of them), so uploads and downloads of the
+    // lanes go straight from / to the caller's arrays.
+    g.input_hwc = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, 3, w, h, n);
+    g.features  = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, w / 32, h / 32, C, n);
+    g.pooled    = ggml_new_tensor_4d(g.ctx, GGML_TYPE_F32, 1, 1, C, n);
+    if (classifier_w) g.logits = ggml_new_tensor_2d(g.ctx, GGML_TYPE_F32, classifier_w->ne[0], n);
+    const int nl = n / S;
+    for (int l = 0; l < S; l++) {
+        forward_graph       lane;
+        ggml_init_params lp = {(size_t)(24u << 20), nullptr, true};  // tensor records only: no_alloc
+        lane.ctx            = ggml_init(lp);
+        GGML_ASSERT(lane.ctx != nullptr);
+        build_graph_body(*this, lane, nl, h, w, false);
+        auto slice = [&](ggml_tensor * whole, ggml_tensor * part) { part->data = (char *)whole->data + (size_t)l * ggml_nbytes(part); };
+        slice(g.input_hwc, lane.input_hwc);
+        slice(g.features, lane.features);
+        slice(g.pooled, lane.pooled);
+        if (g.logits) slice(g.logits, lane.logits);
+        g.lanes.push_back(lane);
+    }
     return graphs.emplace(key, g).first->second;
+}
+
+static void free_graph(forward_graph & g) {
+    for (forward_graph & l : g.lanes) {
+        ggml_graph_release_plan(l.gf);
+        ggml_free(l.ctx);
+    }
+    if (g.gf) ggml_graph_release_plan(g.gf);
+    ggml_free(g.ctx);
+    ggml_b200_host_free(g.pinned_arena);
+    ggml_b200_host_free(g.input_u8);
 }
 
 void model::release(int n, int h, int w) {
     for (auto it = graphs.begin(); it != graphs.end();) {
         if (std::get<0>(it->first) == n && std::get<1>(it->first) == h && std::get<2>(it->first) == w) {
-            ggml_graph_release_plan(it->second.gf);
-            ggml_free(it->second.ctx);
-            ggml_b200_host_free(it->second.pinned_arena);
-            ggml_b200_host_free(it->second.input_u8);
+            free_graph(it->second);
             it = graphs.erase(it);
         } else {
             ++it;
@@ -402,6 +451,63 @@ extern "C" int64_t mvit_num_weights(const mvit_model * m) { return m->m.total_we
 extern "C" int     mvit_out_channels(const mvit_model * m) { return m->m.conv_1x1_exp.out_channels(); }
 extern "C" int     mvit_num_classes(const mvit_model * m) { return m->m.classifier_w ? (int)m->m.classifier_w->ne[0] : 0; }
 
+// ---- running one request: a single graph, or its concurrent lanes ------------------------------------------------------------
+static void prepare_graph(mvit::forward_graph & g, bool own_stream) {
+    if (g.lanes.empty()) {
+        if (!g.gf->plan) {
+            ggml_b200_graph_prepare(g.ctx, g.gf);
+            if (own_stream) ggml_b200_graph_use_private_stream(g.gf);
+        }
+        return;
+    }
+    for (mvit::forward_graph & l : g.lanes)
+        if (!l.gf->plan) {
+            ggml_b200_graph_prepare(l.ctx, l.gf);
+            ggml_b200_graph_use_private_stream(l.gf);
+        }
+}
+// u8_* != 0: the images come as raw u8 [n][src_h][src_w][3] in g.input_u8 and are preprocessed on the device.
+// owner_is_current_stream: synchronous entry points order the work after / before the library's current stream; pipelined slots
+// run on streams of their own (the slot graph's private stream, or lane 0's).
+static int run_graph(mvit::forward_graph & g, bool upload, bool download, bool wait, bool owner_is_current_stream, int u8_n = 0, int src_h = 0, int src_w = 0) {
+    prepare_graph(g, !owner_is_current_stream);
+    if (g.lanes.empty()) {
+        if (u8_n) {
+            if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, g.input_u8, u8_n, src_h, src_w)) return 1;
+            upload = false;
+        }
+        ggml_b200_graph_set_transfers(g.gf, upload, download);
+        if (wait) ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
+        else ggml_b200_graph_compute_async(g.ctx, g.gf);
+        return 0;
+    }
+    std::vector<ggml_cgraph *> gfs;
+    for (mvit::forward_graph & l : g.lanes) gfs.push_back(l.gf);
+    const int S = (int)gfs.size();
+    ggml_b200_graph_group_begin(gfs.data(), S, owner_is_current_stream ? 1 : 0);
+    for (int l = 0; l < S; l++) {
+        mvit::forward_graph & L = g.lanes[(size_t)l];
+        bool up = upload;
+        if (u8_n) {
+            const int nl = u8_n / S;
+            if (ggml_b200_graph_upload_u8_images(L.gf, L.input_hwc, g.input_u8 + (size_t)l * nl * src_h * src_w * 3, nl, src_h, src_w)) return 1;
+            up = false;
+        }
+        ggml_b200_graph_set_transfers(L.gf, up, download);
+        ggml_b200_graph_compute_async(L.ctx, L.gf);
+    }
+    ggml_b200_graph_group_end(gfs.data(), S, owner_is_current_stream ? 1 : 0);
+    if (wait) {
+        if (owner_is_current_stream) ggml_b200_synchronize();
+        else ggml_b200_graph_wait(gfs[0]);
+    }
+    return 0;
+}
+static void wait_graph(mvit::forward_graph & g) {
+    if (g.lanes.empty()) ggml_b200_graph_wait(g.gf);
+    else if (g.lanes[0].gf->plan) ggml_b200_graph_wait(g.lanes[0].gf);  // lane 0's stream is the owner: it waited for its siblings
+}
+
 extern "C" int mvit_compute(mvit_model * m, int n, int h, int w);
 
 extern "C" int mvit_extract_features(mvit_model * m, const float * images_hwc, int n, int h, int w, float * features,
@@ -421,10 +527,7 @@ extern "C" float * mvit_host_input(mvit_model * m, int n, int h, int w) {
 }
 extern "C" int mvit_compute(mvit_model * m, int n, int h, int w) {
     if (!m || !shape_ok(n, h, w)) return 1;
-    mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    if (g.gf->plan) ggml_b200_graph_set_transfers(g.gf, true, true);
-    ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
-    return 0;
+    return run_graph(m->m.graph_for(n, h, w), true, true, true, true);
 }
 extern "C" const float * mvit_host_features(mvit_model * m, int n, int h, int w) {
     if (!m || !shape_ok(n, h, w)) return nullptr;
@@ -452,9 +555,11 @@ extern "C" int mvit_classify(mvit_model * m, const float * images_hwc, int n, in
         for (int i = 0; i < n; i++) top1[i] = (int32_t)(std::max_element(lg + (size_t)i * nc, lg + (size_t)(i + 1) * nc) - (lg + (size_t)i * nc));
     return 0;
 }
+// per-launch profile of the plan (of lane 0 for a split request: n / lanes images)
 extern "C" int mvit_profile_json(mvit_model * m, int n, int h, int w, int reps, char * buf, size_t cap) {
     if (mvit_prepare(m, n, h, w)) return -1;
-    return ggml_b200_graph_profile_json(m->m.graph_for(n, h, w).gf, reps, buf, cap);
+    mvit::forward_graph & g = m->m.graph_for(n, h, w);
+    return ggml_b200_graph_profile_json(g.lanes.empty() ? g.gf : g.lanes[0].gf, reps, buf, cap);
 }
 
 // debug: copy stage tap `idx` (0 stem, 1..5 layers, 6 exp) as [N][C][H][W] floats; needs MVIT_DEBUG_STAGES=1 and a compute
@@ -471,13 +576,14 @@ extern "C" int64_t mvit_debug_stage(mvit_model * m, int n, int h, int w, int idx
 }
 
 // ---- pipelined slots: slot s has its own input buffer, output shadows, device arena and stream ----
+static void wait_graph_if_planned(mvit::forward_graph & g) {
+    if (g.lanes.empty()) { if (g.gf->plan) ggml_b200_graph_wait(g.gf); }
+    else wait_graph(g);
+}
 static mvit::forward_graph * slot_graph(mvit_model * m, int n, int h, int w, int slot) {
     if (!m || !shape_ok(n, h, w) || slot < 0 || slot > 7) return nullptr;
     mvit::forward_graph & g = m->m.graph_for(n, h, w, 1 + slot);  // slot graphs are distinct from the synchronous one (0)
-    if (!g.gf->plan) {
-        ggml_b200_graph_prepare(g.ctx, g.gf);
-        ggml_b200_graph_use_private_stream(g.gf);
-    }
+    prepare_graph(g, true);
     return &g;
 }
 extern "C" float * mvit_slot_input(mvit_model * m, int n, int h, int w, int slot) {
@@ -487,19 +593,19 @@ extern "C" float * mvit_slot_input(mvit_model * m, int n, int h, int w, int slot
 extern "C" int mvit_slot_set_transfers(mvit_model * m, int n, int h, int w, int slot, int upload_inputs, int download_outputs) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     if (!g) return 1;
-    ggml_b200_graph_set_transfers(g->gf, upload_inputs != 0, download_outputs != 0);
+    g->slot_upload   = upload_inputs != 0;
+    g->slot_download = download_outputs != 0;
     return 0;
 }
 extern "C" int mvit_slot_submit(mvit_model * m, int n, int h, int w, int slot) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     if (!g) return 1;
-    ggml_b200_graph_compute_async(g->ctx, g->gf);
-    return 0;
+    return run_graph(*g, g->slot_upload, g->slot_download, false, false);
 }
 extern "C" int mvit_slot_wait(mvit_model * m, int n, int h, int w, int slot) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
     if (!g) return 1;
-    ggml_b200_graph_wait(g->gf);
+    wait_graph(*g);
     return 0;
 }
 extern "C" const float * mvit_slot_features(mvit_model * m, int n, int h, int w, int slot) {
@@ -519,21 +625,16 @@ extern "C" const float * mvit_slot_pooled(mvit_model * m, int n, int h, int w, i
 static uint8_t * u8_staging(mvit::forward_graph & g, int n, int src_h, int src_w) {
     const size_t bytes = (size_t)n * src_h * src_w * 3;
     if (g.input_u8_bytes < bytes) {
-        if (g.gf->plan) ggml_b200_graph_wait(g.gf);  // a submitted copy may still read the old buffer
+        wait_graph_if_planned(g);  // a submitted copy may still read the old buffer
         ggml_b200_host_free(g.input_u8);
         g.input_u8       = (uint8_t *)ggml_b200_host_malloc(bytes);
         g.input_u8_bytes = g.input_u8 ? bytes : 0;
     }
     return g.input_u8;
 }
-static int submit_u8(mvit::forward_graph & g, int n, int src_h, int src_w, bool wait) {
+static int submit_u8(mvit::forward_graph & g, int n, int src_h, int src_w, bool wait, bool owner_is_current_stream) {
     if (!g.input_u8 || g.input_u8_bytes < (size_t)n * src_h * src_w * 3) return 1;
-    ggml_b200_graph_prepare(g.ctx, g.gf);
-    if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, g.input_u8, n, src_h, src_w)) return 1;
-    ggml_b200_graph_set_transfers(g.gf, false, true);
-    if (wait) ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
-    else ggml_b200_graph_compute_async(g.ctx, g.gf);
-    return 0;
+    return run_graph(g, false, true, wait, owner_is_current_stream, n, src_h, src_w);
 }
 extern "C" uint8_t * mvit_host_input_u8(mvit_model * m, int n, int h, int w, int src_h, int src_w) {
     if (!m || !shape_ok(n, h, w) || src_h <= 0 || src_w <= 0) return nullptr;
@@ -541,7 +642,7 @@ extern "C" uint8_t * mvit_host_input_u8(mvit_model * m, int n, int h, int w, int
 }
 extern "C" int mvit_compute_u8(mvit_model * m, int n, int h, int w, int src_h, int src_w) {
     if (!m || !shape_ok(n, h, w) || src_h <= 0 || src_w <= 0) return 1;
-    return submit_u8(m->m.graph_for(n, h, w), n, src_h, src_w, true);
+    return submit_u8(m->m.graph_for(n, h, w), n, src_h, src_w, true, true);
 }
 extern "C" uint8_t * mvit_slot_input_u8(mvit_model * m, int n, int h, int w, int slot, int src_h, int src_w) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
@@ -549,7 +650,7 @@ extern "C" uint8_t * mvit_slot_input_u8(mvit_model * m, int n, int h, int w, int
 }
 extern "C" int mvit_slot_submit_u8(mvit_model * m, int n, int h, int w, int slot, int src_h, int src_w) {
     mvit::forward_graph * g = slot_graph(m, n, h, w, slot);
-    return g && src_h > 0 && src_w > 0 ? submit_u8(*g, n, src_h, src_w, false) : 1;
+    return g && src_h > 0 && src_w > 0 ? submit_u8(*g, n, src_h, src_w, false, false) : 1;
 }
 extern "C" int mvit_preprocess_u8(mvit_model * m, const uint8_t * images, int n, int src_h, int src_w, int h, int w, float * out_hwc) {
     if (!m || !images || !out_hwc || !shape_ok(n, h, w) || src_h <= 0 || src_w <= 0) return 1;
@@ -557,38 +658,45 @@ extern "C" int mvit_preprocess_u8(mvit_model * m, const uint8_t * images, int n,
     uint8_t * st = u8_staging(g, n, src_h, src_w);
     if (!st) return 1;
     memcpy(st, images, (size_t)n * src_h * src_w * 3);
-    ggml_b200_graph_prepare(g.ctx, g.gf);
-    if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, st, n, src_h, src_w)) return 1;
-    return ggml_b200_tensor_download(g.gf, g.input_hwc, out_hwc);
+    prepare_graph(g, false);
+    if (g.lanes.empty()) {
+        if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, st, n, src_h, src_w)) return 1;
+        return ggml_b200_tensor_download(g.gf, g.input_hwc, out_hwc);
+    }
+    const int S = (int)g.lanes.size(), nl = n / S;
+    for (int l = 0; l < S; l++) {
+        mvit::forward_graph & L = g.lanes[(size_t)l];
+        if (ggml_b200_graph_upload_u8_images(L.gf, L.input_hwc, st + (size_t)l * nl * src_h * src_w * 3, nl, src_h, src_w)) return 1;
+        if (ggml_b200_tensor_download(L.gf, L.input_hwc, out_hwc + (size_t)l * nl * h * w * 3)) return 1;
+    }
+    return 0;
 }
 
 extern "C" int mvit_prepare(mvit_model * m, int n, int h, int w) {
     if (!m || !shape_ok(n, h, w)) return 1;
-    mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    ggml_b200_graph_prepare(g.ctx, g.gf);
+    prepare_graph(m->m.graph_for(n, h, w), false);
     return 0;
 }
+// device pointers of the synchronous graph's buffers; NULL for a request that is split into lanes (there is no single buffer)
 extern "C" void * mvit_device_input(mvit_model * m, int n, int h, int w) {
     if (mvit_prepare(m, n, h, w)) return nullptr;
     mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    return ggml_b200_tensor_get_device_data(g.gf, g.input_hwc);
+    return g.lanes.empty() ? ggml_b200_tensor_get_device_data(g.gf, g.input_hwc) : nullptr;
 }
 extern "C" void * mvit_device_features(mvit_model * m, int n, int h, int w) {
     if (mvit_prepare(m, n, h, w)) return nullptr;
     mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    return ggml_b200_tensor_get_device_data(g.gf, g.features);
+    return g.lanes.empty() ? ggml_b200_tensor_get_device_data(g.gf, g.features) : nullptr;
 }
 extern "C" void * mvit_device_pooled(mvit_model * m, int n, int h, int w) {
     if (mvit_prepare(m, n, h, w)) return nullptr;
     mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    return ggml_b200_tensor_get_device_data(g.gf, g.pooled);
+    return g.lanes.empty() ? ggml_b200_tensor_get_device_data(g.gf, g.pooled) : nullptr;
 }
 extern "C" int mvit_forward_device(mvit_model * m, int n, int h, int w) {
-    if (mvit_prepare(m, n, h, w)) return 1;
+    if (!m || !shape_ok(n, h, w)) return 1;
     mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    ggml_b200_graph_set_transfers(g.gf, false, false);
-    ggml_graph_compute_with_ctx(g.ctx, g.gf, 1);
-    return 0;
+    return run_graph(g, false, false, g.lanes.empty(), true);  // lanes: asynchronous on the current stream (the caller synchronises it)
 }
 extern "C" void mvit_release(mvit_model * m, int n, int h, int w) {
     if (m) m->m.release(n, h, w);
@@ -596,14 +704,20 @@ extern "C" void mvit_release(mvit_model * m, int n, int h, int w) {
 extern "C" int mvit_plan_info(mvit_model * m, int n, int h, int w, struct mvit_plan_info * out) {
     if (mvit_prepare(m, n, h, w)) return 1;
     mvit::forward_graph & g = m->m.graph_for(n, h, w);
-    ggml_b200_plan_stats s;
-    ggml_b200_graph_plan_stats(g.gf, &s);
-    out->mode         = s.mode;
-    out->graph_nodes  = s.n_graph_nodes;
-    out->launches     = s.n_launches;
-    out->arena_bytes  = s.arena_bytes;
-    out->naive_bytes  = s.naive_bytes;
-    out->weight_bytes = s.weight_bytes;
-    out->cuda_graph   = s.used_cuda_graph;
+    memset(out, 0, sizeof(*out));
+    out->cuda_graph = 1;
+    const size_t S = g.lanes.empty() ? 1 : g.lanes.size();
+    for (size_t l = 0; l < S; l++) {
+        ggml_b200_plan_stats s;
+        ggml_b200_graph_plan_stats(g.lanes.empty() ? g.gf : g.lanes[l].gf, &s);
+        out->mode         = s.mode;
+        out->graph_nodes  = s.n_graph_nodes;
+        out->launches    += s.n_launches;
+        out->arena_bytes += s.arena_bytes;
+        out->naive_bytes += s.naive_bytes;
+        out->weight_bytes = s.weight_bytes;
+        out->cuda_graph   = out->cuda_graph && s.used_cuda_graph;
+    }
+    out->lanes = (int)S;
     return 0;
 }

@@ -67,6 +67,10 @@ struct forward_graph {
     size_t         input_u8_bytes = 0;
     void *         pinned_arena = nullptr;  // page-locked backing store of ctx (input staging + output shadows)
     std::vector<ggml_tensor *> stages;   // stem, layer_1..layer_5, conv_1x1_exp outputs (debug taps, MVIT_DEBUG_STAGES=1)
+    // Small requests are split into concurrent lanes (sub-batches on their own streams, see graph_for): then gf == nullptr, the
+    // tensors above are plain host buffers and every lane is a complete forward graph aliasing its slice of them.
+    std::vector<forward_graph> lanes;
+    bool slot_upload = true, slot_download = true;  // mvit_slot_set_transfers
 };
 
 struct model {  // mobilevit_model, main.cpp:202-213

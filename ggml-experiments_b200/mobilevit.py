@@ -22,7 +22,7 @@ def native_paths() -> dict:
 class PlanInfo(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int), ("graph_nodes", ctypes.c_int), ("launches", ctypes.c_int),
                 ("arena_bytes", ctypes.c_int64), ("naive_bytes", ctypes.c_int64), ("weight_bytes", ctypes.c_int64),
-                ("cuda_graph", ctypes.c_int)]
+                ("cuda_graph", ctypes.c_int), ("lanes", ctypes.c_int)]
 
 
 _ggml = None

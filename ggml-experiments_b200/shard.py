@@ -31,3 +31,43 @@ def gather_rows(local: np.ndarray, n_total: int, rank: int, world: int, dist=Non
     if rank != dst:
         return None
     return np.concatenate([o.numpy()[:c] for o, c in zip(out, counts)], axis=0)
+
+
+class HostGather:
+    """The "final host-side gather of logits" (BASELINE.json north_star): ONE host buffer [n_total, width] f32 in POSIX
+    shared memory; every rank (one process per GPU) writes the rows of its own images into its disjoint slice right after its
+    device->host copy; rank 0 reads the whole array.  No collective, no extra hop: the data path of a step ends with a memcpy.
+
+    `dist` (torch.distributed, any backend) is used only for two barriers: create -> attach, and before unlink."""
+
+    def __init__(self, name: str, n_total: int, width: int, rank: int, world: int, dist=None):
+        from multiprocessing import shared_memory
+        self.rank, self.world, self.dist = rank, world, dist
+        self.lo, self.hi = shard_range(n_total, rank, world)
+        nbytes = max(1, n_total * width * 4)
+        if rank == 0:
+            try:  # a stale segment of a crashed run
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+        if world > 1:
+            dist.barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.full = np.ndarray((n_total, width), dtype=np.float32, buffer=self.shm.buf)
+        self.mine = self.full[self.lo:self.hi]
+
+    def write(self, rows: np.ndarray) -> None:
+        """this rank's rows ([n_local, width]) -> its slice of the shared buffer"""
+        np.copyto(self.mine, rows)
+
+    def close(self) -> None:
+        if self.world > 1:
+            self.dist.barrier()
+        self.full = self.mine = None
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()

@@ -248,6 +248,12 @@ void   ggml_b200_host_free(void * p);
 void ggml_b200_graph_use_private_stream(struct ggml_cgraph * cgraph);
 void ggml_b200_graph_compute_async(struct ggml_context * ctx, struct ggml_cgraph * cgraph);
 void ggml_b200_graph_wait(struct ggml_cgraph * cgraph);
+/* Concurrent lanes: n prepared graphs (sub-batches of one request) run at the same time on private streams.  begin: every lane's
+ * stream waits for the owner stream (on_current_stream != 0: the library's current stream; 0: lane 0's own stream, for pipelined
+ * slots); the caller then enqueues per-lane work (ggml_b200_graph_upload_u8_images, ggml_b200_graph_compute_async); end: the owner
+ * stream waits for every lane. */
+void ggml_b200_graph_group_begin(struct ggml_cgraph ** cgraphs, int n, int on_current_stream);
+void ggml_b200_graph_group_end(struct ggml_cgraph ** cgraphs, int n, int on_current_stream);
 
 /* Device-side feedback for autoregressive loops: after every compute of `cgraph`, copy node `src` into
  * the device buffer of leaf `dst` (same byte size).  Replaces rnn.cpp:303-310 (host writes the next token id and memcpy's

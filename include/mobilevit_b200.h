@@ -83,7 +83,7 @@ int    mvit_prepare(mvit_model * m, int n, int h, int w);           /* build gra
 void * mvit_device_input(mvit_model * m, int n, int h, int w);      /* device ptr, [N,H,W,3] f32 */
 void * mvit_device_features(mvit_model * m, int n, int h, int w);   /* device ptr, [N,C,H/32,W/32] f32 */
 void * mvit_device_pooled(mvit_model * m, int n, int h, int w);     /* device ptr, [N,C] f32 */
-int    mvit_forward_device(mvit_model * m, int n, int h, int w);    /* async launch on the library stream */
+int    mvit_forward_device(mvit_model * m, int n, int h, int w);    /* async launch, ordered on the library stream */
 void   mvit_release(mvit_model * m, int n, int h, int w);           /* drop the cached graph/plan for a shape */
 
 struct mvit_plan_info {
@@ -94,6 +94,7 @@ struct mvit_plan_info {
     int64_t naive_bytes;   /* what keeping every intermediate alive (the reference's arena) would need */
     int64_t weight_bytes;
     int     cuda_graph;
+    int     lanes;         /* concurrent sub-batch lanes the request is split into (1: one plan); launches / arena are summed over them */
 };
 int mvit_plan_info(mvit_model * m, int n, int h, int w, struct mvit_plan_info * out);
 /* JSON array of per-launch device times, see ggml_b200_graph_profile_json. */

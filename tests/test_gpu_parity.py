@@ -484,3 +484,41 @@ def test_f16_on_disk_and_pretransposed_weight_files_give_identical_features(G, w
         assert info["mode"] == MV.FAST
         np.testing.assert_array_equal(f, f0, err_msg=str(kw))
         np.testing.assert_array_equal(pp, p0, err_msg=str(kw))
+
+
+def test_concurrent_lanes_give_the_same_bits(G, weight_files, monkeypatch):
+    """MVIT_LANES=S: one request runs as S sub-batches on S streams (host/mobilevit.cpp graph_for); inputs and outputs of the lanes alias
+    slices of the caller's buffers.  Synchronous, u8 and pipelined-slot entry points must return exactly the unsplit result."""
+    base = W.synthetic_images(12, 128, 128, seed=7)
+    u8 = np.clip(np.rint(base * 255.0), 0, 255).astype(np.uint8)
+    m = G.MobileViT(weight_files["xs"])
+    try:
+        f0, p0 = m.extract_features(base)
+        m.host_input_u8(12, 128, 128, 128, 128)[:] = u8
+        fu0, pu0 = (a.copy() for a in m.compute_u8(12, 128, 128, 128, 128))
+        assert m.plan_info(12, 128, 128)["lanes"] == 1
+    finally:
+        m.close()
+    for lanes in (2, 3, 4):
+        monkeypatch.setenv("MVIT_LANES", str(lanes))
+        m = G.MobileViT(weight_files["xs"])
+        try:
+            f, p = m.extract_features(base)
+            info = m.plan_info(12, 128, 128)
+            assert info["lanes"] == lanes and info["mode"] == 0 and info["cuda_graph"] == 1
+            np.testing.assert_array_equal(f, f0)
+            np.testing.assert_array_equal(p, p0)
+            m.host_input_u8(12, 128, 128, 128, 128)[:] = u8
+            fu, pu = m.compute_u8(12, 128, 128, 128, 128)
+            np.testing.assert_array_equal(fu, fu0)
+            np.testing.assert_array_equal(pu, pu0)
+            for s in range(2):
+                m.slot_input(12, 128, 128, s)[:] = base
+                m.slot_submit(12, 128, 128, s)
+            for s in range(2):
+                fs, ps = m.slot_wait(12, 128, 128, s)
+                np.testing.assert_array_equal(fs, f0)
+                np.testing.assert_array_equal(ps, p0)
+        finally:
+            m.close()
+        monkeypatch.delenv("MVIT_LANES")

@@ -37,9 +37,13 @@ def _worker(rank, world, port, weight_path, n_total, hw, q):
     a, b = shard.shard_range(n_total, rank, world)
     _, pooled = binding.OracleModel(weight_path).forward(imgs[a:b], 0, 1)
     full = shard.gather_rows(pooled, n_total, rank, world, dist, dst=0)
-    if rank == 0:
-        q.put(full)
+    # the bench's data path: every rank writes its rows into its slice of ONE shared host buffer (no collective)
+    g = shard.HostGather(f"mvit_test_gather_{port}", n_total, pooled.shape[1], rank, world, dist)
+    g.write(pooled)
     dist.barrier()
+    if rank == 0:
+        q.put((full, g.full.copy()))
+    g.close()
     dist.destroy_process_group()
 
 
@@ -53,9 +57,10 @@ def test_two_rank_sharded_run_equals_single_process(weight_files, oracle):
     procs = [ctx.Process(target=_worker, args=(r, world, port, weight_files["xxs"], n_total, hw, q)) for r in range(world)]
     for p in procs:
         p.start()
-    full = q.get(timeout=120)
+    full, shared = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     _, ref = oracle.OracleModel(weight_files["xxs"]).forward(W.synthetic_images(n_total, hw, hw, seed=7), 0, 1)
     assert full.shape == ref.shape and np.array_equal(full, ref)
+    assert shared.shape == ref.shape and np.array_equal(shared, ref)
