@@ -284,6 +284,8 @@ def main():
     from ggml_experiments_b200 import shard
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product path)"
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -57,6 +57,11 @@ class HostGather:
             dist.barrier()
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:  # only the creator owns the segment: keep this process's resource tracker from unlinking (and warning about) it at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.full = np.ndarray((n_total, width), dtype=np.float32, buffer=self.shm.buf)
         self.mine = self.full[self.lo:self.hi]
 
