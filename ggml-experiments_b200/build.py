@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
           "-I" + os.path.join(HERE, "csrc")]
 
 LIB_SOURCES = ["csrc/ggml_b200.cpp", "csrc/plan.cpp", "csrc/exec_exact.cu", "csrc/fuse.cpp", "csrc/fast_kernels.cu",
-               "csrc/gemm_tcgen05.cu", "csrc/dwconv_tma.cu", "csrc/dwreduce.cu", "csrc/ir_fused.cu", "csrc/debug_api.cu"]
+               "csrc/gemm_tcgen05.cu", "csrc/dwconv_tma.cu", "csrc/dwreduce.cu", "csrc/ir_fused.cu", "csrc/attention_tc.cu", "csrc/debug_api.cu"]
 HOST_SOURCES = ["host/mobilevit.cpp", "host/gru.cpp"]
 
 

@@ -774,6 +774,7 @@ void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads,
     const int dp = attention_padded_head_dim(d);
     const int L  = (H / 2) * (W / 2);
     if (dp > 64) B200_ABORT("attention: head dim %d > 64", d);
+    if (launch_attention_tc(qkv, N, H, W, C, heads, out16, st)) return;  // tcgen05 kernel (attention_tc.cu) for sequences of k * 128 tokens
     static bool attr = false;
     if (!attr) {
         B200_CHECK(cudaFuncSetAttribute(k_attention_v1<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

@@ -28,6 +28,8 @@ void launch_layernorm(const float * x, int64_t rows, int C, const float * gamma,
 // materialised.  out: f16 [N*H*W, C] (unpadded).
 int attention_padded_head_dim(int d);
 void launch_attention(const __half * qkv, int N, int H, int W, int C, int heads, __half * out16, cudaStream_t st);
+// the same on tcgen05 (attention_tc.cu): S and P.V accumulate in TMEM; returns false for shapes it does not cover (L % 128, map width)
+bool launch_attention_tc(const __half * qkv, int N, int H, int W, int C, int heads, __half * out16, cudaStream_t st);
 
 // elementwise residual add: out = a + b (f32), optional f16 copy
 void launch_add(const float * a, const float * b, int64_t n, float * out32, __half * out16, cudaStream_t st);
