@@ -7,14 +7,15 @@
 //           buffer {DP, which*heads+h, x/2, y/2, image}, one tensor map per patch position (y%2, x%2): the reference's unfold
 //           (main.cpp:721-747) is a stride in the tensor map, never a copy.  Rows are 128 B (64 halves; columns >= DP are TMA zero fill).
 //   MMA 1 : S (128 x 64, TMEM) = Q . K_j^T                  both operands K-major (the head dimension is contiguous)
-//   warps : thread = one query row: tcgen05.ld S -> running max (online softmax) -> p = exp2((s - m) * log2e / sqrt(d)) -> f16 P_j
-//           into shared memory in the K-major 128B-swizzled UMMA layout; the row's output accumulator lives in REGISTERS
-//   MMA 2 : PV (128 x DP, TMEM) = P_j . V_j                 A = P_j K-major, B = V_j MN-major (token rows of V as they lie in memory:
-//           no transpose; instruction-descriptor bit 16)
-//   warps : tcgen05.ld PV -> O = O * exp2(m_old - m_new) + PV ; after the last block O / l -> f16 -> out[token][h*d ..]
+//   warps : thread = one query row: tcgen05.ld S (64 scores into registers, S is released at once) -> reference max (online softmax
+//           with a lazy rescale, see kTau) -> p = exp2(s * log2e / sqrt(d) - m) -> f16 P_j into shared memory in the K-major
+//           128B-swizzled UMMA layout
+//   MMA 2 : O (128 x DP, TMEM) += P_j . V_j                 A = P_j K-major, B = V_j MN-major (token rows of V as they lie in memory:
+//           no transpose; instruction-descriptor bit 16); O never leaves TMEM during the key loop
+//   warps : after the last block tcgen05.ld O -> O / l -> f16 -> out[token][h*d ..]
 //
-// A fifth warp issues every TMA and MMA.  K/V blocks are double-buffered; S_{j+1} is issued as soon as the softmax warps have read
-// S_j, so it overlaps PV_j and the accumulator update.  Three CTAs fit an SM (64 KB of shared memory, 128 TMEM columns each), which
+// A fifth warp issues every TMA and MMA.  K/V blocks are double-buffered; S_{j+1} is issued as soon as the softmax warps hold S_j
+// in registers, so it runs under their exponentials.  Three CTAs fit an SM (64 KB of shared memory, 128 TMEM columns each), which
 // is what overlaps the softmax of one query block with the MMAs / loads of the others.
 //
 // Used for sequences of a multiple of 128 tokens whose map width divides into 64-token row blocks (L = 256 / 1024 of the first ViT
@@ -41,6 +42,7 @@ constexpr int kKB = 64;   // keys per block (UMMA N of S, K of the second MMA)
 
 struct AttnTcParams {
     int H, W, C, heads, d, L, nqb;  // map size, channels, heads, head dim, tokens per sequence, query blocks per sequence
+    int items;                      // N * 4 * heads * nqb
     int rows_q, rows_k;             // map rows (of width W/2) per 64-token box
     float scale_log2;               // log2(e) / sqrt(d)
     __half * out;                   // [N*H*W][C]
@@ -64,84 +66,173 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// 32 lanes x 16 consecutive f32 columns: TMEM <-> registers (used to rescale / read the output accumulator)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+          "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 64 score columns of this thread's row in two loads, one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t * r = reinterpret_cast<uint32_t *>(v);
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+        uint32_t * q = r + hf * 32;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]),
+              "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]), "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]),
+              "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]), "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]),
+              "=r"(q[31])
+            : "r"(taddr + (uint32_t)(hf * 32))
+            : "memory");
+    }
+    // the wait names every destination register as read-write, so no use of them can be scheduled above it
+#define W8(o) "+r"(r[o]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7])
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : W8(0), W8(8), W8(16), W8(24) : : "memory");
+    asm volatile("" : W8(32), W8(40), W8(48), W8(56) : : "memory");
+#undef W8
+}
+
+// The output accumulator O (128 x DP, f32) stays in TMEM for the whole key loop: P_j . V_j accumulates into it.  The softmax keeps a
+// per-row reference maximum m and only moves it -- rescaling l and the row of O by 2^(m_old - m_new) -- when the block maximum exceeds
+// it by more than kTau (in log2 units): p = 2^(s - m) then stays below 2^kTau, well inside f16, and after the first block or two the
+// rescale (a TMEM read-modify-write, done warp-wide when any lane needs it) practically never happens.
+constexpr float kTau = 8.0f;
+
 template <int DP>
 __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__ CUtensorMap map00, const __grid_constant__ CUtensorMap map01,
                                                          const __grid_constant__ CUtensorMap map10, const __grid_constant__ CUtensorMap map11,
                                                          const AttnTcParams p) {
+    // Persistent CTA: its items (sequence, head, query block) form one flat sequence of key blocks g = 0, 1, ...; every barrier counts
+    // in g, so the loads and the first S of the next item are issued while the softmax warps still work on the current one.
     extern __shared__ uint8_t attn_smem_raw[];
     uint8_t * smem = attn_smem_raw + ((1024u - (smem_u32(attn_smem_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t bars[8];  // q_full, kv_full[2], kv_free[2], s_full, p_full, pv_full
+    __shared__ __align__(8) uint64_t bars[16];  // q_full, q_free, s_full, s_free, p_full, pv_full, k_full[3], k_free[3], v_full[2], v_free[2]
     __shared__ uint32_t tmem_slot;
     const uint32_t sq = smem_u32(smem);               // Q   : 128 x 128 B
-    const uint32_t sk = sq + 16384;                   // K[2]: 64 x 128 B each
-    const uint32_t sv = sk + 2 * 8192;                // V[2]
+    const uint32_t sk = sq + 16384;                   // K[3]: 64 x 128 B each (needed one block ahead of the softmax: three deep)
+    const uint32_t sv = sk + 3 * 8192;                // V[2]
     const uint32_t sp = sv + 2 * 8192;                // P   : 128 x 128 B (64 keys)
-    const uint32_t q_full = smem_u32(&bars[0]), kv_full = smem_u32(&bars[1]), kv_free = smem_u32(&bars[3]);
-    const uint32_t s_full = smem_u32(&bars[5]), p_full = smem_u32(&bars[6]), pv_full = smem_u32(&bars[7]);
+    const uint32_t q_full = smem_u32(&bars[0]), q_free = smem_u32(&bars[1]), s_full = smem_u32(&bars[2]), s_free = smem_u32(&bars[3]);
+    const uint32_t p_full = smem_u32(&bars[4]), pv_full = smem_u32(&bars[5]);
+    const uint32_t k_full = smem_u32(&bars[6]), k_free = smem_u32(&bars[9]), v_full = smem_u32(&bars[12]), v_free = smem_u32(&bars[14]);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb   = p.L / kKB;
+    const int nit   = (int)blockIdx.x < p.items ? (p.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;  // items of this CTA
+    const int nblk  = nit * nkb;                                                                            // key blocks of this CTA
     // item = (image n, patch position pos, head h, query block qb)
-    int it = blockIdx.x;
-    const int qb  = it % p.nqb; it /= p.nqb;
-    const int h   = it % p.heads; it /= p.heads;
-    const int pos = it & 3;
-    const int n   = it >> 2;
-    const int nkb = p.L / kKB;
-    const CUtensorMap * map = pos == 0 ? &map00 : (pos == 1 ? &map01 : (pos == 2 ? &map10 : &map11));
+    auto decode = [&](int k, int & n, int & pos, int & h, int & qb) {
+        int it = (int)blockIdx.x + k * (int)gridDim.x;
+        qb  = it % p.nqb; it /= p.nqb;
+        h   = it % p.heads; it /= p.heads;
+        pos = it & 3;
+        n   = it >> 2;
+    };
 
     if (tid == 0) {
-        for (int i = 0; i < 8; i++) mbar_init(smem_u32(&bars[i]), i == 6 ? 4u : 1u);  // p_full: one arrive per softmax warp
+        for (int i = 0; i < 16; i++) mbar_init(smem_u32(&bars[i]), (i == 3 || i == 4) ? 4u : 1u);  // s_free / p_full: one arrive per softmax warp
         fence_barrier_init();
-        tma_prefetch_desc(map);
+        tma_prefetch_desc(&map00);
+        tma_prefetch_desc(&map01);
+        tma_prefetch_desc(&map10);
+        tma_prefetch_desc(&map11);
     }
     if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_s = tmem_slot, tmem_pv = tmem_slot + 64u;
+    const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 64u;
     pdl_wait();  // qkv is the previous kernel's output; `out` may still be read by it
     pdl_trigger();
 
     if (warp == 4) {
-        // ===================== control warp: TMA + MMA issue =====================
-        if (lane == 0) {
-            auto load_kv = [&](int j) {
-                const uint32_t b = (uint32_t)(j & 1), bar = kv_full + 8u * b;
-                mbar_expect_tx(bar, 2u * 8192u);
-                tma_load_5d(sk + b * 8192u, map, 0, 1 * p.heads + h, 0, j * p.rows_k, n, bar);
-                tma_load_5d(sv + b * 8192u, map, 0, 2 * p.heads + h, 0, j * p.rows_k, n, bar);
+        // ===================== control warp: TMA + MMA issue (whole warp, elected lane issues: ptx_sm100.cuh "_ws") =====================
+        if (nblk > 0) {
+            auto map_of = [&](int pos) { return pos == 0 ? &map00 : (pos == 1 ? &map01 : (pos == 2 ? &map10 : &map11)); };
+            auto load_k = [&](int g) {  // keys of block g of this CTA -> K buffer g % 3
+                int n, pos, h, qb;
+                decode(g / nkb, n, pos, h, qb);
+                const uint32_t b = (uint32_t)(g % 3), bar = k_full + 8u * b;
+                mbar_expect_tx_ws(bar, 8192u);
+                tma_load_5d_ws(sk + b * 8192u, map_of(pos), 0, 1 * p.heads + h, 0, (g % nkb) * p.rows_k, n, bar);
             };
-            mbar_expect_tx(q_full, 16384u);
-            tma_load_5d(sq, map, 0, h, 0, (qb * 2) * p.rows_q, n, q_full);
-            tma_load_5d(sq + 8192u, map, 0, h, 0, (qb * 2 + 1) * p.rows_q, n, q_full);
-            load_kv(0);
-            if (nkb > 1) load_kv(1);
+            auto load_v = [&](int g) {  // values of block g -> V buffer g & 1
+                int n, pos, h, qb;
+                decode(g / nkb, n, pos, h, qb);
+                const uint32_t b = (uint32_t)(g & 1), bar = v_full + 8u * b;
+                mbar_expect_tx_ws(bar, 8192u);
+                tma_load_5d_ws(sv + b * 8192u, map_of(pos), 0, 2 * p.heads + h, 0, (g % nkb) * p.rows_k, n, bar);
+            };
+            auto load_q = [&](int k) {
+                int n, pos, h, qb;
+                decode(k, n, pos, h, qb);
+                mbar_expect_tx_ws(q_full, 16384u);
+                tma_load_5d_ws(sq, map_of(pos), 0, h, 0, (qb * 2) * p.rows_q, n, q_full);
+                tma_load_5d_ws(sq + 8192u, map_of(pos), 0, h, 0, (qb * 2 + 1) * p.rows_q, n, q_full);
+            };
             const uint32_t idesc_s = attn_idesc(kKB, 0), idesc_pv = attn_idesc(DP, 1);
             const uint64_t qdesc = make_smem_desc(sq, 128), pdesc = make_smem_desc(sp, 128);
-            auto issue_s = [&](int j) {
-                mbar_wait(kv_full + 8u * (uint32_t)(j & 1), (uint32_t)((j >> 1) & 1));
+            auto issue_s = [&](int g) {  // S of key block g; the first block of an item waits for the item's Q, the last one releases it
+                const int k = g / nkb, j = g % nkb;
+                if (j == 0) mbar_wait(q_full, (uint32_t)(k & 1));
+                mbar_wait(k_full + 8u * (uint32_t)(g % 3), (uint32_t)((g / 3) & 1));
                 tc_fence_after();
-                const uint64_t kdesc = make_smem_desc(sk + (uint32_t)(j & 1) * 8192u, 128);
+                const uint64_t kdesc = make_smem_desc(sk + (uint32_t)(g % 3) * 8192u, 128);
 #pragma unroll
-                for (int ks = 0; ks < DP / 16; ks++) umma_f16(tmem_s, qdesc + (uint64_t)(2 * ks), kdesc + (uint64_t)(2 * ks), idesc_s, ks != 0);
-                umma_commit(s_full);
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < nkb; j++) {
-                mbar_wait(p_full, (uint32_t)(j & 1));  // P_j is in shared memory; every softmax warp has finished reading S_j
-                tc_fence_after();
-                // V_j as the MN-major B operand: 64 token rows of 128 B, 8-row groups 1 KiB apart; 16 keys per k-step = +2 KiB
-                const uint64_t vdesc = make_smem_desc(sv + (uint32_t)(j & 1) * 8192u, 128);
-#pragma unroll
-                for (int ks = 0; ks < kKB / 16; ks++) umma_f16(tmem_pv, pdesc + (uint64_t)(2 * ks), vdesc + (uint64_t)(128 * ks), idesc_pv, ks != 0);
-                umma_commit(pv_full);
-                umma_commit(kv_free + 8u * (uint32_t)(j & 1));
-                if (j + 1 < nkb) issue_s(j + 1);  // runs behind PV_j on the tensor pipe, under the accumulator update of block j
-                if (j + 2 < nkb) {
-                    mbar_wait(kv_free + 8u * (uint32_t)(j & 1), (uint32_t)((j >> 1) & 1));  // S_j and PV_j have read K_j / V_j
-                    load_kv(j + 2);
+                for (int ks = 0; ks < DP / 16; ks++) umma_f16_ws(tmem_s, qdesc + (uint64_t)(2 * ks), kdesc + (uint64_t)(2 * ks), idesc_s, ks != 0);
+                umma_commit_ws(s_full);
+                umma_commit_ws(k_free + 8u * (uint32_t)(g % 3));
+                if (j == nkb - 1) {
+                    umma_commit_ws(q_free);  // every S of this item has been issued: Q may be replaced once they complete
+                    if (k + 1 < nit) {
+                        mbar_wait(q_free, (uint32_t)(k & 1));
+                        load_q(k + 1);
+                    }
                 }
+            };
+            load_q(0);
+            for (int g = 0; g < 3 && g < nblk; g++) load_k(g);
+            load_v(0);
+            issue_s(0);
+            for (int g = 0; g < nblk; g++) {
+                if (g + 1 < nblk) {
+                    // the softmax warps hold S_g in registers: S_{g+1} (possibly of the next item) is computed under their exponentials
+                    mbar_wait(s_free, (uint32_t)(g & 1));
+                    issue_s(g + 1);
+                    // V_{g+1} -> the buffer P.V_{g-1} has read (it was issued a whole softmax ago); needed only after the NEXT softmax
+                    if (g >= 1) mbar_wait(v_free + 8u * (uint32_t)((g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));
+                    load_v(g + 1);
+                }
+                if (g + 3 < nblk) {  // K_{g+3} -> the buffer S_g has read (S_g is complete: the softmax warps have consumed it)
+                    mbar_wait(k_free + 8u * (uint32_t)(g % 3), (uint32_t)((g / 3) & 1));
+                    load_k(g + 3);
+                }
+                mbar_wait(p_full, (uint32_t)(g & 1));  // P_g is in shared memory (and any rescale of O has been stored)
+                mbar_wait(v_full + 8u * (uint32_t)(g & 1), (uint32_t)((g >> 1) & 1));
+                tc_fence_after();
+                // V_g as the MN-major B operand: 64 token rows of 128 B, 8-row groups 1 KiB apart; 16 keys per k-step = +2 KiB
+                const uint64_t vdesc = make_smem_desc(sv + (uint32_t)(g & 1) * 8192u, 128);
+                const int j = g % nkb;
+#pragma unroll
+                for (int ks = 0; ks < kKB / 16; ks++) umma_f16_ws(tmem_o, pdesc + (uint64_t)(2 * ks), vdesc + (uint64_t)(128 * ks), idesc_pv, (j | ks) != 0);
+                umma_commit_ws(pv_full);
+                umma_commit_ws(v_free + 8u * (uint32_t)(g & 1));
             }
         }
         __syncwarp();
@@ -149,99 +240,91 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
         // ===================== softmax warps: thread = query row =====================
         const int      row  = warp * 32 + lane;                          // TMEM lane
         const uint32_t lsel = (uint32_t)(warp * 32) << 16;
-        float O[DP];
-#pragma unroll
-        for (int c = 0; c < DP; c++) O[c] = 0.f;
-        float m = -INFINITY, l = 0.f;  // running max (in scaled log2 units) and running sum
         const uint32_t prow = sp + (uint32_t)row * 128u, psw = (uint32_t)row & 7u;
-        for (int j = 0; j < nkb; j++) {
-            mbar_wait(s_full, (uint32_t)(j & 1));
-            tc_fence_after();
-            // pass 1: row maximum of the 64 scores
-            float mx = -INFINITY;
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-                float v[32];
-                tmem_ld_32x32(tmem_s + lsel + (uint32_t)(hf * 32), v);
-#pragma unroll
-                for (int c = 0; c < 32; c++) mx = fmaxf(mx, v[c]);
-            }
-            const float m_new = fmaxf(m, mx * p.scale_log2);
-            const float alpha = ex2(m - m_new);  // first block: exp2(-inf) = 0
-            // the previous block's P (and its PV accumulator) must have been consumed before P is overwritten / PV is read again
-            if (j > 0) {
-                mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
+        int g = 0;
+        for (int k = 0; k < nit; k++) {
+            float m = 0.f, l = 0.f;  // reference maximum (scaled log2 units) and running sum
+            for (int j = 0; j < nkb; j++, g++) {
+                mbar_wait(s_full, (uint32_t)(g & 1));
                 tc_fence_after();
+                float v[64];
+                tmem_ld64(tmem_s + lsel, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free);  // S is in registers: the tensor core may overwrite it with the next S
+                float mx4[4] = {v[0], v[1], v[2], v[3]};  // four independent chains instead of one of 63 dependent FMNMX
 #pragma unroll
-                for (int c0 = 0; c0 < DP; c0 += 16) {
-                    float v[16];
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
-                          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-                        : "r"(tmem_pv + lsel + (uint32_t)c0)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int c = 0; c < 16; c++) O[c0 + c] += v[c];
+                for (int c = 4; c < 64; c++) mx4[c & 3] = fmaxf(mx4[c & 3], v[c]);
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+                // the previous P.V has finished: P may be overwritten and O may be rescaled
+                if (g > 0) {
+                    mbar_wait(pv_full, (uint32_t)((g - 1) & 1));
+                    tc_fence_after();
                 }
-            }
-            // O currently holds sum_{i<j} (already rescaled); rescale to the new maximum
+                if (j == 0) {
+                    m = mx;
+                } else {
+                    const bool need = mx > m + kTau;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float m_new = need ? mx : m;
+                        const float alpha = ex2(m - m_new);  // 1 for the lanes that keep their reference
+                        l *= alpha;
+                        m = m_new;
 #pragma unroll
-            for (int c = 0; c < DP; c++) O[c] *= alpha;
-            // pass 2: p = exp2(s * scale - m_new), row sum, f16 P into the swizzled A tile
-            float sum = 0.f;
+                        for (int c0 = 0; c0 < DP; c0 += 16) {
+                            float o[16];
+                            tmem_ld16(tmem_o + lsel + (uint32_t)c0, o);
 #pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-                float v[32];
-                tmem_ld_32x32(tmem_s + lsel + (uint32_t)(hf * 32), v);
+                            for (int c = 0; c < 16; c++) o[c] *= alpha;
+                            tmem_st16(tmem_o + lsel + (uint32_t)c0, o);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                // p = exp2(s * scale - m), row sum, f16 P into the swizzled A tile
+                float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
+                for (int gq = 0; gq < 8; gq++) {
                     float e[8];
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
-                        e[c] = ex2(fmaf(v[g * 8 + c], p.scale_log2, -m_new));
-                        sum += e[c];
+                        e[c] = ex2(fmaf(v[gq * 8 + c], p.scale_log2, -m));
+                        sum4[c & 3] += e[c];
                     }
-                    st_shared_v4(prow + ((((uint32_t)(hf * 4 + g)) ^ psw) << 4), pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+                    st_shared_v4(prow + ((((uint32_t)gq) ^ psw) << 4), pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+                }
+                l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+                tc_fence_before();
+                fence_proxy_async();  // P (generic proxy) -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+            // all of this item's P.V has accumulated: normalise and store
+            mbar_wait(pv_full, (uint32_t)((g - 1) & 1));
+            tc_fence_after();
+            const float inv = 1.0f / l;
+            int n, pos, h, qb;
+            decode(k, n, pos, h, qb);
+            // token of this row -> pixel: t = qb*128 + row, (ty, tx) in the half-resolution lattice of patch position pos
+            const int t  = qb * kQB + row;
+            const int w2 = p.W >> 1;
+            const int ty = t / w2, tx = t - ty * w2;
+            const size_t pix = ((size_t)n * p.H + (size_t)(2 * ty + (pos >> 1))) * p.W + (size_t)(2 * tx + (pos & 1));
+            __half * o = p.out + pix * p.C + h * p.d;
+#pragma unroll
+            for (int c0 = 0; c0 < DP; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_o + lsel + (uint32_t)c0, v);
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    if (c0 + c < p.d) {  // d is even (C and heads are multiples of 4 / 8)
+                        const uint32_t hv = pack2(v[c] * inv, v[c + 1] * inv);
+                        *reinterpret_cast<uint32_t *>(o + c0 + c) = hv;
+                    }
                 }
             }
-            l = fmaf(l, alpha, sum);
-            m = m_new;
             tc_fence_before();
-            fence_proxy_async();  // P (generic proxy) -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
         }
-        // last block's PV, then normalise and store
-        mbar_wait(pv_full, (uint32_t)((nkb - 1) & 1));
-        tc_fence_after();
-        const float inv = 1.0f / l;
-        // token of this row -> pixel: t = qb*128 + row, (ty, tx) in the half-resolution lattice of patch position pos
-        const int t  = qb * kQB + row;
-        const int w2 = p.W >> 1;
-        const int ty = t / w2, tx = t - ty * w2;
-        const size_t pix = ((size_t)n * p.H + (size_t)(2 * ty + (pos >> 1))) * p.W + (size_t)(2 * tx + (pos & 1));
-        __half * o = p.out + pix * p.C + h * p.d;
-#pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-            float v[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
-                  "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-                : "r"(tmem_pv + lsel + (uint32_t)c0)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-                if (c0 + c < p.d) {  // d is even (C and heads are multiples of 4 / 8)
-                    const uint32_t hv = pack2((O[c0 + c] + v[c]) * inv, (O[c0 + c + 1] + v[c + 1]) * inv);
-                    *reinterpret_cast<uint32_t *>(o + c0 + c) = hv;
-                }
-            }
-        }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 0) {
@@ -254,10 +337,12 @@ template <int DP>
 void launch_tc(const CUtensorMap * maps, const AttnTcParams & p, int items, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        B200_CHECK(cudaFuncSetAttribute(k_attention_tc<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(k_attention_tc<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr = true;
     }
-    launch_pdl(k_attention_tc<DP>, dim3((unsigned)items), dim3(160), (size_t)(1024 + 16384 + 4 * 8192 + 16384), st, maps[0], maps[1], maps[2], maps[3], p);
+    const int cap = 3 * runtime().sm_count;  // persistent: three CTAs per SM
+    launch_pdl(k_attention_tc<DP>, dim3((unsigned)(items < cap ? items : cap)), dim3(160), (size_t)(1024 + 16384 + 5 * 8192 + 16384), st, maps[0], maps[1], maps[2],
+               maps[3], p);
 }
 
 }  // namespace
@@ -300,6 +385,7 @@ bool launch_attention_tc(const __half * qkv, int N, int H, int W, int C, int hea
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
     p.out = out16;
     const int items = N * 4 * heads * p.nqb;
+    p.items = items;
     CUtensorMap local[4];
     {
         std::lock_guard<std::mutex> lk(mu);

@@ -344,3 +344,88 @@ extern "C" float ggml_b200_debug_fma_rate(int mode, int iters) {
     const double instr = (double)grid * (block / 32) * (double)iters * 8.0;
     return (float)(instr / (ms * 1e-3) / 148.0 / 1.965e9);
 }
+
+// ---- tcgen05.mma issue-rate probe (tests/mma_rate_probe.py): one thread per CTA issues `iters` back-to-back MMAs of shape 128 x N x 16 on
+// the same shared-memory operands and waits for the final commit; returns cycles per MMA.  ctas_per_sm CTAs share every SM. ----
+#include "ptx_sm100.cuh"
+// warp-uniform issue: every lane of the warp executes the instruction stream with identical operands, one elected lane issues
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__global__ void k_mma_rate(int N, int iters, int commit_every, long long * out, int uniform) {
+    using namespace b200::ptx;
+    extern __shared__ uint8_t probe_smem_raw[];
+    uint8_t * smem = probe_smem_raw + ((1024u - (smem_u32(probe_smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t slot;
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(&slot), 256);
+    for (int i = threadIdx.x; i < (128 + 256) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;  // ones
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (uniform && threadIdx.x < 32) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t adesc = make_smem_desc(smem_u32(smem), 128), bdesc = make_smem_desc(smem_u32(smem) + 16384, 128);
+        const uint32_t tm = __shfl_sync(0xffffffffu, slot, 0);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i++) umma_f16_elect(tm, adesc + (uint64_t)(2 * (i & 3)), bdesc + (uint64_t)(2 * (i & 3)), idesc, 1);
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) umma_commit(smem_u32(&bar));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+        const long long t2 = clock64();
+        if (threadIdx.x == 0) {
+            out[blockIdx.x * 2]     = t1 - t0;
+            out[blockIdx.x * 2 + 1] = t2 - t0;
+        }
+    } else if (!uniform && threadIdx.x == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t adesc = make_smem_desc(smem_u32(smem), 128), bdesc = make_smem_desc(smem_u32(smem) + 16384, 128);
+        uint32_t phase = 0;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i++) {
+            umma_f16(slot, adesc + (uint64_t)(2 * (i & 3)), bdesc + (uint64_t)(2 * (i & 3)), idesc, 1);
+            if (commit_every > 0 && (i + 1) % commit_every == 0) {
+                umma_commit(smem_u32(&bar));
+                mbar_wait(smem_u32(&bar), phase);
+                phase ^= 1u;
+            }
+        }
+        const long long t1 = clock64();
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), phase);
+        const long long t2 = clock64();
+        out[blockIdx.x * 2]     = t1 - t0;
+        out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(slot, 256); }
+}
+// returns cycles per MMA: issue-only in issue_cycles, issue + completion in the return value
+extern "C" float ggml_b200_debug_mma_rate(int N, int iters, int ctas_per_sm, int commit_every, float * issue_cycles) {
+    b200::ensure_device();
+    const int grid = 148 * ctas_per_sm;
+    long long * d = nullptr;
+    cudaMalloc(&d, sizeof(long long) * 2 * grid);
+    const size_t smem = 1024 + (128 + 256) * 128;
+    cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int uniform = commit_every < 0 ? 1 : 0;  // commit_every < 0: warp-uniform issue with an elected lane
+    for (int rep = 0; rep < 2; rep++) k_mma_rate<<<grid, 128, smem>>>(N, iters, commit_every, d, uniform);
+    cudaDeviceSynchronize();
+    std::vector<long long> h((size_t)2 * grid);
+    cudaMemcpy(h.data(), d, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    double a = 0, b = 0;
+    for (int i = 0; i < grid; i++) { a += (double)h[(size_t)2 * i]; b += (double)h[(size_t)2 * i + 1]; }
+    if (issue_cycles) *issue_cycles = (float)(a / grid / iters);
+    return (float)(b / grid / iters);
+}

@@ -125,9 +125,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     // The resident weight tile is a constant: its TMA loads are issued before the PDL wait so that they, too, overlap the
     // tail of the previous kernel (both producer flavours: one k-block per load, num_kb == 1 in the cp.async mode)
-    if (warp == 0 && lane == 0 && p.b_resident && (int)blockIdx.x < num_m_tiles) {
-        mbar_expect_tx(smem_u32(bres_full), (uint32_t)(p.num_kb * b_bytes));
-        for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(smem_u32(smem_bres + (size_t)kb * b_bytes), &map_b, kb * p.kb_elems, n0, smem_u32(bres_full));
+    // (every TMA / MMA below is issued warp-uniformly: all lanes of the warp run the loop, one elected lane issues -- ptx_sm100.cuh "_ws")
+    if (warp == 0 && p.b_resident && (int)blockIdx.x < num_m_tiles) {
+        mbar_expect_tx_ws(smem_u32(bres_full), (uint32_t)(p.num_kb * b_bytes));
+        for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d_ws(smem_u32(smem_bres + (size_t)kb * b_bytes), &map_b, kb * p.kb_elems, n0, smem_u32(bres_full));
     }
     // PDL: everything above (barriers, TMEM, per-column constants, weights) overlapped the tail of the previous kernel;
     // activations, residuals and row statistics are only touched, and outputs only written, once that kernel has completed
@@ -152,13 +153,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
             const uint32_t fb = smem_u32(&full_bar[s]);
             const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-            if (lane == 0) {
-                if (p.b_resident) {
-                    mbar_arrive(fb);  // the weight tile was requested before the PDL wait
-                } else {
-                    mbar_expect_tx(fb, (uint32_t)b_bytes);
-                    tma_load_2d(sa + a_bytes, &map_b, 0, n0, fb);
-                }
+            if (p.b_resident) {
+                mbar_arrive_ws(fb);  // the weight tile was requested before the PDL wait
+            } else {
+                mbar_expect_tx_ws(fb, (uint32_t)b_bytes);
+                tma_load_2d_ws(sa + a_bytes, &map_b, 0, n0, fb);
             }
             const int cshift = cpr == 2 ? 1 : 2;
             for (int i = lane; i < chunks; i += 32) {
@@ -173,8 +172,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fb) : "memory");
         }
     } else if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp, elected lane issues) =====================
+        {
             uint32_t it = 0;  // k-block counter across all tiles of this CTA
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
                 const int m0 = tile * tile_m;
@@ -192,25 +191,26 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
                     if (!p.conv) {
-                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                        tma_load_2d(sa, &map_a0, kb * p.kb_elems, m0, fb);
-                        if (!p.b_resident) tma_load_2d(sb, &map_b, kb * p.kb_elems, n0, fb);
+                        mbar_expect_tx_ws(fb, (uint32_t)stage_bytes);
+                        tma_load_2d_ws(sa, &map_a0, kb * p.kb_elems, m0, fb);
+                        if (!p.b_resident) tma_load_2d_ws(sb, &map_b, kb * p.kb_elems, n0, fb);
                     } else {
-                        mbar_expect_tx(fb, (uint32_t)(p.a_tx_bytes + b_bytes));  // the activation box may be shorter than 128 rows
+                        mbar_expect_tx_ws(fb, (uint32_t)(p.a_tx_bytes + b_bytes));  // the activation box may be shorter than 128 rows
                         const int tap = kb / cblk_tot, r = kb % cblk_tot;
                         const int src = r >= p.cblk0;
                         const int cb  = src ? r - p.cblk0 : r;
                         const int kh = tap / 3, kw = tap % 3;
-                        tma_load_4d(sa, src ? &map_a1 : &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
-                        tma_load_3d(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
+                        if (src) tma_load_4d_ws(sa, &map_a1, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
+                        else tma_load_4d_ws(sa, &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
+                        tma_load_3d_ws(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
                     }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+        {
             const uint32_t idesc = make_idesc(p.block_n);
             uint32_t it = 0, t = 0;
             if (p.b_resident && (int)blockIdx.x < num_m_tiles) mbar_wait(smem_u32(bres_full), 0);
@@ -241,11 +241,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     const uint64_t bdesc  = make_smem_desc(sb, (uint32_t)p.kb_elems * 2);
                     for (int k = 0; k < ksteps; k++) {
                         // advancing 16 f16 (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
-                        umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_f16_ws(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
+                    umma_commit_ws(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
                 }
-                umma_commit(smem_u32(&tmem_full[acc]));  // accumulator complete
+                umma_commit_ws(smem_u32(&tmem_full[acc]));  // accumulator complete
             }
         }
         __syncwarp();

@@ -232,17 +232,17 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
 #endif
 
     if (warp == NCW) {
-        // ===================== control warp: every TMA and MMA of the CTA =====================
-        if (lane == 0 && nitems > 0) {
+        // ===================== control warp: every TMA and MMA of the CTA (whole warp, elected lane issues: ptx_sm100.cuh "_ws") =====================
+        if (nitems > 0) {
             auto issue_we = [&](uint32_t i, int c) {  // expand weights of chunk c -> buffer i & 1
                 const uint32_t bar = we_full + 8u * (i & 1u);
-                mbar_expect_tx(bar, p.we_bytes);
-                for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d(wes + (i & 1u) * p.we_bytes + (uint32_t)kb * p.we_kb_stride, &map_we, kb * 64, c * 64, bar);
+                mbar_expect_tx_ws(bar, p.we_bytes);
+                for (int kb = 0; kb < p.num_kb; kb++) tma_load_2d_ws(wes + (i & 1u) * p.we_bytes + (uint32_t)kb * p.we_kb_stride, &map_we, kb * 64, c * 64, bar);
             };
             auto issue_wr = [&](uint32_t i, int c) {  // reduce weights of chunk c -> buffer i & 1
                 const uint32_t bar = wr_full + 8u * (i & 1u);
-                mbar_expect_tx(bar, p.wr_bytes);
-                tma_load_2d(wrs + (i & 1u) * p.wr_bytes, &map_wr, c * 64, 0, bar);
+                mbar_expect_tx_ws(bar, p.wr_bytes);
+                tma_load_2d_ws(wrs + (i & 1u) * p.wr_bytes, &map_wr, c * 64, 0, bar);
             };
             auto issue_x = [&](int k) {  // input halo of this CTA's k-th tile -> buffer k % nxb
                 int t = (int)blockIdx.x + k * (int)gridDim.x;
@@ -251,9 +251,9 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
                 const int n  = t / p.tiles_y;
                 const uint32_t xb  = (uint32_t)(k % p.nxb);
                 const uint32_t bar = x_full + 8u * xb;
-                mbar_expect_tx(bar, p.x_tx_bytes);
+                mbar_expect_tx_ws(bar, p.x_tx_bytes);
                 for (int kb = 0; kb < p.num_kb; kb++)
-                    tma_load_4d(xs + xb * p.x_buf_stride + (uint32_t)kb * p.x_kb_stride, &map_x, kb * 64, tx * p.TW * STRIDE - 1, ty * p.TH * STRIDE - 1, n, bar);
+                    tma_load_4d_ws(xs + xb * p.x_buf_stride + (uint32_t)kb * p.x_kb_stride, &map_x, kb * 64, tx * p.TW * STRIDE - 1, ty * p.TH * STRIDE - 1, n, bar);
             };
             const uint32_t idesc_e = ir_idesc(64), idesc_r = ir_idesc(p.Cout_pad);
             auto issue_expand = [&](uint32_t i, int k) {
@@ -264,10 +264,10 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
                         const uint64_t adesc = make_smem_desc(xb + (uint32_t)kb * p.x_kb_stride + (uint32_t)mb * 128u * (uint32_t)p.row_bytes, (uint32_t)p.row_bytes);
                         const uint64_t bdesc = make_smem_desc(wb + (uint32_t)kb * p.we_kb_stride, (uint32_t)p.row_bytes);
                         for (int ks = 0; ks < p.ksteps; ks++)
-                            umma_f16(tmem_base + (uint32_t)mb * 64u, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc_e, (kb | ks) != 0);
+                            umma_f16_ws(tmem_base + (uint32_t)mb * 64u, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc_e, (kb | ks) != 0);
                     }
                 }
-                umma_commit(exp_full);
+                umma_commit_ws(exp_full);
             };
             auto issue_reduce = [&](uint32_t i, int c) {
                 const uint64_t bdesc = make_smem_desc(wrs + (i & 1u) * p.wr_bytes, 128);
@@ -275,9 +275,9 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
                     const uint64_t adesc = make_smem_desc(as + (uint32_t)mo * 16384u, 128);
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++)
-                        umma_f16(tmem_red + (uint32_t)mo * (uint32_t)p.red_stride, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc_r, (c | ks) != 0);
+                        umma_f16_ws(tmem_red + (uint32_t)mo * (uint32_t)p.red_stride, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc_r, (c | ks) != 0);
                 }
-                umma_commit(red_done);
+                umma_commit_ws(red_done);
             };
             // weights are constants: requested before the PDL wait, so they overlap the tail of the previous kernel
             issue_we(0, 0);
@@ -332,7 +332,7 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
             mbar_wait(wr_full + 8u * ((i - 1) & 1u), ((i - 1) >> 1) & 1u);
             tc_fence_after();
             issue_reduce(i - 1, p.NC - 1);
-        } else if (lane == 0) {
+        } else {
             pdl_wait();
         }
         __syncwarp();
