@@ -63,6 +63,8 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> dict:
                 extra = ["-Xptxas", "-v"] if verbose_ptxas else []
                 if os.environ.get("GGML_B200_IR_PROFILE"):  # clock64 phase profile inside the fused inverted-residual kernel
                     extra.append("-DGGML_B200_IR_PROFILE")
+                if os.environ.get("GGML_B200_ATTN_PROFILE"):
+                    extra.append("-DGGML_B200_ATTN_PROFILE")
                 _run([NVCC, *ARCH, *COMMON, *extra, "-c", s, "-o", o])
             objs.append(o)
         _run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-lcudart"])

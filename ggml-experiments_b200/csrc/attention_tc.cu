@@ -44,6 +44,7 @@ struct AttnTcParams {
     int H, W, C, heads, d, L, nqb;  // map size, channels, heads, head dim, tokens per sequence, query blocks per sequence
     int items;                      // N * 4 * heads * nqb
     int rows_q, rows_k;             // map rows (of width W/2) per 64-token box
+    int w2_shift;                   // log2(W/2): the envelope makes W/2 a power of two (it divides 64)
     float scale_log2;               // log2(e) / sqrt(d)
     __half * out;                   // [N*H*W][C]
 };
@@ -242,25 +243,36 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
         const uint32_t lsel = (uint32_t)(warp * 32) << 16;
         const uint32_t prow = sp + (uint32_t)row * 128u, psw = (uint32_t)row & 7u;
         int g = 0;
+#ifdef GGML_B200_ATTN_PROFILE
+        long long tacc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define AT_TICK(i) do { if (tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; } } while (0)
+#else
+#define AT_TICK(i) do { } while (0)
+#endif
         for (int k = 0; k < nit; k++) {
             float m = 0.f, l = 0.f;  // reference maximum (scaled log2 units) and running sum
             for (int j = 0; j < nkb; j++, g++) {
+                AT_TICK(6);
                 mbar_wait(s_full, (uint32_t)(g & 1));
                 tc_fence_after();
+                AT_TICK(j == 0 ? 0 : 7);
                 float v[64];
                 tmem_ld64(tmem_s + lsel, v);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_free);  // S is in registers: the tensor core may overwrite it with the next S
+                AT_TICK(1);
                 float mx4[4] = {v[0], v[1], v[2], v[3]};  // four independent chains instead of one of 63 dependent FMNMX
 #pragma unroll
                 for (int c = 4; c < 64; c++) mx4[c & 3] = fmaxf(mx4[c & 3], v[c]);
                 const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
                 // the previous P.V has finished: P may be overwritten and O may be rescaled
+                AT_TICK(2);
                 if (g > 0) {
                     mbar_wait(pv_full, (uint32_t)((g - 1) & 1));
                     tc_fence_after();
                 }
+                AT_TICK(3);
                 if (j == 0) {
                     m = mx;
                 } else {
@@ -294,37 +306,68 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
                     st_shared_v4(prow + ((((uint32_t)gq) ^ psw) << 4), pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
                 }
                 l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+                AT_TICK(4);
                 tc_fence_before();
                 fence_proxy_async();  // P (generic proxy) -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
+                AT_TICK(5);
             }
             // all of this item's P.V has accumulated: normalise and store
             mbar_wait(pv_full, (uint32_t)((g - 1) & 1));
             tc_fence_after();
+            AT_TICK(3);
             const float inv = 1.0f / l;
             int n, pos, h, qb;
             decode(k, n, pos, h, qb);
-            // token of this row -> pixel: t = qb*128 + row, (ty, tx) in the half-resolution lattice of patch position pos
-            const int t  = qb * kQB + row;
-            const int w2 = p.W >> 1;
-            const int ty = t / w2, tx = t - ty * w2;
-            const size_t pix = ((size_t)n * p.H + (size_t)(2 * ty + (pos >> 1))) * p.W + (size_t)(2 * tx + (pos & 1));
-            __half * o = p.out + pix * p.C + h * p.d;
+            // O/l -> f16, staged in this warp's 32 rows of the (now idle) P tile so that the global stores run along the
+            // head's channels: one thread per row would write 4 B to 32 different pixels per instruction.
+            // Row pitch DP/2 + 1 words (conflict-free for one-row-per-thread writes); DP = 64 keeps 32 words and rotates.
+            constexpr int kPitch = DP / 2 + (DP == 64 ? 0 : 1);
+            const uint32_t stage = sp + (uint32_t)warp * 4096u;
+            const uint32_t srow  = stage + (uint32_t)lane * (uint32_t)(kPitch * 4);
 #pragma unroll
             for (int c0 = 0; c0 < DP; c0 += 16) {
                 float v[16];
                 tmem_ld16(tmem_o + lsel + (uint32_t)c0, v);
 #pragma unroll
                 for (int c = 0; c < 16; c += 2) {
-                    if (c0 + c < p.d) {  // d is even (C and heads are multiples of 4 / 8)
-                        const uint32_t hv = pack2(v[c] * inv, v[c + 1] * inv);
-                        *reinterpret_cast<uint32_t *>(o + c0 + c) = hv;
-                    }
+                    const int w = (c0 + c) >> 1;
+                    st_shared_u32(srow + (uint32_t)((DP == 64 ? ((w + lane) & 31) : w) * 4), pack2(v[c] * inv, v[c + 1] * inv));
                 }
             }
             tc_fence_before();
+            AT_TICK(8);
+            __syncwarp();
+            AT_TICK(9);
+            // one (or, for short heads, 2 / 4) row(s) per instruction: lanes run along the head's channels of a pixel
+            const int d2 = p.d >> 1;
+            const int wl = d2 > 16 ? 5 : (d2 > 8 ? 4 : 3);  // log2 of the lanes given to one row
+            const int sub = lane >> wl, w = lane & ((1 << wl) - 1), rstep = 32 >> wl;
+            const int t0 = qb * kQB + warp * 32;
+            if (w < d2) {
+                __half * obase = p.out + h * p.d + 2 * w;
+                const uint32_t sbase = stage + (uint32_t)(w * 4);
+#pragma unroll 4
+                for (int r = sub; r < 32; r += rstep) {
+                    // token of this row -> pixel: (ty, tx) in the half-resolution lattice of patch position pos (W/2 is a power of two)
+                    const int t  = t0 + r;
+                    const int ty = t >> p.w2_shift, tx = t & ((1 << p.w2_shift) - 1);
+                    const size_t pix = ((size_t)n * p.H + (size_t)(2 * ty + (pos >> 1))) * p.W + (size_t)(2 * tx + (pos & 1));
+                    const uint32_t hv = ld_shared_u32(DP == 64 ? stage + (uint32_t)((r * kPitch + ((w + r) & 31)) * 4) : sbase + (uint32_t)(r * kPitch * 4));
+                    *reinterpret_cast<uint32_t *>(obase + pix * p.C) = hv;
+                }
+            }
+            AT_TICK(10);
+            __syncwarp();  // the next block's P overwrites the staging rows
+            tc_fence_before();
         }
+#ifdef GGML_B200_ATTN_PROFILE
+        if (tid == 0 && blockIdx.x == 0)
+            printf("attention_tc phases (cycles, CTA 0, %d items x %d blocks): wait S (first block of item) %lld | ld S %lld | max %lld | wait PV (incl. item end) %lld | exp+P %lld | fence+arrive %lld | store %lld | wait S (other blocks) %lld | O->smem %lld | syncwarp %lld | smem->global %lld\n",
+                   nit, nkb, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10]);
+#endif
+#undef AT_TICK
     }
     __syncthreads();
     if (warp == 0) {
@@ -382,6 +425,8 @@ bool launch_attention_tc(const __half * qkv, int N, int H, int W, int C, int hea
     AttnTcParams p;
     p.H = H; p.W = W; p.C = C; p.heads = heads; p.d = d; p.L = L; p.nqb = L / kQB;
     p.rows_k = kKB / w2; p.rows_q = kKB / w2;
+    p.w2_shift = 0;
+    while ((1 << p.w2_shift) < w2) p.w2_shift++;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
     p.out = out16;
     const int items = N * 4 * heads * p.nqb;

@@ -125,6 +125,29 @@ extern "C" int ggml_b200_debug_attention(const uint16_t * qkv, int N, int H, int
     return 0;
 }
 
+// Average device time (ms) of `reps` back-to-back attention launches on the data of ggml_b200_debug_attention (timing probe).
+extern "C" float ggml_b200_debug_attention_time(const uint16_t * qkv, int N, int H, int W, int C, int heads, int reps) {
+    ensure_device();
+    if (heads <= 0 || C % heads || H % 2 || W % 2 || reps <= 0) return -1.f;
+    const int    dp = attention_padded_head_dim(C / heads);
+    const size_t px = (size_t)N * H * W;
+    DevBuf dQ(qkv, px * 3 * heads * dp * 2), dO(nullptr, px * C * 2);
+    cudaStream_t st = current_stream();
+    cudaEvent_t  e0, e1;
+    B200_CHECK(cudaEventCreate(&e0));
+    B200_CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; i++) launch_attention((const __half *)dQ.p, N, H, W, C, heads, (__half *)dO.p, st);
+    B200_CHECK(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; i++) launch_attention((const __half *)dQ.p, N, H, W, C, heads, (__half *)dO.p, st);
+    B200_CHECK(cudaEventRecord(e1, st));
+    B200_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms / (float)reps;
+}
+
 // LayerNorm folded around two GEMMs, in isolation:
 //   producer  x = A[M,K] . B[C,K]^T + shift0[C]      -> f32 x, f16 x, per-row (sum, sum of squares)
 //   consumer  y = act( LN(x; gamma, beta, eps) . W[N,C]^T + bias[N] ), computed as r * (f16(x) . W'^T - mu * c1) + shift'

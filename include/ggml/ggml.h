@@ -316,6 +316,7 @@ int ggml_b200_debug_stem(const float * x, int chw, int N, int H, int W, const ui
 /* K7 attention core (main.cpp:1073-1086) on a head-padded qkv buffer [N*H*W][3][heads][DP], DP = ..._attention_dp(C/heads) */
 int ggml_b200_debug_attention_dp(int d);
 int ggml_b200_debug_attention(const uint16_t * qkv, int N, int H, int W, int C, int heads, uint16_t * out16);
+float ggml_b200_debug_attention_time(const uint16_t * qkv, int N, int H, int W, int C, int heads, int reps);
 /* LayerNorm folded around two GEMMs (main.cpp:1002-1019 + the following dense): producer x = A.B^T + shift0 with row statistics,
  * consumer y = act(LN(x).W^T + bias); Wf f32 [N][C]; x32 (optional) returns the producer's f32 output */
 int ggml_b200_debug_gemm_ln(const uint16_t * A, const uint16_t * B, int M, int C, int K, const float * shift0, const float * gamma,

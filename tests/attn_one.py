@@ -19,3 +19,6 @@ out = np.zeros((n, hw, hw, c), np.uint16)
 for _ in range(3):
     assert L.ggml_b200_debug_attention(qkv.view(np.uint16).ctypes.data_as(u16p), n, hw, hw, c, heads, out.ctypes.data_as(u16p)) == 0
 print("ok", float(np.abs(out.view(np.float16).astype(np.float32)).mean()))
+L.ggml_b200_debug_attention_time.restype = ctypes.c_float
+L.ggml_b200_debug_attention_time.argtypes = [u16p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+print("us per launch", 1e3 * L.ggml_b200_debug_attention_time(qkv.view(np.uint16).ctypes.data_as(u16p), n, hw, hw, c, heads, 20))
