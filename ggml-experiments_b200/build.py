@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
           "-I" + os.path.join(HERE, "csrc")]
 
 LIB_SOURCES = ["csrc/ggml_b200.cpp", "csrc/plan.cpp", "csrc/exec_exact.cu", "csrc/fuse.cpp", "csrc/fast_kernels.cu",
-               "csrc/gemm_tcgen05.cu", "csrc/dwconv_tma.cu", "csrc/dwreduce.cu", "csrc/ir_fused.cu", "csrc/attention_tc.cu", "csrc/debug_api.cu"]
+               "csrc/gemm_tcgen05.cu", "csrc/dwconv_tma.cu", "csrc/dwreduce.cu", "csrc/ir_fused.cu", "csrc/attention_tc.cu", "csrc/vit_stage.cu", "csrc/debug_api.cu"]
 HOST_SOURCES = ["host/mobilevit.cpp", "host/gru.cpp"]
 
 
@@ -63,6 +63,8 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> dict:
                 extra = ["-Xptxas", "-v"] if verbose_ptxas else []
                 if os.environ.get("GGML_B200_IR_PROFILE"):  # clock64 phase profile inside the fused inverted-residual kernel
                     extra.append("-DGGML_B200_IR_PROFILE")
+                if os.environ.get("GGML_B200_VIT_PROFILE"):
+                    extra.append("-DGGML_B200_VIT_PROFILE")
                 if os.environ.get("GGML_B200_ATTN_PROFILE"):
                     extra.append("-DGGML_B200_ATTN_PROFILE")
                 _run([NVCC, *ARCH, *COMMON, *extra, "-c", s, "-o", o])

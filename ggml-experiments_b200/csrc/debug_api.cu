@@ -1,10 +1,12 @@
 // debug_api.cu -- host-buffer entry points that run ONE kernel of the fast path in isolation, so the parity
 // tests can check each kernel against the oracle / numpy before it is trusted inside a fused plan.
+#include <cstring>
 #include <vector>
 
 #include "fast_kernels.h"
 #include "gemm_tcgen05.h"
 #include "internal.h"
+#include "vit_stage.cuh"
 
 using namespace b200;
 
@@ -451,4 +453,46 @@ extern "C" float ggml_b200_debug_mma_rate(int N, int iters, int ctas_per_sm, int
     for (int i = 0; i < grid; i++) { a += (double)h[(size_t)2 * i]; b += (double)h[(size_t)2 * i + 1]; }
     if (issue_cycles) *issue_cycles = (float)(a / grid / iters);
     return (float)(b / grid / iters);
+}
+
+// K8 in isolation: n_layers transformer layers (main.cpp:988-1172) over the pixel-ordered f32 residual stream x [N,H,W,C].
+// params: n_layers x 16 host pointers in VitLayerHost order (ln1_g ln1_b wq bq wk bk wv bv wo bo ln2_g ln2_b w1 b1 w2 b2), dense kernels
+// f32 [in][out] as the weight file holds them.  reps > 0: returns the mean ms per launch in *ms (outputs then hold the last run).
+extern "C" int ggml_b200_debug_vit_stage(const float * x, int N, int H, int W, int C, int heads, int F, int n_layers, float eps,
+                                         const float * const * params, float * out32, uint16_t * out16, float * stats, int reps, float * ms) {
+    ensure_device();
+    if (!vit_stage_supported(N, H, W, C, heads, F)) return 2;
+    std::vector<VitLayerHost> layers((size_t)n_layers);
+    for (int l = 0; l < n_layers; l++) memcpy(&layers[(size_t)l], params + 16 * l, sizeof(VitLayerHost));
+    std::vector<uint8_t> blob;
+    std::vector<float>   vec;
+    vit_stage_pack(layers.data(), n_layers, C, heads, F, blob, vec);
+    const size_t px = (size_t)N * H * W;
+    DevBuf dX(x, px * C * 4), dB(blob.data(), blob.size()), dV(vec.data(), vec.size() * 4);
+    DevBuf dO32(nullptr, out32 ? px * C * 4 : 0), dO16(nullptr, out16 ? px * C * 2 : 0), dS(nullptr, stats ? px * 8 : 0);
+    VitStageLaunch L;
+    if (!vit_stage_prepare(L, (const float *)dX.p, N, H, W, C, heads, F, n_layers, eps, (const uint8_t *)dB.p, (const float *)dV.p, (float *)dO32.p,
+                           (__half *)dO16.p, (float *)dS.p))
+        return 2;
+    cudaStream_t st = current_stream();
+    vit_stage_launch(L, st);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(st));
+    if (reps > 0 && ms) {
+        cudaEvent_t e0, e1;
+        B200_CHECK(cudaEventCreate(&e0));
+        B200_CHECK(cudaEventCreate(&e1));
+        B200_CHECK(cudaEventRecord(e0, st));
+        for (int i = 0; i < reps; i++) vit_stage_launch(L, st);
+        B200_CHECK(cudaEventRecord(e1, st));
+        B200_CHECK(cudaEventSynchronize(e1));
+        B200_CHECK(cudaEventElapsedTime(ms, e0, e1));
+        *ms /= (float)reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    if (out32) B200_CHECK(cudaMemcpy(out32, dO32.p, px * C * 4, cudaMemcpyDeviceToHost));
+    if (out16) B200_CHECK(cudaMemcpy(out16, dO16.p, px * C * 2, cudaMemcpyDeviceToHost));
+    if (stats) B200_CHECK(cudaMemcpy(stats, dS.p, px * 8, cudaMemcpyDeviceToHost));
+    return 0;
 }

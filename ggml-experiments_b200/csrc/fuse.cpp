@@ -26,6 +26,7 @@
 #include "fast_kernels.h"
 #include "gemm_tcgen05.h"
 #include "internal.h"
+#include "vit_stage.cuh"
 
 namespace b200 {
 namespace {
@@ -47,7 +48,11 @@ struct FVal {  // an activation in pixel-major NHWC order: [N*H*W, C]
     int64_t rows() const { return (int64_t)N * H * W; }
 };
 
-enum FKind { FK_INPUT, FK_STEM, FK_CONV1, FK_CONV3, FK_DW, FK_LN, FK_LINEAR, FK_QKV, FK_ATTN, FK_ADD, FK_POOL, FK_IR };
+enum FKind { FK_INPUT, FK_STEM, FK_CONV1, FK_CONV3, FK_DW, FK_LN, FK_LINEAR, FK_QKV, FK_ATTN, FK_ADD, FK_POOL, FK_IR, FK_VIT };
+
+struct FNode;
+// one transformer layer absorbed into an FK_VIT node (K8): the (dead) nodes whose parameters the fused stage kernel needs
+struct VitLayerNodes { FNode *ln1, *qkv, *proj, *ln2, *up, *down; };
 
 struct BNParams {
     const ggml_tensor *mean = nullptr, *var = nullptr, *gamma = nullptr, *beta = nullptr;
@@ -74,6 +79,8 @@ struct FNode {
     // K4: a reduce conv of kind FK_IR runs the whole inverted residual; ir_expand / ir_dw are the (dead) nodes it absorbed
     FNode *ir_expand = nullptr, *ir_dw = nullptr;
     bool   fused_ir  = false;         // this (dead) node's constants are still needed: it runs inside an FK_IR kernel
+    std::vector<VitLayerNodes> vit;   // K8: the layers of a fused transformer stage (kind FK_VIT)
+    int    vit_F = 0;
     int   order = -1;
     // folded constants (offsets into the plan's constant pool)
     int64_t c_w = -1, c_scale = -1, c_shift = -1, c_c1 = -1;
@@ -596,6 +603,28 @@ struct Planner {
                     n->c_shift = pool.add(bias.data(), bias.size() * 4);
                     plan->n_folded += 12;
                 } break;
+                case FK_VIT: {
+                    // K8: every layer's weights tiled into the streaming order of the fused stage kernel (vit_stage.cu)
+                    std::vector<VitLayerHost> hl;
+                    for (const VitLayerNodes & L : n->vit) {
+                        VitLayerHost h;
+                        h.ln1_g = (const float *)L.ln1->g->data;  h.ln1_b = (const float *)L.ln1->b->data;
+                        h.wq = (const float *)L.qkv->wq->data;    h.bq = (const float *)L.qkv->bq->data;
+                        h.wk = (const float *)L.qkv->wk->data;    h.bk = (const float *)L.qkv->bk->data;
+                        h.wv = (const float *)L.qkv->wv->data;    h.bv = (const float *)L.qkv->bv->data;
+                        h.wo = (const float *)L.proj->w->data;    h.bo = (const float *)L.proj->bias->data;
+                        h.ln2_g = (const float *)L.ln2->g->data;  h.ln2_b = (const float *)L.ln2->b->data;
+                        h.w1 = (const float *)L.up->w->data;      h.b1 = (const float *)L.up->bias->data;
+                        h.w2 = (const float *)L.down->w->data;    h.b2 = (const float *)L.down->bias->data;
+                        hl.push_back(h);
+                    }
+                    std::vector<uint8_t> blob;
+                    std::vector<float>   vec;
+                    vit_stage_pack(hl.data(), (int)hl.size(), n->out->C, n->heads, n->vit_F, blob, vec);
+                    n->c_w     = pool.add(blob.data(), blob.size());
+                    n->c_shift = pool.add(vec.data(), vec.size() * 4);
+                    plan->n_folded += 16 * (int)hl.size();
+                } break;
                 default: break;
             }
         }
@@ -681,6 +710,84 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
     }
     rebuild_users();
 
+    // ---- K8: the transformer layers of one MobileViT block (main.cpp:1196-1204) as ONE kernel: x -> LN -> qkv -> attention -> projection
+    // (+x) -> LN -> up (+SiLU) -> down (+res), repeated; tiles of whole sequences never meet, so the residual stream stays on chip for the
+    // whole stage (vit_stage.cu).  GGML_B200_VIT_FUSE=0 keeps the five launches per layer; =1 fuses every stage the kernel covers;
+    // default: stages of at most kVitAutoTiles 128-token tiles, where the separate launches are latency-bound. ----
+    {
+        const char * e    = getenv("GGML_B200_VIT_FUSE");
+        const int    mode = e ? atoi(e) : 2;
+        auto sole_user = [&](FVal * v, FKind k) -> FNode * {
+            if (!v || out_set.count(v) || v->users.size() != 1 || v->users[0]->kind != k || v->users[0]->dead) return nullptr;
+            return v->users[0];
+        };
+        // one layer starting at the residual stream value x; returns the layer's output value or nullptr
+        auto match_layer = [&](FVal * x, VitLayerNodes & L, int & heads, int & F) -> FVal * {
+            if (!x || out_set.count(x) || x->users.size() != 2) return nullptr;
+            FNode *ln1 = nullptr, *proj = nullptr;
+            for (FNode * u : x->users) {
+                if (u->kind == FK_LN && u->in[0] == x && !u->dead) ln1 = u;
+                else if (u->kind == FK_LINEAR && u->res == x && !u->dead) proj = u;
+            }
+            if (!ln1 || !proj || proj->act || proj->ln_g) return nullptr;
+            FNode * qkv = sole_user(ln1->out, FK_QKV);
+            if (!qkv || qkv->ln_g) return nullptr;
+            FNode * attn = sole_user(qkv->out, FK_ATTN);
+            if (!attn || sole_user(attn->out, FK_LINEAR) != proj || proj->in[0] != attn->out) return nullptr;
+            FVal * x1 = proj->out;
+            if (out_set.count(x1) || x1->users.size() != 2) return nullptr;
+            FNode *ln2 = nullptr, *down = nullptr;
+            for (FNode * u : x1->users) {
+                if (u->kind == FK_LN && u->in[0] == x1 && !u->dead) ln2 = u;
+                else if (u->kind == FK_LINEAR && u->res == x1 && !u->dead) down = u;
+            }
+            if (!ln2 || !down || down->act || down->ln_g) return nullptr;
+            FNode * up = sole_user(ln2->out, FK_LINEAR);
+            if (!up || !up->act || up->res || up->ln_g || sole_user(up->out, FK_LINEAR) != down || down->in[0] != up->out) return nullptr;
+            if (ln1->eps != ln2->eps || x1->C != x->C || down->out->C != x->C) return nullptr;
+            heads = qkv->heads;
+            F     = up->out->C;
+            L     = VitLayerNodes{ln1, qkv, proj, ln2, up, down};
+            return down->out;
+        };
+        constexpr int kVitAutoTiles = 4 * 148;
+        for (size_t vi = 0; mode > 0 && vi < P.vals.size(); vi++) {
+            FVal * x0 = P.vals[vi].get();
+            if (x0->prod && x0->prod->kind == FK_VIT) continue;
+            std::vector<VitLayerNodes> layers;
+            int    heads = 0, F = 0;
+            FVal * x = x0;
+            for (;;) {
+                VitLayerNodes L;
+                int           h2 = 0, f2 = 0;
+                FVal *        nx = match_layer(x, L, h2, f2);
+                if (!nx || (!layers.empty() && (h2 != heads || f2 != F || L.ln1->eps != layers[0].ln1->eps))) break;
+                heads = h2; F = f2;
+                layers.push_back(L);
+                x = nx;
+            }
+            if (layers.empty() || !vit_stage_supported(x0->N, x0->H, x0->W, x0->C, heads, F)) continue;
+            const int64_t tiles = (x0->rows() + 127) / 128;
+            if (mode == 2 && tiles > kVitAutoTiles) continue;
+            FNode * v = layers.back().down;  // becomes the stage node: its output value is the stage's output
+            for (const VitLayerNodes & L : layers) {
+                FNode * attn = L.qkv->out->users[0];
+                for (FNode * d : {L.ln1, L.qkv, attn, L.proj, L.ln2, L.up, L.down})
+                    if (d != v) d->dead = true;
+            }
+            v->kind  = FK_VIT;
+            v->name  = "vit_stage";
+            v->in    = {x0};
+            v->res   = nullptr;
+            v->heads = heads;
+            v->vit_F = F;
+            v->eps   = layers[0].ln1->eps;
+            v->vit   = layers;
+            plan->n_folded += 4 * (int)layers.size();
+            rebuild_users();
+        }
+    }
+
     // ---- LayerNorm folding: LN(x) feeding only GEMMs disappears.  The GEMM that produces x (tile spans the row) also writes
     // per-row (sum, sum of squares) and an f16 copy of x; each consumer multiplies raw x with gamma-scaled weights and applies
     // r * (acc - mu * c1[n]) in its epilogue (beta folded into the shift).  Saves the LN kernels' 4+2 bytes per element. ----
@@ -690,7 +797,7 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
             if (ln->kind != FK_LN || ln->dead) continue;
             FVal *x = ln->in[0], *y = ln->out;
             FNode * pr = x->prod;
-            if (!pr || pr->dead || !(pr->kind == FK_CONV1 || pr->kind == FK_LINEAR) || x->C > 256 || x->C % 8) continue;
+            if (!pr || pr->dead || !(pr->kind == FK_CONV1 || pr->kind == FK_LINEAR || pr->kind == FK_VIT) || x->C > 256 || x->C % 8) continue;
             if (out_set.count(y) || y->users.empty()) continue;
             bool ok = true;
             for (FNode * u : y->users)
@@ -752,7 +859,7 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
             case FK_CONV1: case FK_CONV3: case FK_DW: case FK_LINEAR: case FK_QKV: case FK_ATTN: case FK_IR:
                 for (FVal * v : n->in) v->need16 = true;
                 break;
-            case FK_LN: case FK_ADD:
+            case FK_LN: case FK_ADD: case FK_VIT:
                 for (FVal * v : n->in) v->need32 = true;
                 break;
             case FK_POOL: n->in[0]->need32 = true; break;
@@ -954,6 +1061,21 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                                      2.0 * ((double)E * in->C + 9.0 * E + (double)o->C * E);
                 add_launch(plan, "ir_fused_expand_dw_reduce", [IL](cudaStream_t st) { ir_fused_launch(*IL, st); }, flops, bytes, what + cfg,
                            (double)in->rows() * in->C * 2 + (double)o->rows() * o->C * 2 + 2.0 * ((double)E * in->C + 9.0 * E + (double)o->C * E));
+            } break;
+            case FK_VIT: {
+                FVal * in = n->in[0];
+                auto VL = std::make_shared<VitStageLaunch>();
+                const int nl = (int)n->vit.size(), F = n->vit_F, C = in->C;
+                if (!vit_stage_prepare(*VL, in->p32, in->N, in->H, in->W, C, n->heads, F, nl, n->eps, P.pool.ptr<uint8_t>(n->c_w), P.pool.ptr<float>(n->c_shift),
+                                       o->p32, o->p16, o->need_stats ? o->pstats : nullptr))
+                    return false;
+                const double rows = (double)in->rows(), L = (double)(in->H / 2) * (in->W / 2);
+                const double flops = nl * (2.0 * rows * C * (4.0 * C + 2.0 * F) + 4.0 * in->N * 4 * L * L * C);
+                const double wbytes = nl * 2.0 * C * (4.0 * C + 2.0 * F);
+                char cfg[96];
+                snprintf(cfg, sizeof cfg, " %d layers, %d heads, ffn %d, L=%d, %d tiles", nl, n->heads, F, (int)L, VL->p.tiles);
+                add_launch(plan, "vit_stage_fused", [VL](cudaStream_t st) { vit_stage_launch(*VL, st); }, flops,
+                           rows * C * (4 + (o->p16 ? 2 : 0) + (o->p32 ? 4 : 0)) + wbytes, what + cfg, rows * C * 4 + wbytes);
             } break;
             case FK_CONV3: {
                 FVal * a = n->in[0];

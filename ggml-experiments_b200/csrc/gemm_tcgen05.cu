@@ -31,7 +31,7 @@ namespace b200 {
 static constexpr int kBlockM   = 128;
 static constexpr int kBlockK   = 64;   // 64 f16 = 128 bytes = one swizzle-128B row
 static constexpr int kThreads  = 320;  // 10 warps: TMA, MMA, 2 x 4 epilogue
-static constexpr int kMaxStage = 4;
+static constexpr int kMaxStage = 8;  // deep rings only for small grids (choose_tiling): a lone CTA per SM hides the TMA latency with loads in flight, not with neighbours
 static constexpr int kCtrlBytes = 4096;
 enum { kEpiAct = 1, kEpiRes32 = 2, kEpiOut16 = 4, kEpiOut32 = 8, kEpiLn = 16, kEpiStats = 32, kEpiRes16 = 64 };  // barriers + TMEM slot + per-column scale/shift, padded to keep 1 KiB alignment
 
@@ -534,9 +534,13 @@ static void choose_tiling(GemmLaunch & L, int N) {
     // stays resident (ring = A only) when that does not cost a CTA per SM: one CTA with resident weights was measured slower
     // than two CTAs re-loading them (ffn up-projection 87 -> 99 us), while with equal occupancy it is faster (qkv 96 -> 91 us,
     // expand 16->64 214 -> 129 us).
+    // Small grids (fewer CTAs than SMs: small batches, the last stages) are latency chains of k-blocks on a lone CTA per SM: a second
+    // CTA slot buys nothing there, so the shared memory goes into a deeper ring instead (conv3x3 at 8x8: 2 -> 6 stages in flight).
+    const int  mt_all     = (p.M + p.tile_m - 1) / p.tile_m;
+    const bool small_grid = mt_all * p.n_tiles <= runtime().sm_count && getenv("GGML_B200_GEMM_NO_DEEP") == nullptr;
     auto fit = [&](int stage_bytes, int fixed, int & ctas) {
         int stages = 0;
-        for (ctas = p.block_n <= 128 ? 2 : 1; ctas >= 1; ctas--) {
+        for (ctas = (p.block_n <= 128 && !small_grid) ? 2 : 1; ctas >= 1; ctas--) {
             const int budget = (216 * 1024) / ctas - 1024 - kCtrlBytes - staging - fixed;
             stages           = budget > 0 ? budget / stage_bytes : 0;
             if (stages >= 2 || ctas == 1) break;
@@ -551,7 +555,8 @@ static void choose_tiling(GemmLaunch & L, int N) {
     const int fixed       = p.b_resident ? b_total : 0;
     int       stages      = p.b_resident ? st_res : st_ring;
     L.ctas_per_sm         = p.b_resident ? ctas_res : ctas_ring;
-    if (stages > kMaxStage) stages = kMaxStage;
+    if (stages > (small_grid ? kMaxStage : 4)) stages = small_grid ? kMaxStage : 4;
+    if (small_grid && stages > p.num_kb && !p.a_cp_async) stages = p.num_kb < 2 ? 2 : p.num_kb;  // one tile per CTA: no more slots than its k-blocks
     if (stages < 1) stages = 1;
     if (const char * e = getenv("GGML_B200_GEMM_STAGES")) stages = atoi(e);      // tuning probes
     if (const char * e = getenv("GGML_B200_GEMM_CTAS")) L.ctas_per_sm = atoi(e);

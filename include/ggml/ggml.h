@@ -329,6 +329,12 @@ int ggml_b200_debug_ir_fused(const uint16_t * x, int N, int H, int W, int Cin, i
                              const float * sr, const float * hr, const float * res32, uint16_t * out16, float * out32);
 /* timing probe: mean ms per launch of the fused block and (optionally) of the three separate kernels it replaces */
 float ggml_b200_debug_ir_time(int N, int H, int W, int Cin, int E, int Cout, int stride, int with_res, int reps, float * unfused_ms);
+/* K8 fused transformer stage (transformer_layer::forward, main.cpp:988-1172, x n_layers as mobile_vit_layer::forward loops it,
+ * main.cpp:1196-1204) over the pixel-ordered f32 residual stream x [N,H,W,C]; sequences = pixels sharing a patch position (main.cpp:721-747).
+ * params: n_layers x 16 host pointers (ln1_g ln1_b wq bq wk bk wv bv wo bo ln2_g ln2_b w1 b1 w2 b2), dense kernels f32 [in][out].
+ * Returns 2 when the shape is outside the fused kernel's envelope.  reps > 0: *ms = mean ms per launch. */
+int ggml_b200_debug_vit_stage(const float * x, int N, int H, int W, int C, int heads, int F, int n_layers, float eps,
+                              const float * const * params, float * out32, uint16_t * out16, float * stats, int reps, float * ms);
 
 #ifdef __cplusplus
 }

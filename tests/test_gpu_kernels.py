@@ -241,3 +241,82 @@ def test_fused_inverted_residual_matches_numpy(L, n, h, w, cin, e, cout, stride,
     assert err.max() < 4e-3 * scale and rel < 1.5e-3
     got16 = out16.view(np.float16).astype(np.float64)
     assert np.abs(got16 - out32).max() <= 1e-3 * scale
+
+
+# ---- K8 fused transformer stage (vit_stage.cu) ---------------------------------------------------------------
+def _vit_ref(x, layers, heads, eps):
+    """n transformer layers (main.cpp:988-1172) in float64 over sequences = pixels sharing a patch position (main.cpp:721-747)."""
+    n, h, w, c = x.shape
+    seq_len, d = (h // 2) * (w // 2), c // heads
+    t = x.astype(np.float64).reshape(n, h // 2, 2, w // 2, 2, c).transpose(0, 2, 4, 1, 3, 5).reshape(n * 4, seq_len, c)
+
+    def ln(v, g, b):
+        mu = v.mean(-1, keepdims=True)
+        var = ((v - mu) ** 2).mean(-1, keepdims=True)
+        return (v - mu) / np.sqrt(var + eps) * g + b
+
+    for p in layers:
+        (g1, b1, wq, bq, wk, bk, wv, bv, wo, bo, g2, b2, w1, bf1, w2, bf2) = [a.astype(np.float64) for a in p]
+        y = ln(t, g1, b1)
+        q, k, v = y @ wq + bq, y @ wk + bk, y @ wv + bv
+        split = lambda a: a.reshape(n * 4, seq_len, heads, d).transpose(0, 2, 1, 3)
+        s = split(q) @ split(k).transpose(0, 1, 3, 2) / np.sqrt(d)
+        s = np.exp(s - s.max(-1, keepdims=True))
+        s /= s.sum(-1, keepdims=True)
+        a = (s @ split(v)).transpose(0, 2, 1, 3).reshape(n * 4, seq_len, c)
+        t = t + a @ wo + bo
+        y = ln(t, g2, b2)
+        t = t + _silu(y @ w1 + bf1) @ w2 + bf2
+    return t.reshape(n, 2, 2, h // 2, w // 2, c).transpose(0, 3, 1, 4, 2, 5).reshape(n, h, w, c)
+
+
+def _vit_params(rng, c, f, n_layers):
+    layers = []
+    for _ in range(n_layers):
+        dense = lambda i, o: (rng.standard_normal((i, o)) / np.sqrt(i)).astype(np.float32)
+        vecr = lambda m, s=0.1: (rng.standard_normal(m) * s).astype(np.float32)
+        layers.append([(1.0 + vecr(c)).astype(np.float32), vecr(c), dense(c, c), vecr(c), dense(c, c), vecr(c), dense(c, c), vecr(c),
+                       (dense(c, c) * 0.5).astype(np.float32), vecr(c), (1.0 + vecr(c)).astype(np.float32), vecr(c), dense(c, f), vecr(f),
+                       (dense(f, c) * 0.5).astype(np.float32), vecr(c)])
+    return layers
+
+
+@pytest.mark.parametrize("n,h,w,c,heads,f,nl", [
+    (3, 16, 16, 192, 4, 384, 2),    # MobileViT-S stage 4 (L = 64)
+    (5, 8, 8, 240, 4, 480, 3),      # S stage 5 (L = 16, head dim 60 padded to 64, hidden 480 = 3.75 chunks)
+    (2, 16, 16, 120, 4, 240, 2),    # XS stage 4 (head dim 30 -> 32, C % 32 = 24, N padded to 128)
+    (2, 8, 8, 144, 4, 288, 1),      # XS stage 5 (head dim 36 -> 48)
+    (2, 16, 16, 80, 4, 160, 2),     # XXS stage 4 (head dim 20 -> 32)
+    (7, 8, 8, 96, 4, 192, 2),       # XXS stage 5; 28 sequences of 16 tokens: the last tile is half empty
+    (3, 4, 4, 64, 4, 128, 2),       # 128^2 input: L = 4 (eight sequences per warp)
+    (1, 2, 2, 64, 4, 128, 1),       # 64^2 input: L = 1
+    (1, 8, 16, 192, 4, 384, 1),     # non-square map, L = 32
+    (100, 16, 16, 192, 4, 384, 1),  # 200 tiles: CTAs walk more than one tile
+])
+def test_vit_stage_fused_vs_float64(L, n, h, w, c, heads, f, nl):
+    """k_vit_stage: LN -> qkv -> attention -> projection + residual -> LN -> MLP + residual, nl layers in one launch, vs float64.
+    Operands are f16 (as in the unfused FAST plan), accumulation and the residual stream f32."""
+    vpp = ctypes.POINTER(f32p)
+    L.ggml_b200_debug_vit_stage.argtypes = [f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_float, vpp, f32p, u16p, f32p, ctypes.c_int, f32p]
+    rng = np.random.default_rng(n * 1000 + c)
+    x = rng.standard_normal((n, h, w, c)).astype(np.float32)
+    x += rng.standard_normal((n, h, w, 1)).astype(np.float32) * 2.0  # per-token mean well away from zero (ADVICE: LayerNorm cancellation)
+    layers = _vit_params(rng, c, f, nl)
+    flat = [a for p in layers for a in p]
+    arr = (f32p * len(flat))(*[_p(a, f32p) for a in flat])
+    out32 = np.zeros((n, h, w, c), np.float32)
+    out16 = np.zeros((n, h, w, c), np.float16)
+    stats = np.zeros((n, h, w, 2), np.float32)
+    rc = L.ggml_b200_debug_vit_stage(_p(x, f32p), n, h, w, c, heads, f, nl, 1e-5, arr, _p(out32, f32p), _h(out16), _p(stats, f32p), 0, None)
+    assert rc == 0
+    ref = _vit_ref(x, layers, heads, 1e-5)
+    rms = float(np.sqrt((ref ** 2).mean()))
+    err = np.abs(out32 - ref)
+    rel = float(np.sqrt(((out32 - ref) ** 2).sum() / (ref ** 2).sum()))
+    print(f"vit_stage n={n} {h}x{w} C={c} F={f} layers={nl}: rel-L2 {rel:.2e}, max-abs {err.max():.2e} (rms {rms:.2f})")
+    assert np.isfinite(out32).all()
+    assert rel < 3e-3 and err.max() < 3e-2 * rms
+    assert np.abs(out16.astype(np.float32) - out32).max() <= np.abs(out32).max() * 2.0 ** -10
+    assert np.allclose(stats[..., 0], out32.sum(-1), rtol=1e-4, atol=1e-3 * rms * c ** 0.5)
+    assert np.allclose(stats[..., 1], (out32.astype(np.float64) ** 2).sum(-1), rtol=1e-4)
