@@ -54,11 +54,14 @@ extern "C" int ggml_b200_debug_conv3x3(const uint16_t * x0, int C0, const uint16
     DevBuf dX0(x0, px * C0 * 2), dX1(x1, C1 ? px * C1 * 2 : 0), dW(Wt, (size_t)OC * 9 * (C0 + C1) * 2);
     DevBuf dS(scale, scale ? (size_t)OC * 4 : 0), dH(shift, shift ? (size_t)OC * 4 : 0);
     DevBuf dO(nullptr, px * OC * 4);
+    std::vector<uint8_t> halo;  // the halo-mode kernel is used where the map qualifies (GGML_B200_CONV_NO_HALO=1: per-tap boxes everywhere)
+    conv3x3_pack_halo(Wt, OC, C0, C1, halo);
+    DevBuf dWh(halo.data(), halo.size());
     GemmEpilogue ep;
     ep.scale = (const float *)dS.p; ep.shift = (const float *)dH.p; ep.act = act;
     ep.out32 = (float *)dO.p; ep.ld32 = OC;
     GemmLaunch L;
-    if (!conv3x3_prepare(L, (const __half *)dX0.p, C0, (const __half *)dX1.p, C1, Nimg, H, W, (const __half *)dW.p, OC, ep)) return 1;
+    if (!conv3x3_prepare(L, (const __half *)dX0.p, C0, (const __half *)dX1.p, C1, Nimg, H, W, (const __half *)dW.p, OC, ep, (const uint8_t *)dWh.p)) return 1;
     cudaStream_t st = current_stream();
     gemm_launch(L, st);
     B200_CHECK(cudaGetLastError());

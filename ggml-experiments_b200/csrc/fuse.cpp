@@ -83,7 +83,7 @@ struct FNode {
     int    vit_F = 0;
     int   order = -1;
     // folded constants (offsets into the plan's constant pool)
-    int64_t c_w = -1, c_scale = -1, c_shift = -1, c_c1 = -1;
+    int64_t c_w = -1, c_scale = -1, c_shift = -1, c_c1 = -1, c_w2 = -1;  // c_w2: 3x3 weights in the halo layout (conv3x3_pack_halo)
     // LayerNorm folded into this GEMM (consumer side): gamma / beta of the LN that preceded it
     const ggml_tensor *ln_g = nullptr, *ln_b = nullptr;
     float ln_eps = 0.f;
@@ -535,6 +535,14 @@ struct Planner {
                         n->c_c1 = pool.add(c1.data(), OC * 4);
                     }
                     n->c_w = pool.add(wt.data(), wt.size() * 2);
+                    if (n->kind == FK_CONV3 && KW == 3) {  // the same weights pre-tiled for the halo-mode kernel (gemm_tcgen05.cu, conv == 2)
+                        const int c0 = n->in[0]->C, c1 = n->in.size() > 1 ? n->in[1]->C : 0;
+                        if (c0 + c1 == IC) {
+                            std::vector<uint8_t> halo;
+                            conv3x3_pack_halo(wt.data(), OC, c0, c1, halo);
+                            n->c_w2 = pool.add(halo.data(), halo.size());
+                        }
+                    }
                     plan->n_folded += 2;
                     fold_bn(n, OC, n->ln_g ? &pre : nullptr);
                 } break;
@@ -1087,7 +1095,10 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 ep.out16 = o->p16; ep.ld16 = o->C;
                 ep.out32 = o->p32; ep.ld32 = o->C;
                 auto L = std::make_shared<GemmLaunch>();
-                if (!conv3x3_prepare(*L, a->p16, a->C, b ? b->p16 : nullptr, b ? b->C : 0, a->N, a->H, a->W, P.pool.ptr<__half>(n->c_w), o->C, ep)) return false;
+                if (!conv3x3_prepare(*L, a->p16, a->C, b ? b->p16 : nullptr, b ? b->C : 0, a->N, a->H, a->W, P.pool.ptr<__half>(n->c_w), o->C, ep,
+                                     P.pool.ptr<uint8_t>(n->c_w2)))
+                    return false;
+                if (L->p.conv == 2) what += " halo";
                 const int ict = a->C + (b ? b->C : 0);
                 const double bytes = (double)a->rows() * ict * 2 + (double)o->C * 9 * ict * 2 + (double)o->rows() * o->C * ((o->p16 ? 2 : 0) + (o->p32 ? 4 : 0));
                 add_launch(plan, "conv3x3_tcgen05_implicit_gemm", [L](cudaStream_t st) { gemm_launch(*L, st); }, 2.0 * a->rows() * o->C * 9 * ict, bytes, what,

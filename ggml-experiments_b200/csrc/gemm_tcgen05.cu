@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     const int       stage_bytes = a_bytes + (p.b_resident ? 0 : b_bytes);
     uint8_t *       smem_bres   = smem;
     uint8_t *       ring        = smem + (p.b_resident ? (size_t)p.num_kb * b_bytes : 0);
-    uint64_t *      bars        = (uint64_t *)(ring + (size_t)p.stages * stage_bytes);
+    uint64_t *      bars        = (uint64_t *)(ring + (size_t)p.ring_bytes);
     uint64_t *      full_bar    = bars;
     uint64_t *      empty_bar   = bars + kMaxStage;
     uint64_t *      tmem_full   = bars + 2 * kMaxStage;      // [4]
@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     float *         s_scale     = (float *)(bars + 2 * kMaxStage + 16);  // 16-byte aligned: read back with LDS.128
     float *         s_shift     = s_scale + 256;
     float *         s_c1        = s_shift + 256;  // LayerNorm folding: per-column sum of the gamma-scaled weights
+    uint64_t *      bfull_bar   = (uint64_t *)(s_c1 + 256);  // conv == 2: weight ring [kMaxStage] full / [kMaxStage] empty
+    uint64_t *      bempty_bar  = bfull_bar + kMaxStage;
     // epilogue staging (per epilogue warp group): 128 rows x 128 B tiles in the TMA 128B-swizzle layout
-    uint8_t *       stage_base  = ring + (size_t)p.stages * stage_bytes + kCtrlBytes;
+    uint8_t *       stage_base  = ring + (size_t)p.ring_bytes + kCtrlBytes;
     const int       stg16_bytes = p.ep.out16 ? kBlockM * 128 : 0;      // 64 f16 columns per row
     const int       stg32_bytes = (p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0;  // 2 x 32 f32 columns per row
 
@@ -110,6 +112,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         }
         for (int a = 0; a < 2; a++) mbar_init(smem_u32(&res_full[a]), 1);
         mbar_init(smem_u32(bres_full), 1);
+        for (int s = 0; s < kMaxStage; s++) {
+            mbar_init(smem_u32(&bfull_bar[s]), 1);
+            mbar_init(smem_u32(&bempty_bar[s]), 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -171,6 +177,36 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fb) : "memory");
         }
+    } else if (warp == 0 && p.conv == 2) {
+        // ===================== producer, halo mode: per (64-channel block, kw) ONE activation box with a one-row halo above and
+        // below -- the three kh taps are start-address offsets of W rows into it -- and per tap one pre-tiled weight block by a 1-D
+        // bulk copy.  A third of the activation boxes (and TMA box rows) of the per-tap scheme, no tensor map for the weights. =====
+        uint32_t ia = 0, ib = 0;
+        const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
+        const uint32_t a_box_bytes = (uint32_t)(p.tile_m + 2 * p.W) * 128u, wb_bytes = (uint32_t)p.block_n * 128u;
+        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+            const int m0 = tile * tile_m, hw = p.H * p.W;
+            const int img = m0 / hw, y0 = p.rows_per_tile ? (m0 % hw) / p.W : 0;
+            for (int cb = 0; cb < cblk_tot; cb++) {
+                const int src = cb >= p.cblk0, cbl = src ? cb - p.cblk0 : cb;
+                for (int kw = 0; kw < 3; kw++, ia++) {
+                    const uint32_t sa = ia % (uint32_t)p.stages;
+                    mbar_wait(smem_u32(&empty_bar[sa]), ((ia / (uint32_t)p.stages) & 1u) ^ 1u);
+                    mbar_expect_tx_ws(smem_u32(&full_bar[sa]), a_box_bytes);
+                    const uint32_t dst = smem_u32(ring + (size_t)sa * p.a_slot_bytes);
+                    if (src) tma_load_4d_ws(dst, &map_a1, cbl * kBlockK, kw - 1, y0 - 1, img, smem_u32(&full_bar[sa]));
+                    else tma_load_4d_ws(dst, &map_a0, cbl * kBlockK, kw - 1, y0 - 1, img, smem_u32(&full_bar[sa]));
+                    for (int kh = 0; kh < 3; kh++, ib++) {
+                        const uint32_t sb = ib % (uint32_t)p.b_stages;
+                        mbar_wait(smem_u32(&bempty_bar[sb]), ((ib / (uint32_t)p.b_stages) & 1u) ^ 1u);
+                        mbar_expect_tx_ws(smem_u32(&bfull_bar[sb]), wb_bytes);
+                        const uint8_t * wsrc = p.w_halo + ((size_t)((cb * 3 + kw) * 3 + kh) * p.n_pad + (size_t)n0) * 128u;
+                        bulk_load_1d_ws(smem_u32(ringB + (size_t)sb * wb_bytes), wsrc, wb_bytes, smem_u32(&bfull_bar[sb]));
+                    }
+                }
+            }
+        }
+        __syncwarp();
     } else if (warp == 0) {
         // ===================== TMA producer (whole warp, elected lane issues) =====================
         {
@@ -206,6 +242,46 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     }
                 }
             }
+        }
+        __syncwarp();
+    } else if (warp == 1 && p.conv == 2) {
+        // ===================== MMA issuer, halo mode =====================
+        const uint32_t idesc = make_idesc(p.block_n);
+        const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
+        const uint32_t wb_bytes = (uint32_t)p.block_n * 128u;
+        uint32_t ia = 0, ib = 0, t = 0;
+        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
+            const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;
+            mbar_wait(smem_u32(&tmem_empty[acc]), aph ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
+            uint32_t first = 1;
+            for (int cb = 0; cb < cblk_tot; cb++) {
+                const int src = cb >= p.cblk0;
+                const int rem = src ? p.C1 - (cb - p.cblk0) * kBlockK : p.C0 - cb * kBlockK;
+                const int ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
+                for (int kw = 0; kw < 3; kw++, ia++) {
+                    const uint32_t sa = ia % (uint32_t)p.stages;
+                    mbar_wait(smem_u32(&full_bar[sa]), (ia / (uint32_t)p.stages) & 1u);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(ring + (size_t)sa * p.a_slot_bytes);
+                    for (int kh = 0; kh < 3; kh++, ib++) {
+                        const uint32_t sb = ib % (uint32_t)p.b_stages;
+                        mbar_wait(smem_u32(&bfull_bar[sb]), (ib / (uint32_t)p.b_stages) & 1u);
+                        tc_fence_after();
+                        // tap (kh, kw): the tile's pixels shifted down by kh image rows = W rows of 128 B (a multiple of the 1 KiB swizzle atom)
+                        const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(kh * p.W) * 128u, 128);
+                        const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * wb_bytes), 128);
+                        for (int k = 0; k < ksteps; k++) {
+                            umma_f16_ws(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        umma_commit_ws(smem_u32(&bempty_bar[sb]));
+                    }
+                    umma_commit_ws(smem_u32(&empty_bar[sa]));
+                }
+            }
+            umma_commit_ws(smem_u32(&tmem_full[acc]));
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -561,6 +637,7 @@ static void choose_tiling(GemmLaunch & L, int N) {
     if (const char * e = getenv("GGML_B200_GEMM_STAGES")) stages = atoi(e);      // tuning probes
     if (const char * e = getenv("GGML_B200_GEMM_CTAS")) L.ctas_per_sm = atoi(e);
     p.stages     = stages;
+    p.ring_bytes = stages * stage_bytes;
     L.smem_bytes = 1024 + (size_t)fixed + (size_t)stages * stage_bytes + kCtrlBytes + staging;
 }
 
@@ -658,8 +735,32 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
     return true;
 }
 
+size_t conv3x3_pack_halo(const uint16_t * Wt, int OC, int C0, int C1, std::vector<uint8_t> & out) {
+    // [channel block (source 0 blocks, then source 1)][kw][kh][n_pad rows][64 channels], rows of 128 B with the 16-byte chunk index
+    // XOR (row % 8): exactly what the UMMA descriptor of a 128B-swizzled K-major B tile reads, for ANY run of rows starting at a
+    // multiple of 8 -- so every N tiling of the kernel finds its block as one contiguous piece
+    const int ict = C0 + C1, cb0 = (C0 + kBlockK - 1) / kBlockK, cb1 = C1 > 0 ? (C1 + kBlockK - 1) / kBlockK : 0;
+    const int n_pad = (OC + 63) / 64 * 64;
+    out.assign((size_t)(cb0 + cb1) * 9 * n_pad * 128, 0);
+    uint16_t * dst = reinterpret_cast<uint16_t *>(out.data());
+    for (int cb = 0; cb < cb0 + cb1; cb++) {
+        const int src = cb >= cb0, cbl = src ? cb - cb0 : cb, cs = src ? C1 : C0, coff = src ? C0 : 0;
+        for (int kw = 0; kw < 3; kw++)
+            for (int kh = 0; kh < 3; kh++) {
+                uint16_t * blk = dst + (size_t)((cb * 3 + kw) * 3 + kh) * n_pad * 64;
+                for (int r = 0; r < OC; r++)
+                    for (int c = 0; c < 8; c++)
+                        for (int e = 0; e < 8; e++) {
+                            const int k = cbl * kBlockK + c * 8 + e;
+                            if (k < cs) blk[(size_t)r * 64 + (size_t)((c ^ (r & 7)) * 8 + e)] = Wt[(((size_t)r * 3 + kh) * 3 + kw) * ict + coff + k];
+                        }
+            }
+    }
+    return out.size();
+}
+
 bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x1, int C1, int Nimg, int H, int W,
-                     const __half * Wt, int OC, const GemmEpilogue & ep) {
+                     const __half * Wt, int OC, const GemmEpilogue & ep, const uint8_t * Wt_halo) {
     if (Nimg <= 0 || H <= 0 || W <= 0 || OC % 8 || C0 % 8 || C1 % 8 || C0 <= 0) return false;
     if (W > 128 || ep.res32 || ep.res16 || ep.stats_out || ep.ln_stats) return false;
     // An M tile is a whole number of image rows (or of whole images when an image has fewer than 128 pixels) that divides the
@@ -676,6 +777,9 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
         while (box_n > 1 && Nimg % box_n) box_n--;
         rows_per_tile = 0;
     }
+    // halo mode: one image (or part of one) per tile, map rows of a multiple of 8 pixels (a kh shift must be a whole swizzle atom)
+    const bool halo = Wt_halo != nullptr && W % 8 == 0 && W <= 64 && H * W >= 64 && getenv("GGML_B200_CONV_NO_HALO") == nullptr;
+    if (halo && H * W <= 128) box_n = 1;
     const int tile_m = box_n * box_h * W;
     L = GemmLaunch();
     GemmLaunch::Params & p = L.p;
@@ -689,10 +793,43 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
     p.kb_elems = kBlockK;
     p.ep     = ep;
     choose_tiling(L, OC);
+    const int n_pad = (OC + 63) / 64 * 64;
+    // Measured (profiles/README.md, round 2): the halo scheme moves 30 % fewer bytes but runs one CTA per SM, and at large batches the
+    // two-CTA per-tap scheme keeps more loads in flight (conv 96->96 at 32x32, batch 256: 95 us per-tap vs 113 us halo).  On small
+    // grids (fewer tiles than SMs: the 16x16 / 8x8 stages at batch <= 32, batch-1 latency) the chain of 27-45 dependent k-blocks is what
+    // costs, and the halo scheme is 15-25 % faster -- so it is used there.  GGML_B200_CONV_HALO=1 forces it everywhere.
+    const bool halo_ok = (p.M / tile_m) * p.n_tiles <= runtime().sm_count || getenv("GGML_B200_CONV_HALO") != nullptr;
+    if (halo && halo_ok && p.n_tiles * p.block_n <= n_pad) {
+        // one CTA per SM; shared memory = activation ring (slots of 2W + 128 rows: the MMA of tap kh reads 128 rows from row kh * W)
+        // + weight ring + control + epilogue staging
+        p.conv         = 2;
+        p.w_halo       = Wt_halo;
+        p.n_pad        = n_pad;
+        p.a_slot_bytes = (2 * W + 128) * 128;
+        const int wb_bytes = p.block_n * 128;
+        const int staging  = 2 * ((ep.out16 ? kBlockM * 128 : 0) + (ep.out32 ? 2 * kBlockM * 128 : 0));
+        const int budget   = 216 * 1024 - 1024 - kCtrlBytes - staging;
+        int sa = 3, sb = (budget - sa * p.a_slot_bytes) / wb_bytes;
+        if (sb > kMaxStage) sb = kMaxStage;
+        if (sb > 6) {  // room to spare: a fourth activation slot
+            const int sb4 = (budget - 4 * p.a_slot_bytes) / wb_bytes;
+            if (sb4 >= 6) { sa = 4; sb = sb4 > kMaxStage ? kMaxStage : sb4; }
+        }
+        if (sb >= 3) {
+            p.stages      = sa;
+            p.b_stages    = sb;
+            p.ring_bytes  = sa * p.a_slot_bytes + sb * wb_bytes;
+            L.ctas_per_sm = 1;
+            L.smem_bytes  = 1024 + (size_t)p.ring_bytes + kCtrlBytes + staging;
+        } else {
+            p.conv = 1;
+        }
+    }
+    const int box_rows = p.conv == 2 ? box_h + 2 : box_h;
     auto act_map = [&](CUtensorMap * map, const __half * x, int C) {
         const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         const uint64_t str[3]  = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-        const uint32_t box[4]  = {(uint32_t)kBlockK, (uint32_t)W, (uint32_t)box_h, (uint32_t)box_n};
+        const uint32_t box[4]  = {(uint32_t)kBlockK, (uint32_t)W, (uint32_t)box_rows, (uint32_t)box_n};
         make_map(map, x, 4, dims, str, box);
     };
     act_map(&L.map_a0, x0, C0);

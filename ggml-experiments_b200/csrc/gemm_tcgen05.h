@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 namespace b200 {
 
@@ -49,7 +50,12 @@ struct GemmLaunch {
         const __half * a_ptr;       // cp.async mode: A base pointer and leading dimension
         int lda;
         int ep_warp;                // 1: every epilogue warp stages and TMA-stores its own 32 rows (no residual slab to share)
-        int conv;                   // 0: plain GEMM, 1: 3x3 stride-1 pad-1 implicit GEMM over NHWC
+        int conv;                   // 0: plain GEMM, 1: 3x3 stride-1 pad-1 implicit GEMM over NHWC (one TMA box per tap), 2: the same with halo
+                                    //    boxes (one box per kw, the three kh taps are descriptor offsets into it) and pre-tiled weights
+        int ring_bytes;             // bytes of the operand ring(s) in shared memory (the barriers follow)
+        int a_slot_bytes, b_stages; // conv == 2: activation slot size, depth of the weight ring (`stages` = depth of the activation ring)
+        int n_pad;                  // conv == 2: rows of one (channel block, tap) weight block in the halo layout (OC padded to 64)
+        const uint8_t * w_halo;     // conv == 2: weights as [channel block][kw][kh][n_pad rows x 64 ch], 128B-swizzled (conv3x3_pack_halo)
         int tile_m;                 // output rows (pixels) per M tile: 128, or less when a conv tile is a whole number of image rows
         int a_tx_bytes;             // conv: bytes one activation box delivers (tile_m * 128)
         int H, W, rows_per_tile;    // conv: image rows covered by one 128-pixel tile (0 if a tile spans whole images)
@@ -69,8 +75,12 @@ bool gemm_prepare(GemmLaunch & L, const __half * A, int lda, const __half * B, i
 //   out[(n,y,x), oc] = sum_{kh,kw,ic} in[n, y+kh-1, x+kw-1, ic] * Wt[oc, kh, kw, ic]
 // The input channels may come from two tensors (x0: C0 channels, x1: C1 channels) = a fused ggml_concat.
 // Wt is [OC][3][3][C0+C1] f16.  Returns false if the shape cannot be tiled (W must divide 128 or 128 | W*k).
+// Wt_halo (optional): the same weights in the halo layout (conv3x3_pack_halo); when given and the map qualifies (W % 8 == 0, W <= 64)
+// the kernel runs in halo mode: 3 activation boxes per 64-channel block instead of 9, weights by 1-D bulk copies.
 bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x1, int C1, int Nimg, int H, int W,
-                     const __half * Wt, int OC, const GemmEpilogue & ep);
+                     const __half * Wt, int OC, const GemmEpilogue & ep, const uint8_t * Wt_halo = nullptr);
+// host: Wt [OC][3][3][C0+C1] f16 bits -> halo layout; returns the bytes written to `out` (resized)
+size_t conv3x3_pack_halo(const uint16_t * Wt, int OC, int C0, int C1, std::vector<uint8_t> & out);
 
 void gemm_launch(const GemmLaunch & L, cudaStream_t st);
 

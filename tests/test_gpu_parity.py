@@ -68,7 +68,9 @@ def test_gemm_tcgen05_matches_numpy(G, M, N, K):
                                                   # widths that do not divide 128: a tile is a whole number of image rows / images
                                                   (2, 24, 24, 96, 0, 96), (3, 40, 40, 96, 96, 96), (2, 20, 20, 128, 0, 128),
                                                   (4, 10, 10, 160, 160, 160), (5, 12, 12, 64, 0, 64), (3, 6, 6, 80, 0, 80),
-                                                  (1, 28, 56, 48, 0, 48), (7, 5, 5, 32, 0, 40)])
+                                                  (1, 28, 56, 48, 0, 48), (7, 5, 5, 32, 0, 40),
+                                                  # halo mode with several tiles per CTA / a single image (N split into 64-column tiles)
+                                                  (40, 32, 32, 96, 0, 96), (1, 8, 8, 160, 160, 160), (2, 16, 24, 64, 0, 72)])
 def test_conv3x3_tcgen05_matches_numpy(G, n_img, H, Wd, C0, C1, OC):
     L = G.lib_ggml()
     rng = np.random.default_rng(H * 31 + C0 + OC)
