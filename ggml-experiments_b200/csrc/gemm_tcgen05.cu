@@ -12,7 +12,7 @@
 //   (tcgen05.ld -> BN scale/shift or bias -> SiLU -> residual -> vectorised stores);
 // * smem ring of `stages` x (A 128x64 + B block_n x 64) f16 tiles in the 128-byte swizzled K-major layout
 //   shared by TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA shared-memory descriptors;
-// * the 3x3 convolution walks K as (tap, source, 64-channel block): each step is one 4-D TMA box
+// * the 3x3 convolution walks K as (source, 64-channel block, kw, kh): each step is one 4-D TMA box
 //   {64 ch, W, rows, images} shifted by the tap offset, with the hardware zero-filling the halo, so no
 //   im2col buffer ever exists; a second source tensor map implements ggml_concat (main.cpp:1219) for free.
 //
@@ -232,10 +232,12 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         if (!p.b_resident) tma_load_2d_ws(sb, &map_b, kb * p.kb_elems, n0, fb);
                     } else {
                         mbar_expect_tx_ws(fb, (uint32_t)(p.a_tx_bytes + b_bytes));  // the activation box may be shorter than 128 rows
-                        const int tap = kb / cblk_tot, r = kb % cblk_tot;
+                        // K order = (channel block, kw, kh): the same accumulation order as the halo scheme, so that a tile gives the same
+                        // bits whichever of the two schemes (chosen by grid size) computes it
+                        const int r = kb / 9, t9 = kb % 9;
                         const int src = r >= p.cblk0;
                         const int cb  = src ? r - p.cblk0 : r;
-                        const int kh = tap / 3, kw = tap % 3;
+                        const int kw = t9 / 3, kh = t9 % 3, tap = kh * 3 + kw;
                         if (src) tma_load_4d_ws(sa, &map_a1, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
                         else tma_load_4d_ws(sa, &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
                         tma_load_3d_ws(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         rem = p.K - kb * p.kb_elems;
                         if (rem > p.kb_elems) rem = p.kb_elems;
                     } else {
-                        const int r   = kb % cblk_tot;
+                        const int r   = kb / 9;
                         const int src = r >= p.cblk0;
                         rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
                     }
