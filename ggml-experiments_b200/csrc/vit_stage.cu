@@ -53,7 +53,7 @@ constexpr int kThreads = 192;    // warps 0-3: token rows, warp 4: weight stream
 
 enum {
     B_FULL = 0, B_EMPTY = 3, B_A_READY = 6, B_QKV_DONE, B_QKV_DRAINED, B_S_DONE, B_S_LOADED, B_P_READY, B_O_DONE, B_OS_READY, B_PROJ_DONE,
-    B_U_DONE, B_H_READY = B_U_DONE + 2, B_DOWN_DONE = B_H_READY + 2, B_VEC_FULL = B_DOWN_DONE + 2, B_VEC_FREE, B_COUNT
+    B_U_DONE, B_H_READY = B_U_DONE + 2, B_DOWN_DONE = B_H_READY + 2, B_VEC_FULL = B_DOWN_DONE + 2, B_VEC_FREE, B_XLOAD, B_COUNT
 };
 
 __device__ __forceinline__ uint32_t vs_idesc(int n, int b_mn_major) {
@@ -110,6 +110,13 @@ __device__ __forceinline__ void tst32(uint32_t taddr, const float * v) {
           "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+// per-thread 1-D bulk copies (one token row each): global -> shared with mbarrier completion, shared -> global as a bulk group
+__device__ __forceinline__ void bulk_load_row(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store_row(void * dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tst_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int DP>
@@ -127,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; i++) {
+            if (i == B_XLOAD) { mbar_init(bar(i), 128u); continue; }  // one arrive (+ its row's bytes) per token thread
             const bool from_rows = i == B_A_READY || i == B_QKV_DRAINED || i == B_S_LOADED || i == B_P_READY || i == B_OS_READY || i == B_H_READY || i == B_H_READY + 1 ||
                                    i == B_VEC_FREE;
             mbar_init(bar(i), from_rows ? 4u : 1u);  // one arrive per token warp / one TMA transaction or tcgen05.commit
@@ -206,9 +214,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
         };
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             for (int l = 0; l < p.n_layers; l++) {
-                wait(B_A_READY);
-                gemm_from_a(tW0, 3 * DP);
-                umma_commit_ws(bar(B_QKV_DONE));
+                if (heads > 0) {  // (heads == 0: MLP-only launch, see vit_stage_prepare)
+                    wait(B_A_READY);
+                    gemm_from_a(tW0, 3 * DP);
+                    umma_commit_ws(bar(B_QKV_DONE));
+                }
                 for (int h = 0; h < heads; h++) {
                     wait(B_QKV_DRAINED);
                     {   // S = Q_h . K_h^T
@@ -361,32 +371,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             // token of this row: sequence g = (image, patch position), index j inside it -> pixel (main.cpp:721-747 as index arithmetic)
             const int  g     = tile * seq_per_tile + row / p.L, j = row % p.L;
-            const bool valid = g < p.n_seq;
+            bool       valid = g < p.n_seq;
             size_t     pix   = 0;
-            if (valid) {
+            if (heads == 0) {  // MLP only: tokens are independent, a tile is 128 consecutive pixels
+                pix   = (size_t)tile * 128 + (size_t)row;
+                valid = pix < (size_t)p.total_rows;
+                if (!valid) pix = 0;
+            } else if (valid) {
                 const int n = g >> 2, pos = g & 3, ty = j / p.w2, tx = j % p.w2;
                 pix = ((size_t)n * p.H + (size_t)(2 * ty + (pos >> 1))) * p.W + (size_t)(2 * tx + (pos & 1));
             }
-            {   // X <- x32 row, 64 columns (sixteen independent 16-byte loads) at a time
+            // Staging rows in the (idle) A-tile / attention scratch: every thread moves ITS token row with one bulk copy, so all 128 rows
+            // of the tile are in flight at once (per-thread 16-byte loads cost a DRAM round trip per 64 columns: 7.7 k cycles per tile).
+            // Row pitch C*4 + 16 bytes: one-row-per-thread LDS.128 / STS.128 are conflict-free.
+            const uint32_t srow = sRA + (uint32_t)row * ((uint32_t)C * 4u + 16u);
+            {   // X <- x32 row
                 const float * xr = p.x32 + pix * (size_t)C;
+                if (p.stage_ok) {
+                    fence_proxy_async();  // the area was last written through the generic proxy (A tiles / staged outputs)
+                    if (valid) {
+                        mbar_expect_tx(bar(B_XLOAD), (uint32_t)C * 4u);
+                        bulk_load_row(srow, xr, (uint32_t)C * 4u, bar(B_XLOAD));
+                    } else {
+                        mbar_arrive(bar(B_XLOAD));
+                    }
+                    wait(B_XLOAD);
+                }
                 for (int kb = 0; kb < num_kb; kb++) {
                     float v[64];
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
                         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid && kb * 64 + q * 4 < C) t = __ldg(reinterpret_cast<const float4 *>(xr + kb * 64) + q);
+                        if (valid && kb * 64 + q * 4 < C) {
+                            if (p.stage_ok) t = ld_shared_f4(srow + (uint32_t)(kb * 64 + q * 4) * 4u);
+                            else t = __ldg(reinterpret_cast<const float4 *>(xr + kb * 64) + q);
+                        }
                         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                     }
                     tst32(tX + lsel + (uint32_t)(kb * 64), v);
                     tst32(tX + lsel + (uint32_t)(kb * 64 + 32), v + 32);
                 }
                 tst_wait();
+                if (p.stage_ok) named_bar_sync(1, 128);  // every row has left the staging area: the A tile may be written over it
             }
             VT_SEC(7);
             for (int l = 0; l < p.n_layers; l++) {
                 wait(B_VEC_FULL);
-                layer_norm(l > 0 ? vPend : 0u);
-                arrive(B_A_READY, true);
+                if (heads > 0) {
+                    layer_norm(l > 0 ? vPend : 0u);
+                    arrive(B_A_READY, true);
+                }
                 VT_SEC(0);
                 for (int h = 0; h < heads; h++) {
                     // ---- [q|k|v]_h + bias -> f16 rows of Q, K, V ----
@@ -488,8 +522,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
                     arrive(B_OS_READY, true);
                     VT_SEC(3);
                 }
-                wait(B_PROJ_DONE);  // every head's projection has accumulated into X; all earlier MMAs (they read R_A and R_B) are complete
-                layer_norm(vBo);
+                if (heads > 0) {
+                    wait(B_PROJ_DONE);  // every head's projection has accumulated into X; all earlier MMAs (they read R_A and R_B) are complete
+                    layer_norm(vBo);
+                } else {
+                    layer_norm(l > 0 ? vPend : 0u);
+                }
                 arrive(B_A_READY, true);
                 VT_SEC(4);
                 // ---- hidden layer: chunk j of U + b1 -> SiLU -> f16 rows ----
@@ -543,17 +581,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
                             st_sum += y[k];
                             st_sq = fmaf(y[k], y[k], st_sq);
                         }
+                        // one of the outputs (f32 if there is one, else f16) leaves through the row's staging slot and ONE bulk store
                         if (p.out32) {
-                            float4 * o = reinterpret_cast<float4 *>(p.out32 + pix * (size_t)C + c);
-                            o[0] = make_float4(y[0], y[1], y[2], y[3]);
-                            o[1] = make_float4(y[4], y[5], y[6], y[7]);
+                            if (p.stage_ok) {
+                                st_shared_v4(srow + (uint32_t)c * 4u, __float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
+                                st_shared_v4(srow + (uint32_t)c * 4u + 16u, __float_as_uint(y[4]), __float_as_uint(y[5]), __float_as_uint(y[6]), __float_as_uint(y[7]));
+                            } else {
+                                float4 * o = reinterpret_cast<float4 *>(p.out32 + pix * (size_t)C + c);
+                                o[0] = make_float4(y[0], y[1], y[2], y[3]);
+                                o[1] = make_float4(y[4], y[5], y[6], y[7]);
+                            }
                         }
                         if (p.out16) {
                             uint4 o;
                             o.x = pk2(y[0], y[1]); o.y = pk2(y[2], y[3]); o.z = pk2(y[4], y[5]); o.w = pk2(y[6], y[7]);
-                            *reinterpret_cast<uint4 *>(p.out16 + pix * (size_t)C + c) = o;
+                            if (p.stage_ok && !p.out32) st_shared_v4(srow + (uint32_t)c * 2u, o.x, o.y, o.z, o.w);
+                            else *reinterpret_cast<uint4 *>(p.out16 + pix * (size_t)C + c) = o;
                         }
                     }
+                }
+                if (p.stage_ok) {
+                    fence_proxy_async();  // staged row (generic proxy) -> visible to the bulk-copy engine
+                    if (valid) {
+                        if (p.out32) bulk_store_row(p.out32 + pix * (size_t)C, srow, (uint32_t)C * 4u);
+                        else if (p.out16) bulk_store_row(p.out16 + pix * (size_t)C, srow, (uint32_t)C * 2u);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read();  // the slot is free again (the next tile loads into it); the global write completes by grid end
                 }
                 if (valid && p.stats) *reinterpret_cast<float2 *>(p.stats + 2 * pix) = make_float2(st_sum, st_sq);
                 arrive(B_VEC_FREE, false);
@@ -585,15 +639,15 @@ struct Geo {
 };
 Geo geometry(int H, int W, int C, int heads, int F) {
     Geo g;
-    g.d      = C / heads;
-    g.dp     = attention_padded_head_dim(g.d);
+    g.d      = heads ? C / heads : 0;
+    g.dp     = heads ? attention_padded_head_dim(g.d) : 16;
     g.num_kb = ceil_div(C, 64);
     g.NP     = ceil_div(C, 16) * 16;
     g.nch    = ceil_div(F, 128);
     g.L      = (H / 2) * (W / 2);
     g.ck     = g.num_kb * 64;
     auto nj = [&](int j) { return std::min(128, F - 128 * j); };
-    for (int kb = 0; kb < g.num_kb; kb++) g.rows.push_back(3 * g.dp);
+    for (int kb = 0; heads > 0 && kb < g.num_kb; kb++) g.rows.push_back(3 * g.dp);
     for (int h = 0; h < heads; h++) {
         if (h + 1 < heads)
             for (int kb = 0; kb < g.num_kb; kb++) g.rows.push_back(3 * g.dp);
@@ -612,6 +666,10 @@ Geo geometry(int H, int W, int C, int heads, int F) {
 }  // namespace
 
 bool vit_stage_supported(int N, int H, int W, int C, int heads, int F) {
+    if (heads == 0) {  // MLP-only launch (LN -> up + SiLU -> down + residual): per-token work, any map
+        if (N <= 0 || H <= 0 || W <= 0 || C % 8 || C > 256 || F % 16 || F <= 0) return false;
+        return (int)geometry(H, W, C, 0, F).rows.size() <= 64;
+    }
     if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || heads <= 0 || heads > 8 || C % heads || C % 8 || C > 256 || F % 16 || F <= 0) return false;
     const int L = (H / 2) * (W / 2), d = C / heads;
     if (L > 64 || (L & (L - 1))) return false;  // whole sequences per 128-token tile; the softmax paths cover L = 64 and L <= 32
@@ -658,7 +716,7 @@ void vit_stage_pack(const VitLayerHost * layers, int n_layers, int C, int heads,
                     return kk < C ? w.w1[(size_t)kk * F + (128 * j + r)] * w.ln2_g[kk] : 0.f;
                 });
         };
-        qkv(0);
+        if (heads > 0) qkv(0);
         for (int h = 0; h < heads; h++) {
             if (h + 1 < heads) qkv(h + 1);
             block(NP, [&](int r, int k) -> float { return (r < C && k < d) ? w.wo[(size_t)(h * d + k) * C + r] : 0.f; });
@@ -676,7 +734,7 @@ void vit_stage_pack(const VitLayerHost * layers, int n_layers, int C, int heads,
         }
         float * v = vec.data() + (size_t)stride * l;
         for (int c = 0; c < C; c++) {
-            v[o_bo + c]            = w.bo[c];
+            if (heads > 0) v[o_bo + c] = w.bo[c];
             v[stride + o_pend + c] = w.b2[c];  // pending bias of the NEXT block
         }
         for (int f = 0; f < F; f++) {
@@ -705,6 +763,12 @@ bool vit_stage_prepare(VitStageLaunch & L, const float * x32, int N, int H, int 
     p.N = N; p.H = H; p.W = W; p.C = C; p.heads = heads; p.d = g.d; p.F = F; p.L = g.L; p.n_layers = n_layers;
     p.n_seq  = 4 * N;
     p.tiles  = ceil_div(p.n_seq * g.L, 128);
+    p.total_rows = N * H * W;
+    p.stage_ok   = (128 * (C * 4 + 16) <= g.num_kb * 16384 + kRB && getenv("GGML_B200_VIT_NO_STAGE") == nullptr) ? 1 : 0;
+    if (heads == 0) {  // MLP only: 128 consecutive pixels per tile
+        p.L     = 128;
+        p.tiles = ceil_div(p.total_rows, 128);
+    }
     p.num_kb = g.num_kb; p.NP = g.NP; p.nch = g.nch; p.w2 = W / 2;
     p.n_blk  = (int)g.rows.size();
     size_t layer_bytes = 0;

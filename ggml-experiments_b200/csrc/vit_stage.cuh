@@ -18,7 +18,7 @@ struct VitLayerHost {
 struct VitStageLaunch {
     struct Params {
         int N, H, W, C, heads, d, F, L, n_layers;
-        int n_seq, tiles, num_kb, NP, nch, w2;
+        int n_seq, tiles, num_kb, NP, nch, w2, total_rows, stage_ok;
         int n_blk;                 // weight blocks per layer
         uint16_t blk_rows[64];     // their heights (rows of 128 B) in streaming order
         int   slot_bytes, ra_bytes;
@@ -37,7 +37,10 @@ struct VitStageLaunch {
     size_t smem_bytes;
 };
 
-// whether the fused kernel covers a stage of this shape (sequence length a power of two <= 64, C <= 256, head dim <= 64, ...)
+// whether the fused kernel covers a stage of this shape (sequence length a power of two <= 64, C <= 256, head dim <= 64, ...).
+// heads == 0 everywhere below selects the MLP-ONLY variant: LN -> up-projection + SiLU -> down-projection + residual of ONE layer (the second
+// half of transformer_layer::forward, main.cpp:1113-1165) for stages whose sequences do not fit a tile (L = 256 / 1024); only ln2 / w1 / b1 /
+// w2 / b2 of VitLayerHost are read.
 bool vit_stage_supported(int N, int H, int W, int C, int heads, int F);
 // constant folding (plan time, host): all layers' weights tiled into the kernel's streaming order
 void vit_stage_pack(const VitLayerHost * layers, int n_layers, int C, int heads, int F, std::vector<uint8_t> & blob, std::vector<float> & vec);

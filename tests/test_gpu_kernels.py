@@ -320,3 +320,30 @@ def test_vit_stage_fused_vs_float64(L, n, h, w, c, heads, f, nl):
     assert np.abs(out16.astype(np.float32) - out32).max() <= np.abs(out32).max() * 2.0 ** -10
     assert np.allclose(stats[..., 0], out32.sum(-1), rtol=1e-4, atol=1e-3 * rms * c ** 0.5)
     assert np.allclose(stats[..., 1], (out32.astype(np.float64) ** 2).sum(-1), rtol=1e-4)
+
+
+@pytest.mark.parametrize("n,h,w,c,f", [(3, 32, 32, 144, 288), (1, 32, 32, 96, 192), (2, 64, 64, 144, 288), (1, 6, 10, 64, 128), (40, 32, 32, 144, 288),
+                                       (2, 16, 16, 240, 480)])
+def test_vit_mlp_only_fused_vs_float64(L, n, h, w, c, f):
+    """k_vit_stage with heads = 0: x + W2.silu(W1.LN(x) + b1) + b2 per token (the MLP half of transformer_layer::forward, main.cpp:1113-1165)
+    for stages whose sequences do not fit a 128-token tile; any map size, tiles are 128 consecutive pixels."""
+    vpp = ctypes.POINTER(f32p)
+    L.ggml_b200_debug_vit_stage.argtypes = [f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_float, vpp, f32p, u16p, f32p, ctypes.c_int, f32p]
+    rng = np.random.default_rng(n * 77 + c)
+    x = rng.standard_normal((n, h, w, c)).astype(np.float32) + rng.standard_normal((n, h, w, 1)).astype(np.float32) * 3.0
+    p = _vit_params(rng, c, f, 1)[0]
+    arr = (f32p * 16)(*[_p(a, f32p) for a in p])
+    out32 = np.zeros((n, h, w, c), np.float32)
+    stats = np.zeros((n, h, w, 2), np.float32)
+    rc = L.ggml_b200_debug_vit_stage(_p(x, f32p), n, h, w, c, 0, f, 1, 1e-5, arr, _p(out32, f32p), None, _p(stats, f32p), 0, None)
+    assert rc == 0
+    g2, b2, w1, bf1, w2, bf2 = [a.astype(np.float64) for a in p[10:16]]
+    t = x.astype(np.float64)
+    mu = t.mean(-1, keepdims=True)
+    y = (t - mu) / np.sqrt(((t - mu) ** 2).mean(-1, keepdims=True) + 1e-5) * g2 + b2
+    ref = t + _silu(y @ w1 + bf1) @ w2 + bf2
+    rel = float(np.sqrt(((out32 - ref) ** 2).sum() / (ref ** 2).sum()))
+    print(f"vit_mlp n={n} {h}x{w} C={c} F={f}: rel-L2 {rel:.2e}, max-abs {np.abs(out32 - ref).max():.2e}")
+    assert np.isfinite(out32).all() and rel < 2e-3
+    assert np.allclose(stats[..., 0], out32.sum(-1), rtol=1e-4, atol=1e-2)
