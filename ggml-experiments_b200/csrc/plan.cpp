@@ -285,8 +285,11 @@ Plan * get_or_build_plan(ggml_context * ctx, ggml_cgraph * gf) {
     bool fast_ok = false;
     if (runtime().mode == GGML_B200_MODE_FAST) {
         fast_ok = build_fast_plan(plan, gf);
-        if (!fast_ok && runtime().verbose)
-            fprintf(stderr, "libggml_b200: graph not recognised by the fused planner; using the per-node exact plan (still on device)\n");
+        // a MobileViT-sized graph that misses the fused plan runs ~100x slower: say so once per plan (small graphs -- the GRU cell, unit
+        // tests -- are expected to take the per-node plan and stay quiet unless GGML_B200_VERBOSE is set)
+        if (!fast_ok && (runtime().verbose || gf->n_nodes > 256))
+            fprintf(stderr, "libggml_b200: graph (%d nodes) not recognised by the fused planner; using the per-node exact plan (still on the device, much slower). "
+                            "GGML_B200_VERBOSE=1 names the pattern that failed.\n", gf->n_nodes);
     }
     if (!fast_ok) build_exact_plan(plan, gf);
     plan->mode = fast_ok ? GGML_B200_MODE_FAST : (runtime().mode == GGML_B200_MODE_EXACT_F32 ? GGML_B200_MODE_EXACT_F32 : GGML_B200_MODE_EXACT);

@@ -12,7 +12,7 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 $CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none -k regex:"k_gemm_tcgen05|k_dwconv|k_attention|k_layernorm|k_stem" -c 60 -o /tmp/step_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1 && \
+ncu --set full --clock-control none -k regex:"k_gemm_tcgen05|k_dwconv|k_attention|k_layernorm|k_stem|k_vit_stage" -c 60 -o /tmp/step_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1 && \
 ncu -i /tmp/step_$TAG.ncu-rep --page raw --csv > gpurun_out/metrics_$TAG.csv 2>/dev/null
 $CMD > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"${2:-k_gemm_tcgen05}" -s 2 -c 3 -o gpurun_out/top_$TAG $CMD >> gpurun_out/ncu_full_$TAG.log 2>&1
