@@ -323,7 +323,8 @@ ggml_tensor * model::build_forward(ggml_context * ctx, ggml_tensor * images_hwc,
 // Concurrent lanes (MVIT_LANES=S, default 1): a request of n images runs as S sub-batches on S streams at the same time.  Built to
 // attack the launch-latency chain at small per-GPU batches (strong scaling: 32 images per GPU at 8 GPUs).  Per-image results do not
 // depend on the batch they are computed in (bit for bit: the batch-independence tests), so a split changes nothing but the time --
-// and measured on B200 it does not help: 32 images take 1.18 / 1.22 / 1.43 ms as 1 / 2 / 4 lanes (64: 1.77 / 1.80 / 2.05).  The
+// and measured on B200 it does not help: 32 images take 1.18 / 1.22 / 1.43 ms as 1 / 2 / 4 lanes (64: 1.77 / 1.80 / 2.05); with the
+// fused transformer stages of round 2 (49 launches): 1.00 / 1.06 / 1.25 ms (64: 1.56 / 1.58 / 1.90), tests/lanes_probe.sh.  The
 // persistent kernels of one lane already occupy every SM's shared memory and TMEM, so the lanes time-share the SMs instead of filling
 // each other's gaps.  Kept as an option (and tested); off by default.
 static int choose_lanes(int n, int h, int w) {
