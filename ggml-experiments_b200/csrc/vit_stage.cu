@@ -663,12 +663,20 @@ Geo geometry(int H, int W, int C, int heads, int F) {
     return g;
 }
 
+// dynamic shared memory of a launch: alignment slack + A tile + attention / hidden scratch + weight ring + bias block
+size_t smem_need(const Geo & g, int heads) {
+    int max_rows = 128;
+    for (int r : g.rows) max_rows = std::max(max_rows, r);
+    return 1024 + (size_t)g.num_kb * 16384 + kRB + (size_t)kSlots * max_rows * 128 + (size_t)(512 + heads * 3 * g.dp + g.nch * 128) * 4;
+}
+
 }  // namespace
 
 bool vit_stage_supported(int N, int H, int W, int C, int heads, int F) {
     if (heads == 0) {  // MLP-only launch (LN -> up + SiLU -> down + residual): per-token work, any map
         if (N <= 0 || H <= 0 || W <= 0 || C % 8 || C > 256 || F % 16 || F <= 0) return false;
-        return (int)geometry(H, W, C, 0, F).rows.size() <= 64;
+        const Geo g0 = geometry(H, W, C, 0, F);
+        return (int)g0.rows.size() <= 64 && smem_need(g0, 0) + 512 <= 227 * 1024;
     }
     if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || heads <= 0 || heads > 8 || C % heads || C % 8 || C > 256 || F % 16 || F <= 0) return false;
     const int L = (H / 2) * (W / 2), d = C / heads;
@@ -676,7 +684,7 @@ bool vit_stage_supported(int N, int H, int W, int C, int heads, int F) {
     if (d > 64 || (d & 1)) return false;
     const Geo g = geometry(H, W, C, heads, F);
     if ((int)g.rows.size() > 64) return false;
-    return true;
+    return smem_need(g, heads) + 512 <= 227 * 1024;  // + the kernel's static shared memory (barriers)
 }
 
 void vit_stage_pack(const VitLayerHost * layers, int n_layers, int C, int heads, int F, std::vector<uint8_t> & blob, std::vector<float> & vec) {
