@@ -262,9 +262,13 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_free);  // S is in registers: the tensor core may overwrite it with the next S
                 AT_TICK(1);
-                float mx4[4] = {v[0], v[1], v[2], v[3]};  // four independent chains instead of one of 63 dependent FMNMX
+                float mx4[4] = {v[0], v[1], v[2], v[3]};  // four independent chains of three-input maxima (FMNMX3) instead of 63 dependent FMNMX
 #pragma unroll
-                for (int c = 4; c < 64; c++) mx4[c & 3] = fmaxf(mx4[c & 3], v[c]);
+                for (int c = 4; c < 60; c += 8)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) mx4[i] = fmax3(mx4[i], v[c + i], v[c + 4 + i]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) mx4[i] = fmaxf(mx4[i], v[60 + i]);
                 const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
                 // the previous P.V has finished: P may be overwritten and O may be rescaled
                 AT_TICK(2);
@@ -322,10 +326,12 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
             decode(k, n, pos, h, qb);
             // O/l -> f16, staged in this warp's 32 rows of the (now idle) P tile so that the global stores run along the
             // head's channels: one thread per row would write 4 B to 32 different pixels per instruction.
-            // Row pitch DP/2 + 1 words (conflict-free for one-row-per-thread writes); DP = 64 keeps 32 words and rotates.
-            constexpr int kPitch = DP / 2 + (DP == 64 ? 0 : 1);
+            // Row pitch DP/2 + 2 words: 8-byte aligned rows (read back two words per lane below), two-way conflicts at most on the way in;
+            // DP = 64 keeps dense rows of 32 words, rotated by twice the row index.
+            constexpr int kPitch = DP / 2 + 2;
+            static_assert(32 * (DP / 2 + 2) * 4 <= 4096 || DP == 64, "staging rows of one warp must fit its 4 KiB quarter of the P tile");
             const uint32_t stage = sp + (uint32_t)warp * 4096u;
-            const uint32_t srow  = stage + (uint32_t)lane * (uint32_t)(kPitch * 4);
+            const uint32_t srow  = stage + (uint32_t)lane * (uint32_t)((DP == 64 ? 32 : kPitch) * 4);
 #pragma unroll
             for (int c0 = 0; c0 < DP; c0 += 16) {
                 float v[16];
@@ -333,29 +339,31 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 16; c += 2) {
                     const int w = (c0 + c) >> 1;
-                    st_shared_u32(srow + (uint32_t)((DP == 64 ? ((w + lane) & 31) : w) * 4), pack2(v[c] * inv, v[c + 1] * inv));
+                    st_shared_u32(srow + (uint32_t)((DP == 64 ? ((w + 2 * lane) & 31) : w) * 4), pack2(v[c] * inv, v[c + 1] * inv));
                 }
             }
             tc_fence_before();
             AT_TICK(8);
             __syncwarp();
             AT_TICK(9);
-            // one (or, for short heads, 2 / 4) row(s) per instruction: lanes run along the head's channels of a pixel
-            const int d2 = p.d >> 1;
-            const int wl = d2 > 16 ? 5 : (d2 > 8 ? 4 : 3);  // log2 of the lanes given to one row
-            const int sub = lane >> wl, w = lane & ((1 << wl) - 1), rstep = 32 >> wl;
+            // Global stores: a lane carries 4 channels (8 bytes) of a pixel's head slice, d/4 lanes per row, 32 / (d/4) rows per instruction
+            // (3 rows for d = 36 instead of 1 with 4-byte lanes: the store phase was 20 % of the kernel, profiles/README.md); head dims that
+            // are not a multiple of 4 keep 4-byte lanes
+            const int wpl = (p.d & 3) ? 1 : 2, lp = p.d / (2 * wpl), rstep = 32 / lp, sub = lane / lp, w = lane - sub * lp;
             const int t0 = qb * kQB + warp * 32;
-            if (w < d2) {
-                __half * obase = p.out + h * p.d + 2 * w;
-                const uint32_t sbase = stage + (uint32_t)(w * 4);
-#pragma unroll 4
+            if (sub < rstep) {
+                __half * obase = p.out + h * p.d + 2 * wpl * w;
+#pragma unroll 2
                 for (int r = sub; r < 32; r += rstep) {
                     // token of this row -> pixel: (ty, tx) in the half-resolution lattice of patch position pos (W/2 is a power of two)
                     const int t  = t0 + r;
                     const int ty = t >> p.w2_shift, tx = t & ((1 << p.w2_shift) - 1);
                     const size_t pix = ((size_t)n * p.H + (size_t)(2 * ty + (pos >> 1))) * p.W + (size_t)(2 * tx + (pos & 1));
-                    const uint32_t hv = ld_shared_u32(DP == 64 ? stage + (uint32_t)((r * kPitch + ((w + r) & 31)) * 4) : sbase + (uint32_t)(r * kPitch * 4));
-                    *reinterpret_cast<uint32_t *>(obase + pix * p.C) = hv;
+                    auto word = [&](int i) {  // word i (channels 2i, 2i+1) of staged row r
+                        return ld_shared_u32(stage + (uint32_t)((DP == 64 ? r * 32 + ((i + 2 * r) & 31) : r * kPitch + i) * 4));
+                    };
+                    if (wpl == 2) *reinterpret_cast<uint2 *>(obase + pix * p.C) = make_uint2(word(2 * w), word(2 * w + 1));
+                    else *reinterpret_cast<uint32_t *>(obase + pix * p.C) = word(w);
                 }
             }
             AT_TICK(10);

@@ -450,7 +450,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
                         arrive(B_S_LOADED, false);
                         float mx4[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-                        for (int c = 4; c < 64; c++) mx4[c & 3] = fmaxf(mx4[c & 3], v[c]);
+                        for (int c = 4; c < 60; c += 8)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) mx4[i] = fmax3(mx4[i], v[c + i], v[c + 4 + i]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) mx4[i] = fmaxf(mx4[i], v[60 + i]);
                         const float m = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
                         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
                         const uint32_t own = sP + (uint32_t)kb_own * 16384u + rowb, oth = sP + (uint32_t)(kb_own ^ 1) * 16384u + rowb;
