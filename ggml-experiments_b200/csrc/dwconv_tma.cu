@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
             for (int k = 0; k < 9; k++) w[k] = *reinterpret_cast<const uint4 *>(p.Wt + (size_t)k * p.C + c0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                sc[j] = p.scale ? p.scale[c0 + j] : 1.f;
-                sh[j] = p.shift ? p.shift[c0 + j] : 0.f;
+                const float ah = p.act ? 0.5f : 1.f;  // SiLU works on y/2: folded into scale / shift, exactly (ptx_sm100.cuh silu_h)
+                sc[j] = (p.scale ? p.scale[c0 + j] : 1.f) * ah;
+                sh[j] = (p.shift ? p.shift[c0 + j] : 0.f) * ah;
             }
         }
         mbar_wait(smem_u32(&full_bar[buf]), (it >> 1) & 1u);
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256, 2) k_dwconv_tma(const __grid_constant__ C
                 for (int j = 0; j < 4; j++) {
                     float y0 = fmaf(acc[2 * j], sc[2 * j], sh[2 * j]);
                     float y1 = fmaf(acc[2 * j + 1], sc[2 * j + 1], sh[2 * j + 1]);
-                    if (p.act) { y0 = silu_f(y0); y1 = silu_f(y1); }
+                    if (p.act) { y0 = silu_h(y0); y1 = silu_h(y1); }
                     o.h[j] = __floats2half2_rn(y0, y1);
                 }
                 *reinterpret_cast<H8 *>(op) = o;

@@ -4,6 +4,7 @@
 
 #include "internal.h"
 #include "pdl.cuh"
+#include "ptx_sm100.cuh"
 
 namespace b200 {
 
@@ -141,9 +142,9 @@ __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, 
     __shared__ __align__(16) __half s_out[8][16 * OC];
     __shared__ float ss[OC], sh[OC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    for (int i = threadIdx.x; i < OC; i += blockDim.x) {
-        ss[i] = scale ? scale[i] : 1.f;
-        sh[i] = shift ? shift[i] : 0.f;
+    for (int i = threadIdx.x; i < OC; i += blockDim.x) {  // SiLU works on y/2: folded into scale / shift, exactly
+        ss[i] = (scale ? scale[i] : 1.f) * (act ? 0.5f : 1.f);
+        sh[i] = (shift ? shift[i] : 0.f) * (act ? 0.5f : 1.f);
     }
     // B fragments (weights), constant per thread: bfrag[j][s][h] holds W[oc = 8j+g][k' = 16s + 2t + 8h, +1]
     uint32_t bfrag[NT][2][2];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, 
             const int   oc = 8 * j + 2 * t;
             const float s0 = ss[oc], s1 = ss[oc + 1], h0 = sh[oc], h1 = sh[oc + 1];
             float y0 = fmaf(acc[j][0], s0, h0), y1 = fmaf(acc[j][1], s1, h1), y2 = fmaf(acc[j][2], s0, h0), y3 = fmaf(acc[j][3], s1, h1);
-            if (act) { y0 = silu_fast(y0); y1 = silu_fast(y1); y2 = silu_fast(y2); y3 = silu_fast(y3); }
+            if (act) { y0 = ptx::silu_h(y0); y1 = ptx::silu_h(y1); y2 = ptx::silu_h(y2); y3 = ptx::silu_h(y3); }
             *reinterpret_cast<__half2 *>(so + g * OC + oc)       = __floats2half2_rn(y0, y1);
             *reinterpret_cast<__half2 *>(so + (g + 8) * OC + oc) = __floats2half2_rn(y2, y3);
         }

@@ -119,10 +119,12 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    // SiLU epilogues work on h = y/2 (silu(y) = h + h tanh h): the 1/2 is folded into scale and shift here, exactly (a power of two)
+    const float ah = p.ep.act ? 0.5f : 1.0f;
     for (int i = threadIdx.x; i < p.block_n; i += kThreads) {
         const int n = n0 + i;
-        s_scale[i]  = (p.ep.scale && n < p.N) ? p.ep.scale[n] : 1.0f;
-        s_shift[i]  = (p.ep.shift && n < p.N) ? p.ep.shift[n] : 0.0f;
+        s_scale[i]  = ((p.ep.scale && n < p.N) ? p.ep.scale[n] : 1.0f) * ah;
+        s_shift[i]  = ((p.ep.shift && n < p.N) ? p.ep.shift[n] : 0.0f) * ah;
         s_c1[i]     = (p.ep.ln_c1 && n < p.N) ? p.ep.ln_c1[n] : 0.0f;
     }
     tc_fence_before();
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
                                 float tt = fmaf(v[g * 8 + j], sc[j], sh[j]);
-                                y[j]     = f_act ? silu_f(tt) : tt;
+                                y[j]     = f_act ? silu_h(tt) : tt;  // (scale / shift were halved in the prologue)
                             }
                         }
                         if (f_res32) {

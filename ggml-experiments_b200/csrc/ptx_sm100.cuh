@@ -254,5 +254,18 @@ __device__ __forceinline__ float silu_f(float x) {
 #endif
 }
 
+// The same SiLU given h = x/2 directly: the caller folds the 1/2 into whatever produces the argument (BatchNorm scale / shift, bias,
+// weights) -- exact, a power of two -- and the epilogue saves one multiply per element.
+__device__ __forceinline__ float silu_h(float h) {
+#ifdef GGML_B200_SILU_EXACT
+    const float x = 2.0f * h;
+    return __fdividef(x, 1.0f + __expf(-x));
+#else
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+#endif
+}
+
 }  // namespace ptx
 }  // namespace b200

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
                                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b4.x, b4.y, b4.z, b4.w};
                                 float y[8];
 #pragma unroll
-                                for (int k = 0; k < 8; k++) y[k] = silu_f(v[q * 8 + k] + bb[k]);
+                                for (int k = 0; k < 8; k++) y[k] = silu_h(v[q * 8 + k] + bb[k]);  // weights and bias carry the 1/2 (vit_stage_pack)
                                 st_shared_v4(hs + (uint32_t)(c >> 6) * 16384u + (((uint32_t)q ^ swz) << 4), pk2(y[0], y[1]), pk2(y[2], y[3]), pk2(y[4], y[5]),
                                              pk2(y[6], y[7]));
                             }
@@ -725,7 +725,7 @@ void vit_stage_pack(const VitLayerHost * layers, int n_layers, int C, int heads,
             for (int kb = 0; kb < g.num_kb; kb++)
                 block(nj, [&](int r, int k) -> float {
                     const int kk = kb * 64 + k;
-                    return kk < C ? w.w1[(size_t)kk * F + (128 * j + r)] * w.ln2_g[kk] : 0.f;
+                    return kk < C ? 0.5f * w.w1[(size_t)kk * F + (128 * j + r)] * w.ln2_g[kk] : 0.f;  // 1/2: the SiLU drain works on h = y/2
                 });
         };
         if (heads > 0) qkv(0);
@@ -752,7 +752,7 @@ void vit_stage_pack(const VitLayerHost * layers, int n_layers, int C, int heads,
         for (int f = 0; f < F; f++) {
             double acc = w.b1[f];
             for (int k = 0; k < C; k++) acc += (double)w.ln2_b[k] * (double)w.w1[(size_t)k * F + f];
-            v[o_bf1 + f] = (float)acc;
+            v[o_bf1 + f] = (float)(0.5 * acc);
         }
         const float * ws[3] = {w.wq, w.wk, w.wv};
         const float * bs[3] = {w.bq, w.bk, w.bv};
