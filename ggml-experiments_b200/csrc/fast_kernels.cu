@@ -136,8 +136,10 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 template <int OC>
 __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W,
                                                   const __half * __restrict__ Wt, const float * __restrict__ scale, const float * __restrict__ shift,
-                                                  int act, __half * __restrict__ out16, int tiles_x, int tiles_y) {
+                                                  int act, __half * __restrict__ out16, int tiles_x, int tiles_y,
+                                                  const uint8_t * __restrict__ x8, const int * __restrict__ use_x8) {
     constexpr int TH = 16, TW = 32, IH = 2 * TH + 1, IW = 2 * TW + 1, RS = 200, NT = OC / 8;  // RS: halves per staged row (195 used)
+    __shared__ __half s_lut[256];
     __shared__ __align__(16) __half s_in[(IH + 1) * RS + 8];  // +1 row: the zero-weight K pad (k' = 30, 31) reads input row 2*py + 3
     __shared__ __align__(16) __half s_out[8][16 * OC];
     __shared__ float ss[OC], sh[OC];
@@ -177,20 +179,89 @@ __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, 
     const float * xn = x + n * sn;
     pdl_wait();  // PDL: weights / scale / shift above are constants; the image and the output are not
     pdl_trigger();
-    // stage the (2*TH+2) x (2*TW+1) x 3 patch as f16 (ggml's im2col rounding point); warp = row, lanes = (x, c) pairs
-    for (int yy = warp; yy < IH + 1; yy += 8) {
-        const int  iy     = iy0 + yy;
-        const bool row_ok = iy >= 0 && iy < H && yy < IH;
-        float      v[7];  // all loads of a row are in flight before the first convert/store (the rolled loop exposed one global latency per element)
+    if (use_x8 != nullptr && __ldg(use_x8) != 0) {
+        // u8 source (the quantised image of sam_image_preprocess, main.cpp:592-597, straight into the stem): f16(v / 255) comes
+        // from a 256-entry table built with the reference's own expression, so the staged patch is bit-identical to the f32 route
+        // at a quarter of the bytes.  A row of the patch is 195 bytes starting 3 bytes before a 4-byte boundary (W % 4 == 0, tx0 % 32
+        // == 0): lanes load aligned 32-bit words (51 per row, all of a warp's rows in flight), words are wholly inside or outside
+        // the image row; words 49 and 50 (bytes 195..) are the zero tail of the staged row.
+        s_lut[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
+        __syncthreads();
+        const uint8_t * xn8 = x8 + (int64_t)n * H * W * 3;
+        uint32_t wv[5][2];
 #pragma unroll
-        for (int u = 0; u < 7; u++) {
-            const int i = lane + 32 * u, xx = i / 3, c = i - 3 * xx, ix = ix0 + xx;
-            v[u]        = (row_ok && xx < IW && ix >= 0 && ix < W) ? __ldg(xn + iy * sy + ix * sx + c * sc) : 0.f;
+        for (int r = 0; r < 5; r++) {
+            const int  yy = warp + 8 * r, iy = iy0 + yy;
+            const bool row_ok = yy < IH && iy >= 0 && iy < H;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int w = lane + 32 * u, cb = 6 * tx0 - 4 + 4 * w;  // byte offset of the word inside the image row
+                wv[r][u]    = (row_ok && w < 49 && cb >= 0 && cb < 3 * W) ? __ldg(reinterpret_cast<const uint32_t *>(xn8 + (int64_t)iy * W * 3 + cb)) : 0u;
+            }
         }
 #pragma unroll
-        for (int u = 0; u < 7; u++) {
-            const int i = lane + 32 * u;
-            if (i < RS) s_in[yy * RS + i] = __float2half_rn(v[u]);
+        for (int r = 0; r < 5; r++) {
+            const int yy = warp + 8 * r;
+            if (yy >= IH + 1) continue;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int w = lane + 32 * u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = 4 * w + j - 1;
+                    if (w < 51 && i >= 0 && i < RS) s_in[yy * RS + i] = s_lut[(wv[r][u] >> (8 * j)) & 255u];
+                }
+            }
+        }
+    } else if (sc == 1 && sx == 3 && sy == 3 * (int64_t)W && (W & 3) == 0 && (sn & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        // packed HWC f32 images: the same 51 aligned words per row, 16 bytes each (the scalar loop below spent ~9 instructions per
+        // element on index arithmetic, a convert and a 2-byte store: the kernel was issue-bound at 2.6 TB/s)
+#pragma unroll
+        for (int r0 = 0; r0 < 5; r0 += 3) {  // rows of this warp in two batches (3 + 2): every load of a batch is in flight before its first convert
+            float4 fv[3][2];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int  yy = warp + 8 * (r0 + r), iy = iy0 + yy;
+                const bool row_ok = r0 + r < 5 && yy < IH && iy >= 0 && iy < H;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int w = lane + 32 * u, cf = 6 * tx0 - 4 + 4 * w;  // float offset of the word inside the image row
+                    fv[r][u] = (row_ok && w < 49 && cf >= 0 && cf < 3 * W) ? __ldg(reinterpret_cast<const float4 *>(xn + (int64_t)iy * sy + cf)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int yy = warp + 8 * (r0 + r);
+                if (r0 + r >= 5 || yy >= IH + 1) continue;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int w = lane + 32 * u;
+                    if (w >= 51) continue;
+                    __half * d = s_in + yy * RS + 4 * w;  // elements 4w-1 .. 4w+2
+                    if (w > 0) d[-1] = __float2half_rn(fv[r][u].x);
+                    if (w < 50) {
+                        *reinterpret_cast<__half2 *>(d) = __floats2half2_rn(fv[r][u].y, fv[r][u].z);
+                        d[2] = __float2half_rn(fv[r][u].w);
+                    }
+                }
+            }
+        }
+    } else {
+        // stage the (2*TH+2) x (2*TW+1) x 3 patch as f16 (ggml's im2col rounding point); warp = row, lanes = (x, c) pairs
+        for (int yy = warp; yy < IH + 1; yy += 8) {
+            const int  iy     = iy0 + yy;
+            const bool row_ok = iy >= 0 && iy < H && yy < IH;
+            float      v[7];  // all loads of a row are in flight before the first convert/store (the rolled loop exposed one global latency per element)
+    #pragma unroll
+            for (int u = 0; u < 7; u++) {
+                const int i = lane + 32 * u, xx = i / 3, c = i - 3 * xx, ix = ix0 + xx;
+                v[u]        = (row_ok && xx < IW && ix >= 0 && ix < W) ? __ldg(xn + iy * sy + ix * sx + c * sc) : 0.f;
+            }
+    #pragma unroll
+            for (int u = 0; u < 7; u++) {
+                const int i = lane + 32 * u;
+                if (i < RS) s_in[yy * RS + i] = __float2half_rn(v[u]);
+            }
         }
     }
     __syncthreads();
@@ -233,17 +304,20 @@ __global__ void __launch_bounds__(256) k_stem_mma(const float * __restrict__ x, 
     }
 }
 
+bool stem_takes_u8(int OC, int W, bool hwc, bool out16, bool out32) {
+    static const bool v1 = getenv("GGML_B200_STEM_V1") != nullptr;
+    return !v1 && out16 && !out32 && (OC == 8 || OC == 16 || OC == 24 || OC == 32) && hwc && W % 4 == 0;
+}
 void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W, const __half * Wt, int OC,
-                 const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st) {
+                 const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st, const uint8_t * x8, const int * use_x8) {
     const int tiles_x = (W / 2 + 31) / 32, tiles_y = (H / 2 + 15) / 16;
     const int grid    = N * tiles_x * tiles_y;
-    static const bool v1 = getenv("GGML_B200_STEM_V1") != nullptr;
-    if (!out32 && out16 && !v1) {
+    if (stem_takes_u8(OC, 4, true, out16 != nullptr, out32 != nullptr)) {  // W / layout only matter for the u8 source
         switch (OC) {
-            case 8: launch_pdl(k_stem_mma<8>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
-            case 16: launch_pdl(k_stem_mma<16>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
-            case 24: launch_pdl(k_stem_mma<24>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
-            case 32: launch_pdl(k_stem_mma<32>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y); return;
+            case 8: launch_pdl(k_stem_mma<8>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y, x8, use_x8); return;
+            case 16: launch_pdl(k_stem_mma<16>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y, x8, use_x8); return;
+            case 24: launch_pdl(k_stem_mma<24>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y, x8, use_x8); return;
+            case 32: launch_pdl(k_stem_mma<32>, dim3(grid), dim3(256), 0, st, x, sn, sy, sx, sc, N, H, W, Wt, scale, shift, act, out16, tiles_x, tiles_y, x8, use_x8); return;
             default: break;
         }
     }
@@ -892,15 +966,17 @@ void launch_copy_words(const void * src, void * dst, int64_t n_words, cudaStream
 // One thread per output pixel, all 3 channels.  The arithmetic is the reference's, operation for operation, with explicit
 // round-to-nearest intrinsics so that nvcc cannot contract mul+add into fma: the result is bit-identical to the CPU code.
 __global__ void k_preprocess_u8(const uint8_t * __restrict__ src, int sh, int sw, float * __restrict__ dst, int H, int W, float scale, int nx3, int ny3,
-                                int64_t total) {
+                                int64_t total, uint8_t * __restrict__ dst8) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int     x = (int)(i % W);
     const int     y = (int)((i / W) % H);
     const int64_t n = i / ((int64_t)W * H);
-    float * o = dst + i * 3;
+    float *   o  = dst + i * 3;
+    uint8_t * o8 = dst8 + i * 3;
     if (x >= nx3 || y >= ny3) {
-        o[0] = o[1] = o[2] = 0.f;
+        if (dst8) o8[0] = o8[1] = o8[2] = 0;
+        else o[0] = o[1] = o[2] = 0.f;
         return;
     }
     const float sx = __fsub_rn(__fmul_rn((float)x + 0.5f, scale), 0.5f);
@@ -920,17 +996,18 @@ __global__ void k_preprocess_u8(const uint8_t * __restrict__ src, int sh, int sw
         const float v1 = __fadd_rn(__fmul_rn((float)p10[c], wx0), __fmul_rn((float)p11[c], dx));
         const float v  = __fadd_rn(__fmul_rn(v0, wy0), __fmul_rn(v1, dy));
         const float q  = fminf(fmaxf(roundf(v), 0.0f), 255.0f);
-        o[c]           = __fdiv_rn((float)(uint8_t)q, 255.0f);
+        if (dst8) o8[c] = (uint8_t)q;
+        else o[c] = __fdiv_rn((float)(uint8_t)q, 255.0f);
     }
 }
-void launch_preprocess_u8(const uint8_t * src, int n, int sh, int sw, float * dst, int H, int W, cudaStream_t st) {
+void launch_preprocess_u8(const uint8_t * src, int n, int sh, int sw, float * dst, int H, int W, cudaStream_t st, uint8_t * dst8) {
     // scale as main.cpp:550 for the square target; the general form keeps the whole image inside an H x W target
     const float scale = H == W ? (float)(sw > sh ? sw : sh) * 1.0f / (float)W : fmaxf((float)sw / (float)W, (float)sh / (float)H);
     int nx3 = (int)((float)sw / scale + 0.5f), ny3 = (int)((float)sh / scale + 0.5f);
     if (nx3 > W) nx3 = W;
     if (ny3 > H) ny3 = H;
     const int64_t total = (int64_t)n * H * W;
-    k_preprocess_u8<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, sh, sw, dst, H, W, scale, nx3, ny3, total);
+    k_preprocess_u8<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, sh, sw, dst, H, W, scale, nx3, ny3, total, dst8);
 }
 
 // Classifier head: logits[n][o] = sum_c pooled[n][c] * W[c][o] + bias[o], f32 FFMA.  W is the file's

@@ -12,7 +12,10 @@ namespace b200 {
 // HWC batch input of this build and the CHW input of an unmodified main.cpp work.  Output f16 NHWC.
 // Wt: [OC][3][3][3] f16 (oc, kh, kw, ic).
 void launch_stem(const float * x, int64_t sn, int64_t sy, int64_t sx, int64_t sc, int N, int H, int W, const __half * Wt, int OC,
-                 const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st);
+                 const float * scale, const float * shift, int act, __half * out16, float * out32, cudaStream_t st,
+                 const uint8_t * x8 = nullptr, const int * use_x8 = nullptr);
+// true if launch_stem would run the tensor-core stem, which can also stage its patch from u8 images [N][H][W][3] (x8, when *use_x8 != 0)
+bool stem_takes_u8(int OC, int W, bool hwc, bool out16, bool out32);
 
 // K3: depthwise 3x3 (stride 1 or 2, pad 1) + BN scale/shift + SiLU over NHWC f16.  Wt: [3][3][C] f16.
 void launch_dwconv(const __half * x, int N, int H, int W, int C, int stride, const __half * Wt, const float * scale,
@@ -42,7 +45,8 @@ void launch_pool_mean(const __half * x16, const float * x32, int N, int HW, int 
 void launch_copy_words(const void * src, void * dst, int64_t n_words, cudaStream_t st);  // n_words 4-byte words
 // sam_image_preprocess on the device (main.cpp:538-601): n u8 images [sh][sw][3] -> f32 [n][H][W][3], longer side fills the target,
 // bilinear with the reference's arithmetic, rounded to u8, /255, zero padding, row stride W.
-void launch_preprocess_u8(const uint8_t * src, int n, int sh, int sw, float * dst, int H, int W, cudaStream_t st);
+// dst8 != nullptr: write the quantised u8 image (the value before the /255) instead of the f32 one
+void launch_preprocess_u8(const uint8_t * src, int n, int sh, int sw, float * dst, int H, int W, cudaStream_t st, uint8_t * dst8 = nullptr);
 void launch_head_linear(const float * pooled, const float * W, const float * bias, int N, int C, int OUT, float * out, cudaStream_t st);
 
 }  // namespace b200

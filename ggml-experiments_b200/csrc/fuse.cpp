@@ -1007,7 +1007,23 @@ static bool build_fast_plan_impl(Plan * plan, ggml_cgraph * gf) {
                 const float *scale = P.pool.ptr<float>(n->c_scale), *shift = P.pool.ptr<float>(n->c_shift);
                 const int N = in->N, OC = o->C, act = n->act;
                 __half * o16 = o->p16; float * o32 = o->p32;
-                add_launch(plan, "stem_conv3x3s2_bn_silu", [=](cudaStream_t st) { launch_stem(x, sn, sy, sx, sc, N, (int)H, (int)W, wt, OC, scale, shift, act, o16, o32, st); },
+                // u8 route: the same launch stages its patch from the quantised u8 images when the plan's flag word says so
+                const uint8_t * x8 = nullptr;
+                const int *     x8_flag = nullptr;
+                if (src->kind == FK_INPUT && src->leaf && stem_takes_u8(OC, (int)W, !src->chw, o16 != nullptr, o32 != nullptr) && !plan->u8_input) {
+                    void * buf = nullptr, * flag = nullptr;
+                    B200_CHECK(cudaMalloc(&buf, (size_t)N * H * W * 3));
+                    B200_CHECK(cudaMalloc(&flag, 256));
+                    B200_CHECK(cudaMemset(flag, 0, 256));
+                    plan->owned_device.push_back(buf);
+                    plan->owned_device.push_back(flag);
+                    plan->u8_input = (uint8_t *)buf;
+                    plan->u8_flag  = (int *)flag;
+                    plan->u8_leaf  = src->leaf;
+                    x8 = plan->u8_input;
+                    x8_flag = plan->u8_flag;
+                }
+                add_launch(plan, "stem_conv3x3s2_bn_silu", [=](cudaStream_t st) { launch_stem(x, sn, sy, sx, sc, N, (int)H, (int)W, wt, OC, scale, shift, act, o16, o32, st, x8, x8_flag); },
                            2.0 * o->rows() * OC * 27, (double)in->rows() * 12 + (double)o->rows() * OC * (o16 ? 2 : 0) + (double)o->rows() * OC * (o32 ? 4 : 0), what,
                            (double)in->rows() * 6 + (double)o->rows() * OC * 2);
             } break;

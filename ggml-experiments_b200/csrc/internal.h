@@ -127,6 +127,13 @@ struct Plan {
     size_t                history_bytes  = 0;
     void *                u8_stage       = nullptr;  // device staging of raw u8 images (ggml_b200_graph_upload_u8_images)
     size_t                u8_stage_bytes = 0;
+    // u8 images handed straight to the stem (FAST plan, tensor-core stem): the quantised, resized images [N][H][W][3] and a device
+    // word the stem reads -- non-zero: stage from u8_input instead of the f32 input leaf.  Armed by
+    // ggml_b200_graph_upload_u8_images_fused, disarmed by run_plan after the launch that consumed it.
+    const ggml_tensor *   u8_leaf        = nullptr;
+    uint8_t *             u8_input       = nullptr;
+    int *                 u8_flag        = nullptr;
+    bool                  u8_armed       = false;
     cudaEvent_t           compute_done   = nullptr;  // recorded after this plan's kernels on its private stream
     cudaStream_t          private_stream = nullptr;  // set by ggml_b200_graph_use_private_stream (pipelined submission)
     bool                  concurrent     = false;    // lane of a group (ggml_b200_graph_group_begin): overlaps its siblings, no FIFO chain

@@ -419,6 +419,10 @@ void run_plan(Plan * plan, bool wait_for_results) {
         for (auto & l : plan->launches) l(st);
     }
     B200_CHECK(cudaGetLastError());
+    if (plan->u8_armed) {  // the u8 images were for this launch only: the next compute reads the f32 input leaf again
+        B200_CHECK(cudaMemsetAsync(plan->u8_flag, 0, sizeof(int), st));
+        plan->u8_armed = false;
+    }
     if (chained) {
         if (!plan->compute_done) B200_CHECK(cudaEventCreateWithFlags(&plan->compute_done, cudaEventDisableTiming));
         B200_CHECK(cudaEventRecord(plan->compute_done, st));
@@ -644,6 +648,38 @@ extern "C" int ggml_b200_graph_upload_u8_images(struct ggml_cgraph * gf, struct 
     B200_CHECK(cudaMemcpyAsync(p->u8_stage, host_u8, bytes, cudaMemcpyHostToDevice, st));
     launch_preprocess_u8((const uint8_t *)p->u8_stage, n, src_h, src_w, (float *)it->second.dptr, (int)input->ne[2], (int)input->ne[1], st);
     B200_CHECK(cudaGetLastError());
+    return 0;
+}
+// The same request when the next compute is all that will read the images: in a FAST plan whose stem is the tensor-core kernel, the
+// quantised u8 image (sam_image_preprocess before its /255, main.cpp:592-597) is all that is written -- 3 bytes per pixel instead of
+// 12 -- and the stem stages its patch from it (f16(v / 255) through a table: bit-identical to the f32 route).  Images that already have
+// the target size are copied straight into that buffer: the resize is the identity there (scale 1: dx = dy = 0).  The f32 input
+// leaf is NOT written; other plans fall back to ggml_b200_graph_upload_u8_images.  GGML_B200_NO_U8_STEM=1 forces the fallback.
+extern "C" int ggml_b200_graph_upload_u8_images_fused(struct ggml_cgraph * gf, struct ggml_tensor * input, const uint8_t * host_u8, int n, int src_h,
+                                                      int src_w) {
+    if (!gf->plan) B200_ABORT("ggml_b200_graph_upload_u8_images_fused: call ggml_b200_graph_prepare first");
+    Plan * p = (Plan *)gf->plan;
+    static const bool off = getenv("GGML_B200_NO_U8_STEM") != nullptr;
+    if (off || !p->u8_input || p->u8_leaf != input) return ggml_b200_graph_upload_u8_images(gf, input, host_u8, n, src_h, src_w);
+    if (input->ne[0] != 3 || input->ne[3] != n || !host_u8 || src_h <= 0 || src_w <= 0) return 1;
+    const int    H = (int)input->ne[2], W = (int)input->ne[1];
+    const size_t bytes = (size_t)n * src_h * src_w * 3;
+    cudaStream_t st    = p->private_stream ? p->private_stream : current_stream();
+    if (src_h == H && src_w == W) {
+        B200_CHECK(cudaMemcpyAsync(p->u8_input, host_u8, bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        if (p->u8_stage_bytes < bytes) {
+            B200_CHECK(cudaStreamSynchronize(st));
+            if (p->u8_stage) B200_CHECK(cudaFree(p->u8_stage));
+            B200_CHECK(cudaMalloc(&p->u8_stage, bytes));
+            p->u8_stage_bytes = bytes;
+        }
+        B200_CHECK(cudaMemcpyAsync(p->u8_stage, host_u8, bytes, cudaMemcpyHostToDevice, st));
+        launch_preprocess_u8((const uint8_t *)p->u8_stage, n, src_h, src_w, nullptr, H, W, st, p->u8_input);
+    }
+    B200_CHECK(cudaMemsetAsync(p->u8_flag, 1, sizeof(int), st));
+    B200_CHECK(cudaGetLastError());
+    p->u8_armed = true;
     return 0;
 }
 extern "C" void ggml_b200_graph_set_transfers(struct ggml_cgraph * gf, bool upload_inputs, bool download_outputs) {

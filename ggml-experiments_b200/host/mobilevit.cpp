@@ -474,7 +474,7 @@ static int run_graph(mvit::forward_graph & g, bool upload, bool download, bool w
     prepare_graph(g, !owner_is_current_stream);
     if (g.lanes.empty()) {
         if (u8_n) {
-            if (ggml_b200_graph_upload_u8_images(g.gf, g.input_hwc, g.input_u8, u8_n, src_h, src_w)) return 1;
+            if (ggml_b200_graph_upload_u8_images_fused(g.gf, g.input_hwc, g.input_u8, u8_n, src_h, src_w)) return 1;
             upload = false;
         }
         ggml_b200_graph_set_transfers(g.gf, upload, download);
@@ -491,7 +491,7 @@ static int run_graph(mvit::forward_graph & g, bool upload, bool download, bool w
         bool up = upload;
         if (u8_n) {
             const int nl = u8_n / S;
-            if (ggml_b200_graph_upload_u8_images(L.gf, L.input_hwc, g.input_u8 + (size_t)l * nl * src_h * src_w * 3, nl, src_h, src_w)) return 1;
+            if (ggml_b200_graph_upload_u8_images_fused(L.gf, L.input_hwc, g.input_u8 + (size_t)l * nl * src_h * src_w * 3, nl, src_h, src_w)) return 1;
             up = false;
         }
         ggml_b200_graph_set_transfers(L.gf, up, download);

@@ -273,6 +273,12 @@ int ggml_b200_graph_compute_steps(struct ggml_context * ctx, struct ggml_cgraph 
 int ggml_b200_graph_upload_u8_images(struct ggml_cgraph * cgraph, struct ggml_tensor * input, const uint8_t * host_u8, int n, int src_h,
                                      int src_w);
 
+/* The same request when only the next compute will read the images: a FAST plan with the tensor-core stem keeps the quantised u8
+ * image (3 bytes per pixel; images already H x W are copied straight in) and the stem stages its patch from it -- same bits as the
+ * f32 route.  The f32 input leaf is not written.  Falls back to ggml_b200_graph_upload_u8_images for other plans. */
+int ggml_b200_graph_upload_u8_images_fused(struct ggml_cgraph * cgraph, struct ggml_tensor * input, const uint8_t * host_u8, int n,
+                                           int src_h, int src_w);
+
 /* Synchronous device->host copy of any (contiguous) tensor of the graph's plan, e.g. an intermediate that is not a
  * declared output.  Returns 0 on success. */
 int ggml_b200_tensor_download(struct ggml_cgraph * cgraph, struct ggml_tensor * tensor, void * host_dst);

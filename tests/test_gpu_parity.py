@@ -390,6 +390,32 @@ def test_compute_u8_equals_f32_path_on_preprocessed_images(G, oracle, weight_fil
         m.close()
 
 
+@pytest.mark.parametrize("variant,n,hw,sh,sw", [("xxs", 3, 256, 256, 256), ("s", 2, 128, 128, 128), ("xs", 2, 192, 192, 192), ("xxs", 1, 320, 500, 320),
+                                               ("xxs", 5, 64, 64, 64), ("s", 2, 448, 448, 448)])
+def test_u8_images_staged_by_the_stem_equal_the_f32_route(G, oracle, weight_files, variant, n, hw, sh, sw):
+    """FAST plan: the stem stages its patch from the quantised u8 image (no f32 image in HBM; same-size images skip the resize kernel).
+    Same bits as the forward on the oracle-preprocessed f32 images, for ragged stem tiles, every batch position, and the plan must
+    read the f32 leaf again on the next f32 call (the u8 flag is armed for one compute only)."""
+    rng = np.random.default_rng(n * 1000 + hw)
+    img = rng.integers(0, 256, (n, sh, sw, 3), dtype=np.uint8)
+    pre = oracle.preprocess_u8(img, hw, hw)
+    other = rng.random((n, hw, hw, 3), dtype=np.float32)
+    m = G.MobileViT(weight_files[variant])
+    try:
+        f_ref, p_ref = (a.copy() for a in m.extract_features(pre))
+        f_oth, p_oth = (a.copy() for a in m.extract_features(other))
+        assert not np.array_equal(p_ref, p_oth)
+        m.host_input_u8(n, hw, hw, sh, sw)[:] = img
+        f, p = (a.copy() for a in m.compute_u8(n, hw, hw, sh, sw))
+        np.testing.assert_array_equal(p, p_ref)
+        np.testing.assert_array_equal(f, f_ref)
+        f2, p2 = m.extract_features(other)  # f32 route on the same plan right after a u8 compute
+        np.testing.assert_array_equal(p2, p_oth)
+        np.testing.assert_array_equal(f2, f_oth)
+    finally:
+        m.close()
+
+
 # ---- BASELINE.json's full size (MobileViT-S, batch 256, 256x256) through size-independent properties --------------------
 def test_full_size_batch_256_is_batch_independent_and_matches_the_oracle_sample(G, oracle, weight_files):
     """At the bench's own shape the oracle would need minutes, so: (1) every copy of an image inside the batch of 256 gives
