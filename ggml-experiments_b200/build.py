@@ -65,6 +65,8 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> dict:
                     extra.append("-DGGML_B200_IR_PROFILE")
                 if os.environ.get("GGML_B200_VIT_PROFILE"):
                     extra.append("-DGGML_B200_VIT_PROFILE")
+                if os.environ.get("GGML_B200_GEMM_PROFILE"):
+                    extra.append("-DGGML_B200_GEMM_PROFILE")
                 if os.environ.get("GGML_B200_ATTN_PROFILE"):
                     extra.append("-DGGML_B200_ATTN_PROFILE")
                 _run([NVCC, *ARCH, *COMMON, *extra, "-c", s, "-o", o])

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
     const uint32_t p_full = smem_u32(&bars[4]), pv_full = smem_u32(&bars[5]);
     const uint32_t k_full = smem_u32(&bars[6]), k_free = smem_u32(&bars[9]), v_full = smem_u32(&bars[12]), v_free = smem_u32(&bars[14]);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform -> role loops on the uniform datapath
     const int nkb   = p.L / kKB;
     const int nit   = (int)blockIdx.x < p.items ? (p.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;  // items of this CTA
     const int nblk  = nit * nkb;                                                                            // key blocks of this CTA

@@ -47,6 +47,20 @@ __device__ __forceinline__ uint32_t make_idesc(int block_n) {
 // ---------------------------------------------------------------------------------------------------------
 // EPI: compile-time epilogue variant (bit mask, kEpi* below) so the per-element loops carry no run-time feature tests;
 // EPI = -1 is the generic kernel that reads the flags from the parameters.
+#ifdef GGML_B200_GEMM_PROFILE
+// clock64 phase profile of the halo-mode conv (build with GGML_B200_GEMM_PROFILE=1): cycles each role spends waiting on each barrier
+__device__ unsigned long long g_gemm_prof[64];
+__device__ int g_gemm_noload;  // probe: the halo producer arrives on the full barriers without loading anything (pure MMA-loop timing)
+#define PROF_WAIT(BAR, PAR, ACC)                 \
+    do {                                         \
+        const long long _t0 = clock64();         \
+        mbar_wait((BAR), (PAR));                 \
+        (ACC) += clock64() - _t0;                \
+    } while (0)
+#else
+#define PROF_WAIT(BAR, PAR, ACC) mbar_wait((BAR), (PAR))
+#endif
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a0,
                                                            const __grid_constant__ CUtensorMap map_a1,
@@ -90,7 +104,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     const int       stg16_bytes = p.ep.out16 ? kBlockM * 128 : 0;      // 64 f16 columns per row
     const int       stg32_bytes = (p.ep.out32 || p.ep.res32) ? 2 * kBlockM * 128 : 0;  // 2 x 32 f32 columns per row
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops' barrier addresses, smem / TMEM
+    // addresses and UMMA descriptors in uniform registers (no per-MMA R2UR / VOTEU chains in front of every tcgen05.mma)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * p.block_n;
     const int tile_m      = p.tile_m;  // 128 except for conv tiles that are a whole number of image rows
     const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
@@ -184,30 +200,54 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         // below -- the three kh taps are start-address offsets of W rows into it -- and per tap one pre-tiled weight block by a 1-D
         // bulk copy.  A third of the activation boxes (and TMA box rows) of the per-tap scheme, no tensor map for the weights. =====
         uint32_t ia = 0, ib = 0;
+        long long w_aempty = 0, w_bempty = 0;
+        const long long t_role0 = clock64();
         const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
-        const uint32_t a_box_bytes = (uint32_t)(p.tile_m + 2 * p.W) * 128u, wb_bytes = (uint32_t)p.block_n * 128u;
-        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+        // pair mode: the box holds TWO vertically adjacent M tiles (2 * tile_m + 2W rows): every weight block and every activation
+        // row is fetched once per 256 pixels -- the kernel is bound by the L2 -> SM rate, so the bytes per pixel are what counts
+        const int      tpb         = p.pair ? 2 : 1;  // M tiles per box
+        const uint32_t a_box_bytes = (uint32_t)(tpb * p.tile_m + 2 * p.W) * 128u, wb_bytes = (uint32_t)p.block_n * 128u;
+        for (int tile = blockIdx.x * tpb; tile < num_m_tiles; tile += gridDim.x * tpb) {
             const int m0 = tile * tile_m, hw = p.H * p.W;
             const int img = m0 / hw, y0 = p.rows_per_tile ? (m0 % hw) / p.W : 0;
             for (int cb = 0; cb < cblk_tot; cb++) {
                 const int src = cb >= p.cblk0, cbl = src ? cb - p.cblk0 : cb;
                 for (int kw = 0; kw < 3; kw++, ia++) {
                     const uint32_t sa = ia % (uint32_t)p.stages;
-                    mbar_wait(smem_u32(&empty_bar[sa]), ((ia / (uint32_t)p.stages) & 1u) ^ 1u);
-                    mbar_expect_tx_ws(smem_u32(&full_bar[sa]), a_box_bytes);
+                    PROF_WAIT(smem_u32(&empty_bar[sa]), ((ia / (uint32_t)p.stages) & 1u) ^ 1u, w_aempty);
                     const uint32_t dst = smem_u32(ring + (size_t)sa * p.a_slot_bytes);
+#ifdef GGML_B200_GEMM_PROFILE
+                    if (g_gemm_noload & 1) { if (lane == 0) mbar_arrive(smem_u32(&full_bar[sa])); } else
+#endif
+                    {
+                    mbar_expect_tx_ws(smem_u32(&full_bar[sa]), a_box_bytes);
                     if (src) tma_load_4d_ws(dst, &map_a1, cbl * kBlockK, kw - 1, y0 - 1, img, smem_u32(&full_bar[sa]));
                     else tma_load_4d_ws(dst, &map_a0, cbl * kBlockK, kw - 1, y0 - 1, img, smem_u32(&full_bar[sa]));
+                    }
                     for (int kh = 0; kh < 3; kh++, ib++) {
                         const uint32_t sb = ib % (uint32_t)p.b_stages;
-                        mbar_wait(smem_u32(&bempty_bar[sb]), ((ib / (uint32_t)p.b_stages) & 1u) ^ 1u);
-                        mbar_expect_tx_ws(smem_u32(&bfull_bar[sb]), wb_bytes);
+                        PROF_WAIT(smem_u32(&bempty_bar[sb]), ((ib / (uint32_t)p.b_stages) & 1u) ^ 1u, w_bempty);
                         const uint8_t * wsrc = p.w_halo + ((size_t)((cb * 3 + kw) * 3 + kh) * p.n_pad + (size_t)n0) * 128u;
+#ifdef GGML_B200_GEMM_PROFILE
+                        if (g_gemm_noload & 2) { if (lane == 0) mbar_arrive(smem_u32(&bfull_bar[sb])); } else
+#endif
+                        {
+                        mbar_expect_tx_ws(smem_u32(&bfull_bar[sb]), wb_bytes);
                         bulk_load_1d_ws(smem_u32(ringB + (size_t)sb * wb_bytes), wsrc, wb_bytes, smem_u32(&bfull_bar[sb]));
+                        }
                     }
                 }
             }
         }
+#ifdef GGML_B200_GEMM_PROFILE
+        if (lane == 0) {
+            unsigned long long * g = g_gemm_prof + 16 * ((p.W == 32 ? 0 : 1) * 2 + (p.C1 > 0));
+            atomicAdd(g + 0, (unsigned long long)w_aempty); atomicAdd(g + 1, (unsigned long long)w_bempty);
+            atomicAdd(g + 2, (unsigned long long)(clock64() - t_role0)); atomicAdd(g + 3, 1ull);
+        }
+#else
+        (void)w_aempty; (void)w_bempty; (void)t_role0;
+#endif
         __syncwarp();
     } else if (warp == 0) {
         // ===================== TMA producer (whole warp, elected lane issues) =====================
@@ -254,11 +294,17 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
         const uint32_t wb_bytes = (uint32_t)p.block_n * 128u;
         uint32_t ia = 0, ib = 0, t = 0;
-        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
-            const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;
-            mbar_wait(smem_u32(&tmem_empty[acc]), aph ^ 1u);
+        long long w_tmem = 0, w_afull = 0, w_bfull = 0;
+        const long long t_role0 = clock64();
+        const int tpb = p.pair ? 2 : 1;  // M tiles per activation box: each weight block feeds tpb accumulators
+        for (int tile = blockIdx.x * tpb; tile < num_m_tiles; tile += gridDim.x * tpb, t += (uint32_t)tpb) {
+            uint32_t tmem_d[2] = {0, 0};
+            for (int h = 0; h < tpb; h++) {
+                const uint32_t acc = (t + (uint32_t)h) % (uint32_t)p.acc_stages, aph = ((t + (uint32_t)h) / (uint32_t)p.acc_stages) & 1u;
+                PROF_WAIT(smem_u32(&tmem_empty[acc]), aph ^ 1u, w_tmem);
+                tmem_d[h] = tmem_base + acc * (uint32_t)p.block_n;
+            }
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
             uint32_t first = 1;
             for (int cb = 0; cb < cblk_tot; cb++) {
                 const int src = cb >= p.cblk0;
@@ -266,27 +312,37 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 const int ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
                 for (int kw = 0; kw < 3; kw++, ia++) {
                     const uint32_t sa = ia % (uint32_t)p.stages;
-                    mbar_wait(smem_u32(&full_bar[sa]), (ia / (uint32_t)p.stages) & 1u);
+                    PROF_WAIT(smem_u32(&full_bar[sa]), (ia / (uint32_t)p.stages) & 1u, w_afull);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(ring + (size_t)sa * p.a_slot_bytes);
                     for (int kh = 0; kh < 3; kh++, ib++) {
                         const uint32_t sb = ib % (uint32_t)p.b_stages;
-                        mbar_wait(smem_u32(&bfull_bar[sb]), (ib / (uint32_t)p.b_stages) & 1u);
+                        PROF_WAIT(smem_u32(&bfull_bar[sb]), (ib / (uint32_t)p.b_stages) & 1u, w_bfull);
                         tc_fence_after();
-                        // tap (kh, kw): the tile's pixels shifted down by kh image rows = W rows of 128 B (a multiple of the 1 KiB swizzle atom)
-                        const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(kh * p.W) * 128u, 128);
                         const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * wb_bytes), 128);
-                        for (int k = 0; k < ksteps; k++) {
-                            umma_f16_ws(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                            first = 0;
+                        for (int h = 0; h < tpb; h++) {
+                            // tap (kh, kw) of M tile h: the box rows shifted down by kh image rows (+ one tile) = a multiple of the 1 KiB swizzle atom
+                            const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(kh * p.W + h * tile_m) * 128u, 128);
+                            for (int k = 0; k < ksteps; k++)
+                                umma_f16_ws(tmem_d[h], adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
                         }
+                        first = 0;
                         umma_commit_ws(smem_u32(&bempty_bar[sb]));
                     }
                     umma_commit_ws(smem_u32(&empty_bar[sa]));
                 }
             }
-            umma_commit_ws(smem_u32(&tmem_full[acc]));
+            for (int h = 0; h < tpb; h++) umma_commit_ws(smem_u32(&tmem_full[(t + (uint32_t)h) % (uint32_t)p.acc_stages]));
         }
+#ifdef GGML_B200_GEMM_PROFILE
+        if (lane == 0) {
+            unsigned long long * g = g_gemm_prof + 16 * ((p.W == 32 ? 0 : 1) * 2 + (p.C1 > 0));
+            atomicAdd(g + 4, (unsigned long long)w_tmem); atomicAdd(g + 5, (unsigned long long)w_afull); atomicAdd(g + 6, (unsigned long long)w_bfull);
+            atomicAdd(g + 7, (unsigned long long)(clock64() - t_role0));
+        }
+#else
+        (void)w_tmem; (void)w_afull; (void)w_bfull; (void)t_role0;
+#endif
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, elected lane issues) =====================
@@ -353,7 +409,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const uint32_t swz   = (uint32_t)(row & 7);
         const uint32_t rbar  = smem_u32(&res_full[group]);
         uint32_t t = 0, ri = 0;
-        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
+        const bool paired = p.conv == 2 && p.pair;  // local tiles 2i, 2i+1 are the two halves of the CTA's i-th activation box
+        for (int tile = paired ? 2 * (int)blockIdx.x : (int)blockIdx.x; tile < num_m_tiles;
+             t++, tile = paired ? 2 * (int)(blockIdx.x + (t >> 1) * gridDim.x) + (int)(t & 1u) : (int)(blockIdx.x + t * gridDim.x)) {
             if ((t & 1u) != group) continue;
             const int      m0  = tile * tile_m;
             const int      m   = m0 + row;
@@ -691,7 +749,7 @@ static void make_output_maps(GemmLaunch & L) {
 }
 
 static void choose_grid(GemmLaunch & L) {
-    const int num_m_tiles = (L.p.M + L.p.tile_m - 1) / L.p.tile_m;
+    const int num_m_tiles = (L.p.M + L.p.tile_m - 1) / L.p.tile_m / (L.p.conv == 2 && L.p.pair ? 2 : 1);  // pair mode: boxes of two tiles
     int       per_n       = (L.ctas_per_sm * runtime().sm_count) / L.p.n_tiles;
     if (per_n < 1) per_n = 1;
     L.grid = dim3((unsigned)(num_m_tiles < per_n ? num_m_tiles : per_n), (unsigned)L.p.n_tiles, 1);
@@ -802,14 +860,26 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
     // two-CTA per-tap scheme keeps more loads in flight (conv 96->96 at 32x32, batch 256: 95 us per-tap vs 113 us halo).  On small
     // grids (fewer tiles than SMs: the 16x16 / 8x8 stages at batch <= 32, batch-1 latency) the chain of 27-45 dependent k-blocks is what
     // costs, and the halo scheme is 15-25 % faster -- so it is used there.  GGML_B200_CONV_HALO=1 forces it everywhere.
-    const bool halo_ok = (p.M / tile_m) * p.n_tiles <= runtime().sm_count || getenv("GGML_B200_CONV_HALO") != nullptr;
+    // Pair mode (round 2): the kernel is bound by the L2 -> SM rate (~42 B/clk/SM chip-wide), i.e. by operand bytes per pixel: 387 KB per
+    // 128 pixels at C = N = 96 in the per-tap scheme (9 activation boxes + 9 weight blocks), 276 KB with the halo box, 202 KB when two
+    // vertically adjacent tiles share the box (rows 2 * tile_m + 2W) and every weight block (4 accumulators of N <= 128 columns in TMEM).
+    // Full 128-pixel tiles of whole image rows, an even number of them per image.
+    const bool pair_ok = halo && rows_per_tile > 0 && tile_m == kBlockM && (H / box_h) % 2 == 0 && p.block_n <= 128 && p.n_tiles == 1 &&
+                         (2 * tile_m + 2 * W) / W <= 256 && getenv("GGML_B200_CONV_NO_PAIR") == nullptr;
+    const bool big_grid = (p.M / tile_m) * p.n_tiles > 2 * runtime().sm_count;
+    const bool halo_ok = (p.M / tile_m) * p.n_tiles <= runtime().sm_count || (pair_ok && big_grid) || getenv("GGML_B200_CONV_HALO") != nullptr;
     if (halo && halo_ok && p.n_tiles * p.block_n <= n_pad) {
+        p.pair = pair_ok && (big_grid || getenv("GGML_B200_CONV_PAIR") != nullptr) ? 1 : 0;
+        if (p.pair) {
+            p.acc_stages = 4;
+            p.tmem_cols  = 4 * p.block_n <= 256 ? 256 : 512;
+        }
         // one CTA per SM; shared memory = activation ring (slots of 2W + 128 rows: the MMA of tap kh reads 128 rows from row kh * W)
         // + weight ring + control + epilogue staging
         p.conv         = 2;
         p.w_halo       = Wt_halo;
         p.n_pad        = n_pad;
-        p.a_slot_bytes = (2 * W + 128) * 128;
+        p.a_slot_bytes = (2 * W + (p.pair ? 2 : 1) * 128) * 128;
         const int wb_bytes = p.block_n * 128;
         const int staging  = 2 * ((ep.out16 ? kBlockM * 128 : 0) + (ep.out32 ? 2 * kBlockM * 128 : 0));
         const int budget   = 216 * 1024 - 1024 - kCtrlBytes - staging;
@@ -819,6 +889,11 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
             const int sb4 = (budget - 4 * p.a_slot_bytes) / wb_bytes;
             if (sb4 >= 6) { sa = 4; sb = sb4 > kMaxStage ? kMaxStage : sb4; }
         }
+        if (sb < 3 && p.pair) {  // two (larger) activation slots leave room for the weight ring
+            sa = 2;
+            sb = (budget - sa * p.a_slot_bytes) / wb_bytes;
+            if (sb > kMaxStage) sb = kMaxStage;
+        }
         if (sb >= 3) {
             p.stages      = sa;
             p.b_stages    = sb;
@@ -827,9 +902,11 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
             L.smem_bytes  = 1024 + (size_t)p.ring_bytes + kCtrlBytes + staging;
         } else {
             p.conv = 1;
+            p.pair = 0;
+            choose_tiling(L, OC);  // restores the accumulator stages of the per-tap scheme
         }
     }
-    const int box_rows = p.conv == 2 ? box_h + 2 : box_h;
+    const int box_rows = p.conv == 2 ? (p.pair ? 2 : 1) * box_h + 2 : box_h;
     auto act_map = [&](CUtensorMap * map, const __half * x, int C) {
         const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         const uint64_t str[3]  = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
@@ -859,6 +936,20 @@ static void gemm_launch_variant(const GemmLaunch & L, cudaStream_t st) {
     }
     launch_pdl(k_gemm_tcgen05<EPI>, L.grid, dim3(kThreads), L.smem_bytes, st, L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
 }
+
+#ifdef GGML_B200_GEMM_PROFILE
+extern "C" void ggml_b200_debug_gemm_prof(unsigned long long * out64, int reset) {
+    if (out64) B200_CHECK(cudaMemcpyFromSymbol(out64, g_gemm_prof, sizeof(unsigned long long) * 64));
+    if (reset >= 16) {
+        const int v = reset - 16;
+        B200_CHECK(cudaMemcpyToSymbol(g_gemm_noload, &v, sizeof v));
+    }
+    if (reset) {
+        unsigned long long z[64] = {0};
+        B200_CHECK(cudaMemcpyToSymbol(g_gemm_prof, z, sizeof z));
+    }
+}
+#endif
 
 void gemm_launch(const GemmLaunch & L, cudaStream_t st) {
     const GemmEpilogue & ep = L.p.ep;

@@ -54,6 +54,7 @@ struct GemmLaunch {
                                     //    boxes (one box per kw, the three kh taps are descriptor offsets into it) and pre-tiled weights
         int ring_bytes;             // bytes of the operand ring(s) in shared memory (the barriers follow)
         int a_slot_bytes, b_stages; // conv == 2: activation slot size, depth of the weight ring (`stages` = depth of the activation ring)
+        int pair;                   // conv == 2: 1 = two vertically adjacent 128-pixel M tiles per activation box and weight block (4 accumulators)
         int n_pad;                  // conv == 2: rows of one (channel block, tap) weight block in the halo layout (OC padded to 64)
         const uint8_t * w_halo;     // conv == 2: weights as [channel block][kw][kh][n_pad rows x 64 ch], 128B-swizzled (conv3x3_pack_halo)
         int tile_m;                 // output rows (pixels) per M tile: 128, or less when a conv tile is a whole number of image rows

@@ -179,7 +179,7 @@ k_ir_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
     const uint32_t exp_full = smem_u32(&bars[6]), red_done = smem_u32(&bars[7]), es_done = smem_u32(&bars[8]), as_full = smem_u32(&bars[9]);
     const uint32_t res_bar = smem_u32(&bars[10]);  // residual slab landed (reduce epilogue)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform -> role loops on the uniform datapath
 
     if (tid == 0) {
         for (int i = 0; i < 8; i++) mbar_init(smem_u32(&bars[i]), 1);

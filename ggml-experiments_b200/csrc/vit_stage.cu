@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vit_stage(const __grid_constant
     const uint32_t bar0 = smem_u32(&bars[0]);
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform -> role loops on the uniform datapath
     if (tid == 0) {
         for (int i = 0; i < B_COUNT; i++) {
             if (i == B_XLOAD) { mbar_init(bar(i), 128u); continue; }  // one arrive (+ its row's bytes) per token thread

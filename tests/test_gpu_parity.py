@@ -70,7 +70,10 @@ def test_gemm_tcgen05_matches_numpy(G, M, N, K):
                                                   (4, 10, 10, 160, 160, 160), (5, 12, 12, 64, 0, 64), (3, 6, 6, 80, 0, 80),
                                                   (1, 28, 56, 48, 0, 48), (7, 5, 5, 32, 0, 40),
                                                   # halo mode with several tiles per CTA / a single image (N split into 64-column tiles)
-                                                  (40, 32, 32, 96, 0, 96), (1, 8, 8, 160, 160, 160), (2, 16, 24, 64, 0, 72)])
+                                                  (40, 32, 32, 96, 0, 96), (1, 8, 8, 160, 160, 160), (2, 16, 24, 64, 0, 72),
+                                                  # pair mode (two M tiles per activation box and weight block): grids above 2 x 148 tiles
+                                                  (80, 32, 32, 96, 0, 96), (40, 32, 32, 96, 96, 96), (160, 16, 16, 128, 128, 128),
+                                                  (150, 16, 16, 128, 0, 128), (75, 32, 32, 64, 0, 72)])
 def test_conv3x3_tcgen05_matches_numpy(G, n_img, H, Wd, C0, C1, OC):
     L = G.lib_ggml()
     rng = np.random.default_rng(H * 31 + C0 + OC)
@@ -89,6 +92,28 @@ def test_conv3x3_tcgen05_matches_numpy(G, n_img, H, Wd, C0, C1, OC):
         for kw in range(3):
             ref += np.einsum("nhwc,oc->nhwo", xp[:, kh:kh + H, kw:kw + Wd, :], w64[:, kh, kw, :])
     assert np.abs(out - ref).max() < 3e-3 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n_img,H,Wd,C0,C1,OC", [(3, 32, 32, 96, 0, 96), (1, 16, 16, 128, 128, 128), (5, 32, 32, 96, 96, 96), (2, 64, 32, 32, 0, 48)])
+def test_conv3x3_pair_mode_gives_the_bits_of_the_other_schemes(G, n_img, H, Wd, C0, C1, OC, monkeypatch):
+    """Per-tap boxes, the halo box and the halo box shared by two M tiles accumulate in the same K order: identical bits."""
+    L = G.lib_ggml()
+    rng = np.random.default_rng(H + C0 + OC)
+    x0 = rng.normal(size=(n_img, H, Wd, C0)).astype(np.float16)
+    x1 = rng.normal(size=(n_img, H, Wd, C1)).astype(np.float16) if C1 else None
+    Wt = (rng.normal(size=(OC, 3, 3, C0 + C1)) / np.sqrt(9 * (C0 + C1))).astype(np.float16)
+    outs = []
+    for env in ({"GGML_B200_CONV_NO_HALO": "1"}, {"GGML_B200_CONV_NO_PAIR": "1"}, {"GGML_B200_CONV_PAIR": "1"}):
+        for k in ("GGML_B200_CONV_NO_HALO", "GGML_B200_CONV_NO_PAIR", "GGML_B200_CONV_PAIR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = np.zeros((n_img, H, Wd, OC), np.float32)
+        assert L.ggml_b200_debug_conv3x3(_p(x0.view(np.uint16), u16p), C0, _p(x1.view(np.uint16), u16p) if C1 else None, C1, n_img,
+                                         H, Wd, _p(Wt.view(np.uint16), u16p), OC, None, None, 0, _p(out, f32p)) == 0
+        outs.append(out)
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
 
 
 # ---- whole model through the ggml boundary ------------------------------------------------------------
