@@ -404,6 +404,19 @@ __global__ void k_mma_rate(int N, int iters, int commit_every, long long * out, 
         const uint64_t adesc = make_smem_desc(smem_u32(smem), 128), bdesc = make_smem_desc(smem_u32(smem) + 16384, 128);
         const uint32_t tm = __shfl_sync(0xffffffffu, slot, 0);
         const long long t0 = clock64();
+        if (commit_every < -1) {
+            // the conv loop's shape: groups of -commit_every MMAs alternating between two accumulators, an asynchronous commit (to a
+            // barrier nobody waits for) after every group
+            __shared__ __align__(8) uint64_t sink;
+            if (threadIdx.x == 0) mbar_init(smem_u32(&sink), 1 << 20);
+            __syncwarp();
+            const int g = -commit_every;
+            for (int i = 0; i < iters; i += g) {
+                for (int j = 0; j < g; j++)
+                    umma_f16_elect(tm + (uint32_t)((j >> 2) & 1) * (uint32_t)N, adesc + (uint64_t)(2 * (j & 3)), bdesc + (uint64_t)(2 * (j & 3)), idesc, 1);
+                umma_commit_ws(smem_u32(&sink));
+            }
+        } else
         for (int i = 0; i < iters; i++) umma_f16_elect(tm, adesc + (uint64_t)(2 * (i & 3)), bdesc + (uint64_t)(2 * (i & 3)), idesc, 1);
         const long long t1 = clock64();
         if (threadIdx.x == 0) umma_commit(smem_u32(&bar));

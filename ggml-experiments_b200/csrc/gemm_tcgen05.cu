@@ -30,7 +30,7 @@ namespace b200 {
 
 static constexpr int kBlockM   = 128;
 static constexpr int kBlockK   = 64;   // 64 f16 = 128 bytes = one swizzle-128B row
-static constexpr int kThreads  = 320;  // 10 warps: TMA, MMA, 2 x 4 epilogue
+static constexpr int kThreads  = 352;  // 11 warps: TMA, MMA, 2 x 4 epilogue, second MMA issuer (conv3x3 pair mode)
 static constexpr int kMaxStage = 8;  // deep rings only for small grids (choose_tiling): a lone CTA per SM hides the TMA latency with loads in flight, not with neighbours
 static constexpr int kCtrlBytes = 4096;
 enum { kEpiAct = 1, kEpiRes32 = 2, kEpiOut16 = 4, kEpiOut32 = 8, kEpiLn = 16, kEpiStats = 32, kEpiRes16 = 64 };  // barriers + TMEM slot + per-column scale/shift, padded to keep 1 KiB alignment
@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     const int tile_m      = p.tile_m;  // 128 except for conv tiles that are a whole number of image rows
     const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
 
+    // conv3x3 pair mode: the two M tiles of a box are issued by TWO warps (1 and 10, different SM sub-partitions), one accumulator each.
+    // The issue loop -- barrier polls, commits and the uniform-datapath descriptor arithmetic -- costs ~120 cycles per MMA against 56 of
+    // math at N = 96 (tests/conv_prof.py with loads and epilogue off), so a second issuer nearly doubles the tensor pipe's duty cycle.
+    const uint32_t n_issuers = (p.conv == 2 && p.pair) ? 2u : 1u;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_b);
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         if (p.ep.res32) tma_prefetch_desc(&map_r32);
         for (int s = 0; s < p.stages; s++) {
             mbar_init(smem_u32(&full_bar[s]), p.a_cp_async ? 33 : 1);  // TMA thread (+ 32 cp.async lanes)
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), n_issuers);
         }
         for (int a = 0; a < 4; a++) {
             mbar_init(smem_u32(&tmem_full[a]), 1);
@@ -130,14 +134,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         mbar_init(smem_u32(bres_full), 1);
         for (int s = 0; s < kMaxStage; s++) {
             mbar_init(smem_u32(&bfull_bar[s]), 1);
-            mbar_init(smem_u32(&bempty_bar[s]), 1);
+            mbar_init(smem_u32(&bempty_bar[s]), n_issuers);
         }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     // SiLU epilogues work on h = y/2 (silu(y) = h + h tanh h): the 1/2 is folded into scale and shift here, exactly (a power of two)
     const float ah = p.ep.act ? 0.5f : 1.0f;
-    for (int i = threadIdx.x; i < p.block_n; i += kThreads) {
+    for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
         const int n = n0 + i;
         s_scale[i]  = ((p.ep.scale && n < p.N) ? p.ep.scale[n] : 1.0f) * ah;
         s_shift[i]  = ((p.ep.shift && n < p.N) ? p.ep.shift[n] : 0.0f) * ah;
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             }
         }
         __syncwarp();
-    } else if (warp == 1 && p.conv == 2) {
+    } else if ((warp == 1 || (warp == 10 && n_issuers == 2)) && p.conv == 2) {
         // ===================== MMA issuer, halo mode =====================
         const uint32_t idesc = make_idesc(p.block_n);
         const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
@@ -297,13 +301,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         long long w_tmem = 0, w_afull = 0, w_bfull = 0;
         const long long t_role0 = clock64();
         const int tpb = p.pair ? 2 : 1;  // M tiles per activation box: each weight block feeds tpb accumulators
+        const int h   = warp == 1 ? 0 : 1;  // the half of the box this issuer owns
         for (int tile = blockIdx.x * tpb; tile < num_m_tiles; tile += gridDim.x * tpb, t += (uint32_t)tpb) {
-            uint32_t tmem_d[2] = {0, 0};
-            for (int h = 0; h < tpb; h++) {
-                const uint32_t acc = (t + (uint32_t)h) % (uint32_t)p.acc_stages, aph = ((t + (uint32_t)h) / (uint32_t)p.acc_stages) & 1u;
-                PROF_WAIT(smem_u32(&tmem_empty[acc]), aph ^ 1u, w_tmem);
-                tmem_d[h] = tmem_base + acc * (uint32_t)p.block_n;
-            }
+            const uint32_t acc = (t + (uint32_t)h) % (uint32_t)p.acc_stages, aph = ((t + (uint32_t)h) / (uint32_t)p.acc_stages) & 1u;
+            PROF_WAIT(smem_u32(&tmem_empty[acc]), aph ^ 1u, w_tmem);
+            const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
             tc_fence_after();
             uint32_t first = 1;
             for (int cb = 0; cb < cblk_tot; cb++) {
@@ -319,20 +321,18 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         const uint32_t sb = ib % (uint32_t)p.b_stages;
                         PROF_WAIT(smem_u32(&bfull_bar[sb]), (ib / (uint32_t)p.b_stages) & 1u, w_bfull);
                         tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * wb_bytes), 128);
-                        for (int h = 0; h < tpb; h++) {
-                            // tap (kh, kw) of M tile h: the box rows shifted down by kh image rows (+ one tile) = a multiple of the 1 KiB swizzle atom
-                            const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(kh * p.W + h * tile_m) * 128u, 128);
-                            for (int k = 0; k < ksteps; k++)
-                                umma_f16_ws(tmem_d[h], adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
-                        }
+                        const uint32_t b_lo = smem_desc_lo(smem_u32(ringB + (size_t)sb * wb_bytes));
+                        // tap (kh, kw) of M tile h: the box rows shifted down by kh image rows (+ one tile) = a multiple of the 1 KiB swizzle atom
+                        const uint32_t a_lo = smem_desc_lo(a0 + (uint32_t)(kh * p.W + h * tile_m) * 128u);
+                        for (int k = 0; k < ksteps; k++)
+                            umma_f16_ws_split(tmem_d, a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), smem_desc_hi(128), idesc, (first && k == 0) ? 0u : 1u);
                         first = 0;
                         umma_commit_ws(smem_u32(&bempty_bar[sb]));
                     }
                     umma_commit_ws(smem_u32(&empty_bar[sa]));
                 }
             }
-            for (int h = 0; h < tpb; h++) umma_commit_ws(smem_u32(&tmem_full[(t + (uint32_t)h) % (uint32_t)p.acc_stages]));
+            umma_commit_ws(smem_u32(&tmem_full[acc]));
         }
 #ifdef GGML_B200_GEMM_PROFILE
         if (lane == 0) {
@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         // ===================== MMA issuer (whole warp, elected lane issues) =====================
         {
             const uint32_t idesc = make_idesc(p.block_n);
+            const uint32_t desc_hi = p.kb_elems == 64 ? smem_desc_hi(128) : (p.kb_elems == 32 ? smem_desc_hi(64) : smem_desc_hi(32));
             uint32_t it = 0, t = 0;
             if (p.b_resident && (int)blockIdx.x < num_m_tiles) mbar_wait(smem_u32(bres_full), 0);
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
@@ -373,11 +374,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
                     }
                     const int      ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
-                    const uint64_t adesc  = make_smem_desc(sa, (uint32_t)p.kb_elems * 2);
-                    const uint64_t bdesc  = make_smem_desc(sb, (uint32_t)p.kb_elems * 2);
+                    const uint32_t a_lo = smem_desc_lo(sa), b_lo = smem_desc_lo(sb);
                     for (int k = 0; k < ksteps; k++) {
                         // advancing 16 f16 (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
-                        umma_f16_ws(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_f16_ws_split(tmem_d, a_lo + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k), desc_hi, idesc, (kb | k) != 0);
                     }
                     umma_commit_ws(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
                 }
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < 10) {
         // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
         // A thread owns one output row (TMEM lane).  Writing rows straight to global costs one 16-byte wavefront per
         // lane (32 per instruction) and made output-heavy layers LSU-bound; instead each group stages a
@@ -428,6 +428,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             mbar_wait(smem_u32(&tmem_full[acc]), aph);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
+#ifdef GGML_B200_GEMM_PROFILE
+            if (g_gemm_noload & 4) {  // probe: the epilogue hands the accumulator straight back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+                continue;
+            }
+#endif
             for (int cc = 0; cc < p.block_n; cc += 64) {
                 if (n0 + cc >= p.N) break;  // group-uniform
                 // the previous slab must have been read out by the TMA before it is overwritten.  Without a residual slab
@@ -866,7 +874,7 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
     // Full 128-pixel tiles of whole image rows, an even number of them per image.
     const bool pair_ok = halo && rows_per_tile > 0 && tile_m == kBlockM && (H / box_h) % 2 == 0 && p.block_n <= 128 && p.n_tiles == 1 &&
                          (2 * tile_m + 2 * W) / W <= 256 && getenv("GGML_B200_CONV_NO_PAIR") == nullptr;
-    const bool big_grid = (p.M / tile_m) * p.n_tiles > 2 * runtime().sm_count;
+    const bool big_grid = (p.M / tile_m) * p.n_tiles > runtime().sm_count;  // up to 148 tiles the plain halo scheme gives every tile its own SM
     const bool halo_ok = (p.M / tile_m) * p.n_tiles <= runtime().sm_count || (pair_ok && big_grid) || getenv("GGML_B200_CONV_HALO") != nullptr;
     if (halo && halo_ok && p.n_tiles * p.block_n <= n_pad) {
         p.pair = pair_ok && (big_grid || getenv("GGML_B200_CONV_PAIR") != nullptr) ? 1 : 0;
@@ -934,7 +942,8 @@ static void gemm_launch_variant(const GemmLaunch & L, cudaStream_t st) {
         B200_CHECK(cudaFuncSetAttribute(k_gemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    launch_pdl(k_gemm_tcgen05<EPI>, L.grid, dim3(kThreads), L.smem_bytes, st, L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
+    launch_pdl(k_gemm_tcgen05<EPI>, L.grid, dim3(L.p.conv == 2 && L.p.pair ? kThreads : kThreads - 32), L.smem_bytes, st,  // the 11th warp only exists in pair mode
+               L.map_a0, L.map_a1, L.map_b, L.map_o16, L.map_o32, L.map_r32, L.p);
 }
 
 #ifdef GGML_B200_GEMM_PROFILE

@@ -135,6 +135,24 @@ __device__ __forceinline__ void umma_f16_ws(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with the descriptors split into their 32-bit halves: the upper half of a K-major swizzled descriptor is a constant and the
+// lower half (start address >> 4 | 1 << 16) only ever moves by small amounts that cannot carry, so the issue loop does 32-bit uniform
+// adds instead of 64-bit add-with-carry pairs per operand and MMA (the uniform datapath is the issue loop's bottleneck).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ constexpr uint32_t smem_desc_hi(uint32_t row_bytes) {
+    return ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u)) << 29);
+}
+__device__ __forceinline__ void umma_f16_ws_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_ws(uint32_t bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"

@@ -23,5 +23,4 @@ for s in range(4):
     if not g[3]:
         continue
     c = g[3]
-    print(f"{names[s]:14s} CTAs*launches {c}: producer total {g[2]/c:9.0f} clk, waits A-empty {g[0]/c:9.0f}  B-empty {g[1]/c:9.0f} | "
-          f"MMA total {g[7]/c:9.0f}, waits tmem-empty {g[4]/c:9.0f}  A-full {g[5]/c:9.0f}  B-full {g[6]/c:9.0f}")
+    print(f"{names[s]:13s} MMA role {g[7]/c:8.0f} clk (waits: tmem {g[4]/c:6.0f} A {g[5]/c:6.0f} B {g[6]/c:6.0f}) | producer {g[2]/c:8.0f} (waits: A-empty {g[0]/c:6.0f} B-empty {g[1]/c:6.0f})")

@@ -12,3 +12,8 @@ for ctas in (1, 2):
             tot = L.ggml_b200_debug_mma_rate(n, 2048, ctas, ce, ctypes.byref(iss))
             ideal = 128 * n * 16 * 2 / 8192.0
             print(f"ctas/SM={ctas} N={n:3d} {'thread-0 issue (divergent)' if ce == 0 else 'warp-uniform elect issue':>28}: {iss.value:7.1f} cycles/MMA to issue, {tot:7.1f} incl. completion (math alone {ideal:5.1f})", flush=True)
+for n in (96, 128):
+    for ce in (-1, -4, -8, -12, -24):
+        iss = ctypes.c_float(0)
+        tot = L.ggml_b200_debug_mma_rate(n, 2304, 1, ce, ctypes.byref(iss))
+        print(f"N={n:3d} uniform issue, {'no commits' if ce == -1 else f'async commit every {-ce} MMAs, 2 accumulators'}: {iss.value:7.1f} cycles/MMA to issue, {tot:7.1f} incl. completion", flush=True)
