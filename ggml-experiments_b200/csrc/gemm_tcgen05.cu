@@ -47,9 +47,19 @@ __device__ __forceinline__ uint32_t make_idesc(int block_n) {
 // ---------------------------------------------------------------------------------------------------------
 // EPI: compile-time epilogue variant (bit mask, kEpi* below) so the per-element loops carry no run-time feature tests;
 // EPI = -1 is the generic kernel that reads the flags from the parameters.
+// Position in a ring of n slots -- slot index and parity of the current pass -- advanced without the integer divisions that
+// `it % n`, `(it / n) & 1` cost on the uniform datapath (a run-time divisor is a ~30-instruction sequence, once per k-block)
+struct RingPos {
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ void advance(uint32_t n) {
+        if (++s == n) { s = 0; ph ^= 1u; }
+    }
+};
+
 #ifdef GGML_B200_GEMM_PROFILE
 // clock64 phase profile of the halo-mode conv (build with GGML_B200_GEMM_PROFILE=1): cycles each role spends waiting on each barrier
 __device__ unsigned long long g_gemm_prof[64];
+__device__ unsigned long long g_gemm_prof1[16];  // per-tap conv at W == 8: [0] producer waits on empty, [1] producer total, [2] CTAs, [3] MMA waits on full, [4] MMA waits tmem, [5] MMA total, [6] epilogue wait on tmem_full (warp 2), [7] epilogue total
 __device__ int g_gemm_noload;  // probe: the halo producer arrives on the full barriers without loading anything (pure MMA-loop timing)
 #define PROF_WAIT(BAR, PAR, ACC)                 \
     do {                                         \
@@ -173,11 +183,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const int      cpr   = p.kb_elems >> 3;              // 16-byte chunks per row (2 or 4)
         const int      chunks = kBlockM * cpr;
         const uint32_t row_bytes = (uint32_t)p.kb_elems * 2;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, it++) {
+        RingPos rp;
+        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, rp.advance((uint32_t)p.stages)) {
             const int      m0 = tile * tile_m;
-            const int      s  = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1u;
+            const int      s  = (int)rp.s;
+            const uint32_t ph = rp.ph;
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
             const uint32_t fb = smem_u32(&full_bar[s]);
             const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
@@ -203,7 +213,8 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         // ===================== producer, halo mode: per (64-channel block, kw) ONE activation box with a one-row halo above and
         // below -- the three kh taps are start-address offsets of W rows into it -- and per tap one pre-tiled weight block by a 1-D
         // bulk copy.  A third of the activation boxes (and TMA box rows) of the per-tap scheme, no tensor map for the weights. =====
-        uint32_t ia = 0, ib = 0;
+        RingPos ra, rb;
+        const uint32_t n_sa = (uint32_t)p.stages, n_sb = (uint32_t)p.b_stages;
         long long w_aempty = 0, w_bempty = 0;
         const long long t_role0 = clock64();
         const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
@@ -216,9 +227,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             const int img = m0 / hw, y0 = p.rows_per_tile ? (m0 % hw) / p.W : 0;
             for (int cb = 0; cb < cblk_tot; cb++) {
                 const int src = cb >= p.cblk0, cbl = src ? cb - p.cblk0 : cb;
-                for (int kw = 0; kw < 3; kw++, ia++) {
-                    const uint32_t sa = ia % (uint32_t)p.stages;
-                    PROF_WAIT(smem_u32(&empty_bar[sa]), ((ia / (uint32_t)p.stages) & 1u) ^ 1u, w_aempty);
+                for (int kw = 0; kw < 3; kw++, ra.advance(n_sa)) {
+                    const uint32_t sa = ra.s;
+                    PROF_WAIT(smem_u32(&empty_bar[sa]), ra.ph ^ 1u, w_aempty);
                     const uint32_t dst = smem_u32(ring + (size_t)sa * p.a_slot_bytes);
 #ifdef GGML_B200_GEMM_PROFILE
                     if (g_gemm_noload & 1) { if (lane == 0) mbar_arrive(smem_u32(&full_bar[sa])); } else
@@ -228,9 +239,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     if (src) tma_load_4d_ws(dst, &map_a1, cbl * kBlockK, kw - 1, y0 - 1, img, smem_u32(&full_bar[sa]));
                     else tma_load_4d_ws(dst, &map_a0, cbl * kBlockK, kw - 1, y0 - 1, img, smem_u32(&full_bar[sa]));
                     }
-                    for (int kh = 0; kh < 3; kh++, ib++) {
-                        const uint32_t sb = ib % (uint32_t)p.b_stages;
-                        PROF_WAIT(smem_u32(&bempty_bar[sb]), ((ib / (uint32_t)p.b_stages) & 1u) ^ 1u, w_bempty);
+                    for (int kh = 0; kh < 3; kh++, rb.advance(n_sb)) {
+                        const uint32_t sb = rb.s;
+                        PROF_WAIT(smem_u32(&bempty_bar[sb]), rb.ph ^ 1u, w_bempty);
                         const uint8_t * wsrc = p.w_halo + ((size_t)((cb * 3 + kw) * 3 + kh) * p.n_pad + (size_t)n0) * 128u;
 #ifdef GGML_B200_GEMM_PROFILE
                         if (g_gemm_noload & 2) { if (lane == 0) mbar_arrive(smem_u32(&bfull_bar[sb])); } else
@@ -256,7 +267,10 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
     } else if (warp == 0) {
         // ===================== TMA producer (whole warp, elected lane issues) =====================
         {
-            uint32_t it = 0;  // k-block counter across all tiles of this CTA
+            RingPos rp;  // k-block position across all tiles of this CTA
+            const uint32_t n_st = (uint32_t)p.stages;
+            long long w_empty = 0;
+            const long long t_role0 = clock64();
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
                 const int m0 = tile * tile_m;
                 int img = 0, y0 = 0;
@@ -265,10 +279,11 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                     img          = m0 / hw;
                     y0           = p.rows_per_tile ? (m0 % hw) / p.W : 0;
                 }
-                for (int kb = 0; kb < p.num_kb; kb++, it++) {
-                    const int      s  = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1u;
-                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                int r = 0, kw = 0, kh = 0;  // conv: k-block = (channel block r, kw, kh), kh fastest
+                for (int kb = 0; kb < p.num_kb; kb++, rp.advance(n_st)) {
+                    const int      s  = (int)rp.s;
+                    const uint32_t ph = rp.ph;
+                    PROF_WAIT(smem_u32(&empty_bar[s]), ph ^ 1u, w_empty);
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
@@ -280,16 +295,26 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         mbar_expect_tx_ws(fb, (uint32_t)(p.a_tx_bytes + b_bytes));  // the activation box may be shorter than 128 rows
                         // K order = (channel block, kw, kh): the same accumulation order as the halo scheme, so that a tile gives the same
                         // bits whichever of the two schemes (chosen by grid size) computes it
-                        const int r = kb / 9, t9 = kb % 9;
                         const int src = r >= p.cblk0;
                         const int cb  = src ? r - p.cblk0 : r;
-                        const int kw = t9 / 3, kh = t9 % 3, tap = kh * 3 + kw;
+                        const int tap = kh * 3 + kw;
                         if (src) tma_load_4d_ws(sa, &map_a1, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
                         else tma_load_4d_ws(sa, &map_a0, cb * kBlockK, kw - 1, y0 + kh - 1, img, fb);
                         tma_load_3d_ws(sb, &map_b, (src ? p.C0 : 0) + cb * kBlockK, tap, n0, fb);
+                        if (++kh == 3) {
+                            kh = 0;
+                            if (++kw == 3) { kw = 0; r++; }
+                        }
                     }
                 }
             }
+#ifdef GGML_B200_GEMM_PROFILE
+            if (lane == 0 && p.conv == 1 && p.W == 8) {
+                atomicAdd(g_gemm_prof1 + 0, (unsigned long long)w_empty); atomicAdd(g_gemm_prof1 + 1, (unsigned long long)(clock64() - t_role0)); atomicAdd(g_gemm_prof1 + 2, 1ull);
+            }
+#else
+            (void)w_empty; (void)t_role0;
+#endif
         }
         __syncwarp();
     } else if ((warp == 1 || (warp == 10 && n_issuers == 2)) && p.conv == 2) {
@@ -297,13 +322,16 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         const uint32_t idesc = make_idesc(p.block_n);
         const uint8_t * ringB = ring + (size_t)p.stages * p.a_slot_bytes;
         const uint32_t wb_bytes = (uint32_t)p.block_n * 128u;
-        uint32_t ia = 0, ib = 0, t = 0;
+        RingPos ra, rb;
+        const uint32_t n_sa = (uint32_t)p.stages, n_sb = (uint32_t)p.b_stages;
+        const uint32_t acc_mask = (uint32_t)p.acc_stages - 1u, acc_shift = p.acc_stages == 4 ? 2u : 1u;  // 2 or 4 accumulators
+        uint32_t t = 0;
         long long w_tmem = 0, w_afull = 0, w_bfull = 0;
         const long long t_role0 = clock64();
         const int tpb = p.pair ? 2 : 1;  // M tiles per activation box: each weight block feeds tpb accumulators
         const int h   = warp == 1 ? 0 : 1;  // the half of the box this issuer owns
         for (int tile = blockIdx.x * tpb; tile < num_m_tiles; tile += gridDim.x * tpb, t += (uint32_t)tpb) {
-            const uint32_t acc = (t + (uint32_t)h) % (uint32_t)p.acc_stages, aph = ((t + (uint32_t)h) / (uint32_t)p.acc_stages) & 1u;
+            const uint32_t acc = (t + (uint32_t)h) & acc_mask, aph = ((t + (uint32_t)h) >> acc_shift) & 1u;
             PROF_WAIT(smem_u32(&tmem_empty[acc]), aph ^ 1u, w_tmem);
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
             tc_fence_after();
@@ -312,14 +340,14 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 const int src = cb >= p.cblk0;
                 const int rem = src ? p.C1 - (cb - p.cblk0) * kBlockK : p.C0 - cb * kBlockK;
                 const int ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
-                for (int kw = 0; kw < 3; kw++, ia++) {
-                    const uint32_t sa = ia % (uint32_t)p.stages;
-                    PROF_WAIT(smem_u32(&full_bar[sa]), (ia / (uint32_t)p.stages) & 1u, w_afull);
+                for (int kw = 0; kw < 3; kw++, ra.advance(n_sa)) {
+                    const uint32_t sa = ra.s;
+                    PROF_WAIT(smem_u32(&full_bar[sa]), ra.ph, w_afull);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(ring + (size_t)sa * p.a_slot_bytes);
-                    for (int kh = 0; kh < 3; kh++, ib++) {
-                        const uint32_t sb = ib % (uint32_t)p.b_stages;
-                        PROF_WAIT(smem_u32(&bfull_bar[sb]), (ib / (uint32_t)p.b_stages) & 1u, w_bfull);
+                    for (int kh = 0; kh < 3; kh++, rb.advance(n_sb)) {
+                        const uint32_t sb = rb.s;
+                        PROF_WAIT(smem_u32(&bfull_bar[sb]), rb.ph, w_bfull);
                         tc_fence_after();
                         const uint32_t b_lo = smem_desc_lo(smem_u32(ringB + (size_t)sb * wb_bytes));
                         // tap (kh, kw) of M tile h: the box rows shifted down by kh image rows (+ one tile) = a multiple of the 1 KiB swizzle atom
@@ -349,17 +377,23 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
         {
             const uint32_t idesc = make_idesc(p.block_n);
             const uint32_t desc_hi = p.kb_elems == 64 ? smem_desc_hi(128) : (p.kb_elems == 32 ? smem_desc_hi(64) : smem_desc_hi(32));
-            uint32_t it = 0, t = 0;
+            RingPos rp;
+            const uint32_t n_st = (uint32_t)p.stages;
+            const uint32_t acc_mask = (uint32_t)p.acc_stages - 1u, acc_shift = p.acc_stages == 4 ? 2u : 1u;  // 2 or 4 accumulators
+            uint32_t t = 0;
+            long long w_full = 0, w_tmem = 0;
+            const long long t_role0 = clock64();
             if (p.b_resident && (int)blockIdx.x < num_m_tiles) mbar_wait(smem_u32(bres_full), 0);
             for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, t++) {
-                const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;
-                mbar_wait(smem_u32(&tmem_empty[acc]), aph ^ 1u);  // epilogue has drained this accumulator
+                const uint32_t acc = t & acc_mask, aph = (t >> acc_shift) & 1u;
+                PROF_WAIT(smem_u32(&tmem_empty[acc]), aph ^ 1u, w_tmem);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
-                for (int kb = 0; kb < p.num_kb; kb++, it++) {
-                    const int      s  = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1u;
-                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                int r = 0, t9 = 0;  // conv: channel block of this k-block (9 taps each)
+                for (int kb = 0; kb < p.num_kb; kb++, rp.advance(n_st)) {
+                    const int      s  = (int)rp.s;
+                    const uint32_t ph = rp.ph;
+                    PROF_WAIT(smem_u32(&full_bar[s]), ph, w_full);
                     if (p.a_cp_async) fence_proxy_async();  // cp.async wrote through the generic proxy
                     tc_fence_after();
                     const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
@@ -369,9 +403,9 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                         rem = p.K - kb * p.kb_elems;
                         if (rem > p.kb_elems) rem = p.kb_elems;
                     } else {
-                        const int r   = kb / 9;
                         const int src = r >= p.cblk0;
                         rem           = (src ? p.C1 - (r - p.cblk0) * kBlockK : p.C0 - r * kBlockK);
+                        if (++t9 == 9) { t9 = 0; r++; }
                     }
                     const int      ksteps = rem >= kBlockK ? 4 : (rem + 15) / 16;
                     const uint32_t a_lo = smem_desc_lo(sa), b_lo = smem_desc_lo(sb);
@@ -383,6 +417,13 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
                 }
                 umma_commit_ws(smem_u32(&tmem_full[acc]));  // accumulator complete
             }
+#ifdef GGML_B200_GEMM_PROFILE
+            if (lane == 0 && p.conv == 1 && p.W == 8) {
+                atomicAdd(g_gemm_prof1 + 3, (unsigned long long)w_full); atomicAdd(g_gemm_prof1 + 4, (unsigned long long)w_tmem); atomicAdd(g_gemm_prof1 + 5, (unsigned long long)(clock64() - t_role0));
+            }
+#else
+            (void)w_full; (void)w_tmem; (void)t_role0;
+#endif
         }
         __syncwarp();
     } else if (warp < 10) {
@@ -415,7 +456,7 @@ __global__ void __launch_bounds__(kThreads) k_gemm_tcgen05(const __grid_constant
             if ((t & 1u) != group) continue;
             const int      m0  = tile * tile_m;
             const int      m   = m0 + row;
-            const uint32_t acc = t % (uint32_t)p.acc_stages, aph = (t / (uint32_t)p.acc_stages) & 1u;  // (t & 1) == group
+            const uint32_t acc = t & ((uint32_t)p.acc_stages - 1u), aph = (t >> (p.acc_stages == 4 ? 2 : 1)) & 1u;  // 2 or 4 accumulators; (t & 1) == group
             // folded LayerNorm: this row's mean and 1/std from the producer's (sum, sum of squares)
             float ln_r = 1.f, ln_mr = 0.f, st_sum = 0.f, st_sq = 0.f;
             if (f_ln && m < p.M) {
@@ -891,7 +932,7 @@ bool conv3x3_prepare(GemmLaunch & L, const __half * x0, int C0, const __half * x
         const int wb_bytes = p.block_n * 128;
         const int staging  = 2 * ((ep.out16 ? kBlockM * 128 : 0) + (ep.out32 ? 2 * kBlockM * 128 : 0));
         const int budget   = 216 * 1024 - 1024 - kCtrlBytes - staging;
-        int sa = 3, sb = (budget - sa * p.a_slot_bytes) / wb_bytes;
+        int sa = 3, sb = (budget - sa * p.a_slot_bytes) / wb_bytes;  // (2 activation slots + a deeper weight ring: measured equal)
         if (sb > kMaxStage) sb = kMaxStage;
         if (sb > 6) {  // room to spare: a fourth activation slot
             const int sb4 = (budget - 4 * p.a_slot_bytes) / wb_bytes;
@@ -949,6 +990,12 @@ static void gemm_launch_variant(const GemmLaunch & L, cudaStream_t st) {
 #ifdef GGML_B200_GEMM_PROFILE
 extern "C" void ggml_b200_debug_gemm_prof(unsigned long long * out64, int reset) {
     if (out64) B200_CHECK(cudaMemcpyFromSymbol(out64, g_gemm_prof, sizeof(unsigned long long) * 64));
+    if (out64 && reset == 0) {  // second block: the per-tap counters
+        unsigned long long z[16];
+        B200_CHECK(cudaMemcpyFromSymbol(z, g_gemm_prof1, sizeof z));
+        fprintf(stderr, "per-tap conv at 8x8: CTAs*launches %llu: producer total %.0f clk (waits empty %.0f) | MMA total %.0f (waits full %.0f, tmem %.0f)\n", z[2],
+                (double)z[1] / z[2], (double)z[0] / z[2], (double)z[5] / z[2], (double)z[3] / z[2], (double)z[4] / z[2]);
+    }
     if (reset >= 16) {
         const int v = reset - 16;
         B200_CHECK(cudaMemcpyToSymbol(g_gemm_noload, &v, sizeof v));
@@ -956,6 +1003,7 @@ extern "C" void ggml_b200_debug_gemm_prof(unsigned long long * out64, int reset)
     if (reset) {
         unsigned long long z[64] = {0};
         B200_CHECK(cudaMemcpyToSymbol(g_gemm_prof, z, sizeof z));
+        B200_CHECK(cudaMemcpyToSymbol(g_gemm_prof1, z, sizeof(unsigned long long) * 16));
     }
 }
 #endif
