@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
     const uint32_t sp = sv + 2 * 8192;                // P   : 128 x 128 B (64 keys)
     const uint32_t q_full = smem_u32(&bars[0]), q_free = smem_u32(&bars[1]), s_full = smem_u32(&bars[2]), s_free = smem_u32(&bars[3]);
     const uint32_t p_full = smem_u32(&bars[4]), pv_full = smem_u32(&bars[5]);
-    const uint32_t k_full = smem_u32(&bars[6]), k_free = smem_u32(&bars[9]), v_full = smem_u32(&bars[12]), v_free = smem_u32(&bars[14]);
+    const uint32_t k_full = smem_u32(&bars[6]), v_full = smem_u32(&bars[12]), v_free = smem_u32(&bars[14]);  // (bars[9..11], once "K buffer free", are unused)
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;  // shuffle: provably warp-uniform -> role loops on the uniform datapath
     const int nkb   = p.L / kKB;
@@ -166,19 +166,29 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
         // ===================== control warp: TMA + MMA issue (whole warp, elected lane issues: ptx_sm100.cuh "_ws") =====================
         if (nblk > 0) {
             auto map_of = [&](int pos) { return pos == 0 ? &map00 : (pos == 1 ? &map01 : (pos == 2 ? &map10 : &map11)); };
+            // Every stream of this warp (K loads, V loads, S issue, P.V issue) walks the CTA's key blocks g = 0, 1, 2, ... in order: a cursor
+            // keeps (item, block inside the item) and decodes the item once -- the run-time divisions of g / nkb, g % nkb and decode() per
+            // call were a third of the warp's instructions (they run on the uniform datapath, which has no divider)
+            struct Cursor { int k = -1, j = 0, n = 0, pos = 0, h = 0, qb = 0; };
+            auto step = [&](Cursor & c) {  // position the cursor on the next block
+                if (c.k < 0 || ++c.j == nkb) {
+                    c.j = 0;
+                    decode(++c.k, c.n, c.pos, c.h, c.qb);
+                }
+            };
+            Cursor ck, cv, cs;
+            int    jpv = 0;  // P.V: block inside the item
             auto load_k = [&](int g) {  // keys of block g of this CTA -> K buffer g % 3
-                int n, pos, h, qb;
-                decode(g / nkb, n, pos, h, qb);
+                step(ck);
                 const uint32_t b = (uint32_t)(g % 3), bar = k_full + 8u * b;
                 mbar_expect_tx_ws(bar, 8192u);
-                tma_load_5d_ws(sk + b * 8192u, map_of(pos), 0, 1 * p.heads + h, 0, (g % nkb) * p.rows_k, n, bar);
+                tma_load_5d_ws(sk + b * 8192u, map_of(ck.pos), 0, 1 * p.heads + ck.h, 0, ck.j * p.rows_k, ck.n, bar);
             };
             auto load_v = [&](int g) {  // values of block g -> V buffer g & 1
-                int n, pos, h, qb;
-                decode(g / nkb, n, pos, h, qb);
+                step(cv);
                 const uint32_t b = (uint32_t)(g & 1), bar = v_full + 8u * b;
                 mbar_expect_tx_ws(bar, 8192u);
-                tma_load_5d_ws(sv + b * 8192u, map_of(pos), 0, 2 * p.heads + h, 0, (g % nkb) * p.rows_k, n, bar);
+                tma_load_5d_ws(sv + b * 8192u, map_of(cv.pos), 0, 2 * p.heads + cv.h, 0, cv.j * p.rows_k, cv.n, bar);
             };
             auto load_q = [&](int k) {
                 int n, pos, h, qb;
@@ -188,17 +198,17 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
                 tma_load_5d_ws(sq + 8192u, map_of(pos), 0, h, 0, (qb * 2 + 1) * p.rows_q, n, q_full);
             };
             const uint32_t idesc_s = attn_idesc(kKB, 0), idesc_pv = attn_idesc(DP, 1);
-            const uint64_t qdesc = make_smem_desc(sq, 128), pdesc = make_smem_desc(sp, 128);
+            const uint32_t q_lo = smem_desc_lo(sq), p_lo = smem_desc_lo(sp);  // descriptors as 32-bit halves (ptx_sm100.cuh)
             auto issue_s = [&](int g) {  // S of key block g; the first block of an item waits for the item's Q, the last one releases it
-                const int k = g / nkb, j = g % nkb;
+                step(cs);
+                const int k = cs.k, j = cs.j;
                 if (j == 0) mbar_wait(q_full, (uint32_t)(k & 1));
                 mbar_wait(k_full + 8u * (uint32_t)(g % 3), (uint32_t)((g / 3) & 1));
                 tc_fence_after();
-                const uint64_t kdesc = make_smem_desc(sk + (uint32_t)(g % 3) * 8192u, 128);
+                const uint32_t k_lo = smem_desc_lo(sk + (uint32_t)(g % 3) * 8192u);
 #pragma unroll
-                for (int ks = 0; ks < DP / 16; ks++) umma_f16_ws(tmem_s, qdesc + (uint64_t)(2 * ks), kdesc + (uint64_t)(2 * ks), idesc_s, ks != 0);
-                umma_commit_ws(s_full);
-                umma_commit_ws(k_free + 8u * (uint32_t)(g % 3));
+                for (int ks = 0; ks < DP / 16; ks++) umma_f16_ws_split(tmem_s, q_lo + (uint32_t)(2 * ks), k_lo + (uint32_t)(2 * ks), smem_desc_hi(128), idesc_s, ks != 0);
+                umma_commit_ws(s_full);  // (no separate "K buffer free" commit: see the K reload below)
                 if (j == nkb - 1) {
                     umma_commit_ws(q_free);  // every S of this item has been issued: Q may be replaced once they complete
                     if (k + 1 < nit) {
@@ -220,18 +230,19 @@ __global__ void __launch_bounds__(160, 3) k_attention_tc(const __grid_constant__
                     if (g >= 1) mbar_wait(v_free + 8u * (uint32_t)((g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));
                     load_v(g + 1);
                 }
-                if (g + 3 < nblk) {  // K_{g+3} -> the buffer S_g has read (S_g is complete: the softmax warps have consumed it)
-                    mbar_wait(k_free + 8u * (uint32_t)(g % 3), (uint32_t)((g / 3) & 1));
-                    load_k(g + 3);
-                }
+                // K_{g+3} -> the buffer S_g has read.  g + 3 < nblk implies the s_free wait above: the softmax warps have loaded S_g, so the
+                // MMA that produced it -- the only reader of that K buffer -- is complete; no barrier of its own (a tcgen05.commit costs
+                // ~100 cycles of issue time on this warp, which is on the critical path together with the softmax warps)
+                if (g + 3 < nblk) load_k(g + 3);
                 mbar_wait(p_full, (uint32_t)(g & 1));  // P_g is in shared memory (and any rescale of O has been stored)
                 mbar_wait(v_full + 8u * (uint32_t)(g & 1), (uint32_t)((g >> 1) & 1));
                 tc_fence_after();
                 // V_g as the MN-major B operand: 64 token rows of 128 B, 8-row groups 1 KiB apart; 16 keys per k-step = +2 KiB
-                const uint64_t vdesc = make_smem_desc(sv + (uint32_t)(g & 1) * 8192u, 128);
-                const int j = g % nkb;
+                const uint32_t v_lo = smem_desc_lo(sv + (uint32_t)(g & 1) * 8192u);
+                const int j = jpv;
+                if (++jpv == nkb) jpv = 0;
 #pragma unroll
-                for (int ks = 0; ks < kKB / 16; ks++) umma_f16_ws(tmem_o, pdesc + (uint64_t)(2 * ks), vdesc + (uint64_t)(128 * ks), idesc_pv, (j | ks) != 0);
+                for (int ks = 0; ks < kKB / 16; ks++) umma_f16_ws_split(tmem_o, p_lo + (uint32_t)(2 * ks), v_lo + (uint32_t)(128 * ks), smem_desc_hi(128), idesc_pv, (j | ks) != 0);
                 umma_commit_ws(pv_full);
                 umma_commit_ws(v_free + 8u * (uint32_t)(g & 1));
             }
