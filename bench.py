@@ -442,7 +442,7 @@ def main():
     u8_sync_s = max_over_ranks(time.perf_counter() - t0)
     e2e_u8 = {"value": args.batch * world * args.steps / u8_s, "unit": "images/s", "h2d_bytes_per_step": int(img_u8.nbytes),
               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * u8_s / args.steps, "synchronous_call_ms": 1e3 * u8_sync_s / args.steps,
-              "api": "mvit_slot_submit_u8 (device-side sam_image_preprocess), 2 slots in flight, logits gathered into one shared host buffer"}
+              "api": "mvit_slot_submit_u8 (device-side sam_image_preprocess: the stem reads the quantised u8 images; 256x256 sources need no resize pass), 2 slots in flight, logits gathered into one shared host buffer"}
 
     # ---- the gathered logits of all ranks == one GPU running the whole batch, bit for bit ---------------------
     barrier()
