@@ -162,7 +162,8 @@ def preprocess_numpy(img, H, W_):
 
 
 @pytest.mark.parametrize("sh,sw,H,W_", [(256, 256, 256, 256), (300, 400, 256, 256), (400, 300, 256, 256), (100, 80, 256, 256),
-                                        (1080, 1920, 256, 256), (7, 5, 64, 64), (512, 512, 256, 256), (300, 500, 128, 256)])
+                                        (1080, 1920, 256, 256), (7, 5, 64, 64), (512, 512, 256, 256), (300, 500, 128, 256),
+                                        (128, 256, 128, 256), (64, 64, 64, 64)])  # same size as the target: the identity the u8 stem route copies straight in
 def test_oracle_preprocess_u8_is_the_reference_arithmetic(oracle, sh, sw, H, W_):
     img = np.random.default_rng(sh * 7 + sw).integers(0, 256, (2, sh, sw, 3), dtype=np.uint8)
     got = oracle.preprocess_u8(img, H, W_)
